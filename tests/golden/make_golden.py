@@ -1,0 +1,403 @@
+"""Generate golden vectors by running the UNMODIFIED reference (PKU-MARL/HARL) on CPU.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference's own functions are imported from /root/reference and executed on seeded
+synthetic inputs; inputs and outputs are written to tests/golden/*.npz (a few hundred KB in
+total).  Nothing from the reference is copied into the repo -- only tensors it computed.
+The GPU box has no /root/reference: tests read the committed .npz files only.
+
+Shims (the same two SURVEY.md section 8(c) lists): a stub ``tensorboardX`` module (imported
+by harl/utils/configs_tools.py:86) and fake ``Box`` / ``Discrete`` space classes (the
+reference dispatches on ``__class__.__name__``).
+"""
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("HARL_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+tbx = types.ModuleType("tensorboardX")
+tbx.SummaryWriter = object
+sys.modules.setdefault("tensorboardX", tbx)
+
+from harl.algorithms.actors.happo import HAPPO  # noqa: E402
+from harl.algorithms.critics.v_critic import VCritic  # noqa: E402
+from harl.common.buffers.on_policy_actor_buffer import OnPolicyActorBuffer  # noqa: E402
+from harl.common.buffers.on_policy_critic_buffer_ep import OnPolicyCriticBufferEP  # noqa: E402
+from harl.common.buffers.on_policy_critic_buffer_fp import OnPolicyCriticBufferFP  # noqa: E402
+from harl.common.valuenorm import ValueNorm  # noqa: E402
+from harl.models.policy_models.stochastic_policy import StochasticPolicy  # noqa: E402
+from harl.models.value_function_models.v_net import VNet  # noqa: E402
+from harl.runners.on_policy_base_runner import OnPolicyBaseRunner  # noqa: E402
+from harl.runners.on_policy_ha_runner import OnPolicyHARunner  # noqa: E402
+
+
+class Box:
+    def __init__(self, n):
+        self.shape = (n,)
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+        self.shape = ()
+
+
+VERSIONS = np.array([torch.__version__, np.__version__])
+
+
+def base_args(**over):
+    a = dict(
+        hidden_sizes=[32, 32], activation_func="relu", use_feature_normalization=True,
+        initialization_method="orthogonal_", gain=0.01, use_naive_recurrent_policy=False,
+        use_recurrent_policy=False, recurrent_n=1, data_chunk_length=4, lr=5e-4, critic_lr=5e-4,
+        opti_eps=1e-5, weight_decay=0, std_x_coef=1, std_y_coef=0.5,
+        ppo_epoch=3, critic_epoch=3, use_clipped_value_loss=True, clip_param=0.2,
+        actor_num_mini_batch=1, critic_num_mini_batch=1, entropy_coef=0.01, value_loss_coef=1,
+        use_max_grad_norm=True, max_grad_norm=10.0, use_gae=True, gamma=0.99, gae_lambda=0.95,
+        use_huber_loss=True, use_policy_active_masks=True, huber_delta=10.0,
+        action_aggregation="prod", share_param=False, fixed_order=True,
+        episode_length=8, n_rollout_threads=6, use_valuenorm=True, use_proper_time_limits=True,
+    )
+    a.update(over)
+    return a
+
+
+def sd_np(module, prefix):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def perturb(module, g, scale=0.1):
+    """Move every parameter off its init so LN affines / biases / log_std matter."""
+    with torch.no_grad():
+        for p in module.parameters():
+            p.add_(scale * torch.randn(p.shape, generator=g))
+
+
+def save(name, **arrs):
+    arrs["versions"] = VERSIONS
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+    print("wrote", name, sum(np.asarray(v).nbytes for v in arrs.values()), "bytes")
+
+
+# ------------------------------------------------------------------ random rollout data
+def fill_buffers(rng, args, A, od, sd, act_space, state_type, with_deaths=True):
+    """Drive the reference runner's own insert() with random env outputs; return buffers."""
+    T, N = args["episode_length"], args["n_rollout_threads"]
+    h, R = args["hidden_sizes"][-1], args["recurrent_n"]
+    disc = act_space.__class__.__name__ == "Discrete"
+    abufs = [OnPolicyActorBuffer(args, Box(od), act_space) for _ in range(A)]
+    cbuf = (OnPolicyCriticBufferEP(args, Box(sd)) if state_type == "EP"
+            else OnPolicyCriticBufferFP(args, Box(sd), A))
+    fake = SimpleNamespace(num_agents=A, recurrent_n=R, rnn_hidden_size=h, state_type=state_type,
+                           algo_args={"train": {"n_rollout_threads": N}},
+                           actor_buffer=abufs, critic_buffer=cbuf)
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+
+    def avail_sample():
+        av = (rng.random((N, A, act_space.n)) < 0.7).astype(np.float32)
+        av[..., 1] = 1.0
+        return av
+
+    for a in range(A):
+        abufs[a].obs[0] = f(N, od)
+        if disc:
+            abufs[a].available_actions[0] = avail_sample()[:, a]
+    cbuf.share_obs[0] = f(N, sd) if state_type == "EP" else f(N, A, sd)
+    dead = np.zeros((N, A), bool)
+    log = dict(dones=[], bad=[])
+    for t in range(T):
+        if disc:
+            actions = rng.integers(0, act_space.n, (N, A, 1)).astype(np.float32)
+            ad = 1
+        else:
+            ad = act_space.shape[0]
+            actions = f(N, A, ad)
+        logp = -np.abs(f(N, A, ad)) - 0.5
+        values = f(N, 1) if state_type == "EP" else f(N, A, 1)
+        rnn = f(N, A, R, h)
+        rnn_c = f(N, R, h) if state_type == "EP" else f(N, A, R, h)
+        rew = np.repeat(f(N, 1, 1), A, axis=1)
+        if with_deaths:
+            dead |= rng.random((N, A)) < 0.12
+        env_done = dead.all(1) | (rng.random(N) < 0.1)
+        dones = dead | env_done[:, None]
+        trunc = env_done & (rng.random(N) < 0.5)
+        infos = [[({"bad_transition": True} if trunc[n] else {}) for _ in range(A)] for n in range(N)]
+        data = (f(N, A, od), f(N, A, sd), rew, dones.copy(), infos,
+                avail_sample() if disc else np.array([None] * N), values, actions, logp, rnn, rnn_c)
+        OnPolicyBaseRunner.insert(fake, data)
+        log["dones"].append(dones.copy())
+        log["bad"].append(np.repeat(trunc[:, None], A, 1))
+        dead[env_done] = False
+    return abufs, cbuf, log
+
+
+def abuf_np(b, prefix):
+    d = {prefix + k: getattr(b, k).copy() for k in
+         ("obs", "rnn_states", "actions", "action_log_probs", "masks", "active_masks")}
+    if b.available_actions is not None:
+        d[prefix + "available_actions"] = b.available_actions.copy()
+    return d
+
+
+def cbuf_np(b, prefix="c."):
+    return {prefix + k: getattr(b, k).copy() for k in
+            ("share_obs", "rnn_states_critic", "value_preds", "returns", "rewards", "masks", "bad_masks")}
+
+
+# ------------------------------------------------------------------ cases
+def case_insert():
+    for st in ("EP", "FP"):
+        rng = np.random.default_rng(11)
+        args = base_args(hidden_sizes=[8])
+        ab, cb, log = fill_buffers(rng, args, 3, 5, 7, Discrete(4), st)
+        out = dict(dones=np.array(log["dones"]), bad=np.array(log["bad"]))
+        for a in range(3):
+            out.update({f"a{a}.masks": ab[a].masks, f"a{a}.active_masks": ab[a].active_masks,
+                        f"a{a}.rnn_states": ab[a].rnn_states})
+        out.update({"c.masks": cb.masks, "c.bad_masks": cb.bad_masks, "c.rnn_states_critic": cb.rnn_states_critic})
+        save(f"insert_{st}", **out)
+
+
+def case_gae():
+    for st in ("EP", "FP"):
+        for use_gae in (True, False):
+            for ptl in (True, False):
+                for use_vn in (True, False):
+                    rng = np.random.default_rng(5)
+                    args = base_args(use_gae=use_gae, use_proper_time_limits=ptl, hidden_sizes=[8],
+                                     episode_length=16, n_rollout_threads=5)
+                    ab, cb, _ = fill_buffers(rng, args, 3, 4, 6, Box(2), st)
+                    vn = None
+                    if use_vn:
+                        vn = ValueNorm(1)
+                        vn.update(rng.standard_normal((64, 1)).astype(np.float32) * 3 + 1)
+                        vn.update(rng.standard_normal((64, 1)).astype(np.float32) * 2 - 1)
+                    nv = rng.standard_normal(cb.value_preds[-1].shape).astype(np.float32)
+                    inp = cbuf_np(cb, "in.")
+                    cb.compute_returns(nv, vn)
+                    out = dict(inp, next_value=nv, returns=cb.returns, value_preds=cb.value_preds,
+                               gamma=args["gamma"], gae_lambda=args["gae_lambda"])
+                    if use_vn:
+                        out.update(vn_mean=vn.running_mean.numpy(), vn_mean_sq=vn.running_mean_sq.numpy(),
+                                   vn_debias=vn.debiasing_term.numpy(),
+                                   denorm_vp=vn.denormalize(cb.value_preds[:-1]))
+                        adv = cb.returns[:-1] - vn.denormalize(cb.value_preds[:-1])
+                    else:
+                        adv = cb.returns[:-1] - cb.value_preds[:-1]
+                    out["advantages"] = adv
+                    save(f"gae_{st}_gae{int(use_gae)}_ptl{int(ptl)}_vn{int(use_vn)}", **out)
+
+
+def case_valuenorm():
+    rng = np.random.default_rng(2)
+    vn = ValueNorm(1)
+    xs = [rng.standard_normal((50, 1)).astype(np.float32) * s + m for s, m in ((3, 1), (0.01, 0), (10, -4))]
+    st = []
+    q = rng.standard_normal((9, 1)).astype(np.float32)
+    for x in xs:
+        vn.update(x)
+        st.append([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()])
+    save("valuenorm", xs=np.array(xs), states=np.array(st, np.float32), q=q,
+         norm=vn.normalize(q).numpy(), denorm=vn.denormalize(q))
+
+
+def case_policy():
+    for tag, over, act_space in (
+        ("mlp_disc", {}, Discrete(5)),
+        ("mlp_box", dict(hidden_sizes=[32, 32, 32]), Box(3)),
+        ("gru_disc", dict(use_recurrent_policy=True, hidden_sizes=[16, 16]), Discrete(6)),
+        ("gru_box", dict(use_recurrent_policy=True, hidden_sizes=[16], recurrent_n=2), Box(2)),
+        ("mlp_disc_tanh", dict(activation_func="tanh", use_feature_normalization=False), Discrete(4)),
+    ):
+        torch.manual_seed(3)
+        g = torch.Generator().manual_seed(4)
+        rng = np.random.default_rng(6)
+        args = base_args(**over)
+        od, T, N = 7, 5, 4
+        h, R = args["hidden_sizes"][-1], args["recurrent_n"]
+        pol = StochasticPolicy(args, Box(od), act_space)
+        perturb(pol, g)
+        vnet = VNet(args, Box(od + 2))
+        perturb(vnet, g)
+        disc = act_space.__class__.__name__ == "Discrete"
+        f = lambda *s: rng.standard_normal(s).astype(np.float32)
+        B = T * N
+        obs, cobs = f(B, od), f(B, od + 2)
+        masks = (rng.random((B, 1)) > 0.2).astype(np.float32)
+        active = (rng.random((B, 1)) > 0.2).astype(np.float32)
+        if disc:
+            avail = (rng.random((B, act_space.n)) < 0.7).astype(np.float32)
+            avail[:, 1] = 1
+            acts = np.array([[rng.choice(np.flatnonzero(avail[i]))] for i in range(B)], np.float32)
+        else:
+            avail, acts = None, f(B, act_space.shape[0])
+        out = dict(obs=obs, cobs=cobs, masks=masks, active=active, actions=acts)
+        if disc:
+            out["avail"] = avail
+        # sequence mode (rows = T*N time-major, hxs [N,R,h]) and row mode (hxs [B,R,h])
+        for mode, hx in (("seq", f(N, R, h)), ("row", f(B, R, h))):
+            lp, ent, dist = pol.evaluate_actions(obs, hx, acts, masks, avail, active)
+            out[f"{mode}.hxs"] = hx
+            out[f"{mode}.logp"] = lp.detach().numpy()
+            out[f"{mode}.entropy"] = ent.detach().numpy()
+            if disc:
+                out[f"{mode}.logits"] = dist.logits.detach().numpy()
+            else:
+                out[f"{mode}.mean"] = dist.loc.detach().numpy()
+                out[f"{mode}.std"] = dist.scale.detach().numpy()
+            v, hc = vnet(cobs, hx, masks)
+            out[f"{mode}.values"] = v.detach().numpy()
+            out[f"{mode}.hxs_critic_out"] = hc.detach().numpy()
+        a_det, lp_det, h_det = pol(obs, out["row.hxs"], masks, avail, deterministic=True)
+        out.update(det_action=a_det.detach().numpy().astype(np.float32), det_logp=lp_det.detach().numpy(),
+                   det_hxs=h_det.detach().numpy())
+        out.update(sd_np(pol, "actor/"))
+        out.update(sd_np(vnet, "critic/"))
+        save(f"policy_{tag}", **out)
+
+
+class PermRecorder:
+    """Record (and later replay) every torch.randperm the reference draws."""
+
+    def __init__(self):
+        self.log = []
+        self._orig = torch.randperm
+
+    def __enter__(self):
+        def rec(n, *a, **k):
+            p = self._orig(n, *a, **k)
+            self.log.append(p.numpy().copy())
+            return p
+        torch.randperm = rec
+        return self
+
+    def __exit__(self, *a):
+        torch.randperm = self._orig
+
+
+def case_ha_train():
+    """Full OnPolicyHARunner.train() through the unmodified reference classes."""
+    for tag, over, act_space, st, A in (
+        ("mlp_disc_EP", {}, Discrete(5), "EP", 3),
+        ("mlp_box_EP", dict(hidden_sizes=[32, 32, 32], clip_param=0.05), Box(2), "EP", 2),
+        ("mlp_disc_mb2_EP", dict(actor_num_mini_batch=2, critic_num_mini_batch=2), Discrete(5), "EP", 2),
+        ("gru_disc_FP", dict(use_recurrent_policy=True, hidden_sizes=[16, 16], gamma=0.95), Discrete(6), "FP", 3),
+        ("gru_box_EP", dict(use_recurrent_policy=True, hidden_sizes=[16]), Box(2), "EP", 2),
+        ("naive_gru_disc_EP", dict(use_naive_recurrent_policy=True, hidden_sizes=[16]), Discrete(4), "EP", 2),
+    ):
+        torch.manual_seed(7)
+        g = torch.Generator().manual_seed(8)
+        rng = np.random.default_rng(9)
+        args = base_args(**over)
+        od, sd = 6, 9
+        ab, cb, _ = fill_buffers(rng, args, A, od, sd, act_space, st)
+        actors = [HAPPO(args, Box(od), act_space) for _ in range(A)]
+        critic = VCritic(args, Box(sd))
+        for a in actors:
+            perturb(a.actor, g)
+        perturb(critic.critic, g)
+        vn = ValueNorm(1)
+        vn.update(rng.standard_normal((64, 1)).astype(np.float32) * 2 + 0.5)
+        nv = rng.standard_normal(cb.value_preds[-1].shape).astype(np.float32)
+        cb.compute_returns(nv, vn)
+        out = {}
+        for a in range(A):
+            out.update(abuf_np(ab[a], f"a{a}."))
+            out.update(sd_np(actors[a].actor, f"actor{a}/"))
+        out.update(cbuf_np(cb))
+        out.update(sd_np(critic.critic, "critic/"))
+        out["vn_in"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+        fake = SimpleNamespace(algo_args={"train": args}, value_normalizer=vn, critic_buffer=cb, actor_buffer=ab,
+                               actor=actors, critic=critic, state_type=st, num_agents=A, fixed_order=True,
+                               action_aggregation=args["action_aggregation"])
+        for x in actors:
+            x.prep_training()
+        critic.prep_training()
+        with PermRecorder() as pr:
+            ainfos, cinfo = OnPolicyHARunner.train(fake)
+        out["n_perms"] = len(pr.log)
+        for i, p in enumerate(pr.log):
+            out[f"perm{i}"] = p
+        for a in range(A):
+            out.update(sd_np(actors[a].actor, f"out.actor{a}/"))
+            out[f"out.factor{a}"] = ab[a].factor
+            out[f"out.info{a}"] = np.array([float(ainfos[a][k]) for k in
+                                            ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio")], np.float64)
+        out.update(sd_np(critic.critic, "out.critic/"))
+        out["out.cinfo"] = np.array([float(cinfo["value_loss"]), float(cinfo["critic_grad_norm"])], np.float64)
+        out["out.vn"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+        out["cfg_keys"] = np.array(sorted(over.keys()))
+        out["cfg_vals"] = np.array([repr(over[k]) for k in sorted(over.keys())])
+        out["meta"] = np.array([tag, act_space.__class__.__name__, st, str(A), str(od), str(sd),
+                                str(act_space.n if hasattr(act_space, "n") else act_space.shape[0])])
+        save(f"ha_train_{tag}", **out)
+
+
+def case_single_update():
+    """One HAPPO.update and one VCritic.update: raw gradients before clipping."""
+    for tag, over, act_space in (("disc", {}, Discrete(5)), ("box", dict(hidden_sizes=[32, 32, 32]), Box(3))):
+        torch.manual_seed(21)
+        g = torch.Generator().manual_seed(22)
+        rng = np.random.default_rng(23)
+        args = base_args(ppo_epoch=1, critic_epoch=1, **over)
+        od, sd, A = 6, 9, 1
+        ab, cb, _ = fill_buffers(rng, args, A, od, sd, act_space, "EP")
+        actor = HAPPO(args, Box(od), act_space)
+        critic = VCritic(args, Box(sd))
+        perturb(actor.actor, g)
+        perturb(critic.critic, g)
+        vn = ValueNorm(1)
+        vn.update(rng.standard_normal((64, 1)).astype(np.float32))
+        cb.compute_returns(rng.standard_normal((args["n_rollout_threads"], 1)).astype(np.float32), vn)
+        T, N = args["episode_length"], args["n_rollout_threads"]
+        factor = (1 + 0.1 * rng.standard_normal((T, N, 1))).astype(np.float32)
+        adv = rng.standard_normal((T, N, 1)).astype(np.float32)
+        ab[0].update_factor(factor)
+        out = dict(abuf_np(ab[0], "a0."), **cbuf_np(cb), factor=factor, adv=adv)
+        out.update(sd_np(actor.actor, "actor0/"))
+        out.update(sd_np(critic.critic, "critic/"))
+        out["vn_in"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+        # identity permutation so the batch is the buffer in time-major order
+        orig = torch.randperm
+        torch.randperm = lambda n, *a, **k: torch.arange(n)
+        try:
+            sample = next(ab[0].feed_forward_generator_actor(adv, 1))
+            pl, ent, gn, imp = actor.update(sample)
+            for n_, p in actor.actor.named_parameters():
+                out["grad.actor0/" + n_] = p.grad.numpy().copy()  # post-clip grads
+            out["actor_scalars"] = np.array([pl.item(), ent.item(), float(gn), imp.mean().item()], np.float64)
+            csample = next(cb.feed_forward_generator_critic(1))
+            vl, cgn = critic.update(csample, vn)
+            for n_, p in critic.critic.named_parameters():
+                out["grad.critic/" + n_] = p.grad.numpy().copy()
+            out["critic_scalars"] = np.array([vl.item(), float(cgn)], np.float64)
+        finally:
+            torch.randperm = orig
+        out.update(sd_np(actor.actor, "out.actor0/"))
+        out.update(sd_np(critic.critic, "out.critic/"))
+        out["meta"] = np.array([tag, act_space.__class__.__name__, "EP", "1", str(od), str(sd),
+                                str(act_space.n if hasattr(act_space, "n") else act_space.shape[0])])
+        out["cfg_keys"] = np.array(sorted(list(over.keys()) + ["ppo_epoch", "critic_epoch"]))
+        over2 = dict(over, ppo_epoch=1, critic_epoch=1)
+        out["cfg_vals"] = np.array([repr(over2[k]) for k in sorted(over2.keys())])
+        save(f"single_update_{tag}", **out)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    case_insert()
+    case_gae()
+    case_valuenorm()
+    case_policy()
+    case_single_update()
+    case_ha_train()
