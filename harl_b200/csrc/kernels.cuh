@@ -1,0 +1,73 @@
+// Internal kernel-launcher interface shared by the translation units.
+#pragma once
+#include "common.cuh"
+
+namespace hb {
+
+enum { MODE_ACT = 0, MODE_EVAL = 1, MODE_GRAD = 2 };
+
+struct HeadArgs {
+  const float* feat;     // [rows, h]  trunk output (batch-row indexed)
+  int h, out;
+  const float* hw;       // [out][h]
+  const float* hbias;    // [out]
+  const float* log_std;  // [out] (Box)
+  float std_x, std_y;
+  int64_t rows;
+  const int32_t* index;  // batch row -> buffer row (nullable)
+  // act
+  int deterministic;
+  uint64_t seed, offset;
+  float* actions_out;    // [rows, ad]
+  float* logp_out;       // [rows, ad]
+  // evaluate / grad (buffer-row indexed)
+  const float* actions;
+  const float* avail;
+  const float* old_logp;
+  const float* adv;
+  const float* factor;
+  const float* active;
+  const float* logp_ref;
+  float* factor_inout;
+  int agg_prod;
+  // grad
+  float clip, entropy_coef;
+  int use_active, use_clip;
+  const double* norm3;
+  float* dfeat;          // [rows, h]
+  float* g_hw;           // [out][h]
+  float* g_hbias;        // [out]
+  float* g_log_std;      // [out]
+  double* scalars;       // += (loss_num, entropy_num, ratio_sum, rows)
+};
+
+struct ValueArgs {
+  const float* feat; int h;
+  const float* hw; const float* hbias;
+  int64_t rows; const int32_t* index;
+  float* values_out;            // forward mode
+  const float* value_preds; const float* returns;  // buffer-row indexed
+  const float* vn_state;        // nullable
+  float clip, huber_delta, coef;  // coef = value_loss_coef * inv_count
+  int use_huber, use_clipped;
+  float* dfeat; float* g_hw; float* g_hbias; double* scalars;  // scalars += (loss_sum, rows)
+};
+
+// launchers (gemm_simt.cu, rowwise.cu, optim.cu)
+int launch_linear_ln_fwd(int act, const float* X, int ldx, const float* WT, const float* bias, const float* lnw,
+                         const float* lnb, float* Z, float* Y, float* stats, int64_t M, int N, int Kred, cudaStream_t st);
+int launch_dx_ln_bwd(int act, const float* dZ, int N, const float* W, const float* Zp, const float* stats_p,
+                     const float* lnw_p, float* dZp, float* g_lnw_p, float* g_lnb_p, int64_t M, int Np, cudaStream_t st);
+int launch_dw_accum(const float* dZ, int N, const float* X, int ldx, int K, float* dW, float* db, int64_t M,
+                    cudaStream_t st);
+int launch_feat_norm(const float* obs, int in_dim, const int32_t* index, int64_t rows, int feature_norm, float* xout,
+                     int ldx, cudaStream_t st);
+int launch_ln_act_bwd(const float* dY, const float* Z, const float* stats, const float* lnw, float* dZ, float* g_lnw,
+                      float* g_lnb, int64_t rows, int N, int act, cudaStream_t st);
+int launch_featnorm_fold(const hb_net_desc* d, const float* params, float* grad, cudaStream_t st);
+
+int launch_policy_head(int head, int mode, const HeadArgs& a, cudaStream_t st);
+int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st);
+
+
+}  // namespace hb

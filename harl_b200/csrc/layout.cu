@@ -1,0 +1,182 @@
+// Parameter layout (reference state_dict order), derived-weight preparation, error plumbing.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace hb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return HB_ERR_CUDA;
+}
+
+static int add_tensor(hb_net_layout* L, int* cursor, const char* name, int rows, int cols) {
+  int off = round_up(*cursor, 4);
+  if (L) {
+    int i = L->n_tensors++;
+    L->offset[i] = off;
+    L->rows[i] = rows;
+    L->cols[i] = cols;
+    strncpy(L->names[i], name, sizeof(L->names[i]) - 1);
+    L->names[i][sizeof(L->names[i]) - 1] = 0;
+  }
+  *cursor = off + rows * cols;
+  return off;
+}
+
+// Order follows the reference modules' registration order:
+// StochasticPolicy (stochastic_policy.py:33-51): base, rnn, act;  MLPBase (mlp.py:55-62):
+// feature_norm, mlp.fc.{3l, 3l+2};  RNNLayer (rnn.py:14-21): rnn.rnn.*, rnn.norm;
+// DiagGaussian (distributions.py:80-82): fc_mean registered before log_std is assigned, but
+// nn.Module yields own parameters (log_std) before sub-modules (fc_mean);  VNet: v_out.
+int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_layout* out) {
+  if (!d) { set_error("net desc is NULL"); return HB_ERR_INVALID; }
+  if (d->n_layers < 1 || d->n_layers > HB_MAX_LAYERS) { set_error("n_layers %d outside 1..%d", d->n_layers, HB_MAX_LAYERS); return HB_ERR_UNSUPPORTED; }
+  if (d->in_dim < 1) { set_error("in_dim %d", d->in_dim); return HB_ERR_INVALID; }
+  for (int l = 0; l < d->n_layers; ++l)
+    if (d->hidden[l] < 4 || d->hidden[l] > 256 || d->hidden[l] % 4) { set_error("hidden size %d unsupported (need multiple of 4 in 4..256)", d->hidden[l]); return HB_ERR_UNSUPPORTED; }
+  if (d->activation < 0 || d->activation > HB_ACT_IDENTITY) { set_error("activation %d unsupported", d->activation); return HB_ERR_UNSUPPORTED; }
+  if (d->head < 0 || d->head > HB_HEAD_VALUE) { set_error("head %d unsupported", d->head); return HB_ERR_UNSUPPORTED; }
+  if (d->out_dim < 1 || d->out_dim > 32) { set_error("out_dim %d unsupported (1..32)", d->out_dim); return HB_ERR_UNSUPPORTED; }
+  if (d->rnn_layers < 0 || d->rnn_layers > 2) { set_error("rnn_layers %d unsupported", d->rnn_layers); return HB_ERR_UNSUPPORTED; }
+  ParamLayout P;
+  memset(&P, 0xff, sizeof(P));
+  if (out) memset(out, 0, sizeof(*out));
+  int cur = 0;
+  char nm[64];
+  if (d->feature_norm) {
+    P.fn_w = add_tensor(out, &cur, "base.feature_norm.weight", 1, d->in_dim);
+    P.fn_b = add_tensor(out, &cur, "base.feature_norm.bias", 1, d->in_dim);
+  }
+  int prev = d->in_dim;
+  for (int l = 0; l < d->n_layers; ++l) {
+    int h = d->hidden[l];
+    snprintf(nm, sizeof nm, "base.mlp.fc.%d.weight", 3 * l); P.w[l] = add_tensor(out, &cur, nm, h, prev);
+    snprintf(nm, sizeof nm, "base.mlp.fc.%d.bias", 3 * l);   P.b[l] = add_tensor(out, &cur, nm, 1, h);
+    snprintf(nm, sizeof nm, "base.mlp.fc.%d.weight", 3 * l + 2); P.lnw[l] = add_tensor(out, &cur, nm, 1, h);
+    snprintf(nm, sizeof nm, "base.mlp.fc.%d.bias", 3 * l + 2);   P.lnb[l] = add_tensor(out, &cur, nm, 1, h);
+    prev = h;
+  }
+  for (int r = 0; r < d->rnn_layers; ++r) {
+    snprintf(nm, sizeof nm, "rnn.rnn.weight_ih_l%d", r); add_tensor(out, &cur, nm, 3 * prev, prev);
+    snprintf(nm, sizeof nm, "rnn.rnn.weight_hh_l%d", r); add_tensor(out, &cur, nm, 3 * prev, prev);
+    snprintf(nm, sizeof nm, "rnn.rnn.bias_ih_l%d", r); add_tensor(out, &cur, nm, 1, 3 * prev);
+    snprintf(nm, sizeof nm, "rnn.rnn.bias_hh_l%d", r); add_tensor(out, &cur, nm, 1, 3 * prev);
+  }
+  if (d->rnn_layers) {
+    add_tensor(out, &cur, "rnn.norm.weight", 1, prev);
+    add_tensor(out, &cur, "rnn.norm.bias", 1, prev);
+  }
+  if (d->head == HB_HEAD_DISCRETE) {
+    P.hw = add_tensor(out, &cur, "act.action_out.linear.weight", d->out_dim, prev);
+    P.hbias = add_tensor(out, &cur, "act.action_out.linear.bias", 1, d->out_dim);
+  } else if (d->head == HB_HEAD_BOX) {
+    P.log_std = add_tensor(out, &cur, "act.action_out.log_std", 1, d->out_dim);
+    P.hw = add_tensor(out, &cur, "act.action_out.fc_mean.weight", d->out_dim, prev);
+    P.hbias = add_tensor(out, &cur, "act.action_out.fc_mean.bias", 1, d->out_dim);
+  } else {
+    P.hw = add_tensor(out, &cur, "v_out.weight", 1, prev);
+    P.hbias = add_tensor(out, &cur, "v_out.bias", 1, 1);
+  }
+  P.total = round_up(cur, 4);
+
+  PrepLayout Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.n_layers = d->n_layers;
+  int c = 0;
+  prev = d->in_dim;
+  for (int l = 0; l < d->n_layers; ++l) {
+    Q.k[l] = prev;
+    Q.kpad[l] = round_up(prev, 4);
+    Q.n[l] = d->hidden[l];
+    Q.wt[l] = c;   c += Q.kpad[l] * Q.n[l];
+    Q.bias[l] = c; c += Q.n[l];
+    Q.lnw[l] = c;  c += Q.n[l];
+    Q.lnb[l] = c;  c += Q.n[l];
+    prev = d->hidden[l];
+  }
+  Q.hw = c;    c += round_up(d->out_dim * prev, 4);
+  Q.hbias = c; c += round_up(d->out_dim, 4);
+  Q.log_std = c; c += round_up(d->out_dim, 4);
+  Q.total = c;
+  if (pl) *pl = P;
+  if (pp) *pp = Q;
+  if (out) { out->total = P.total; out->prepared_total = Q.total; }
+  return HB_OK;
+}
+
+__global__ void prepare_kernel(ParamLayout P, PrepLayout Q, int feature_norm, int head, int out_dim,
+                               const float* __restrict__ params, float* __restrict__ prep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q.total) return;
+  for (int l = 0; l < Q.n_layers; ++l) {
+    int n = Q.n[l], K = Q.k[l], kp = Q.kpad[l];
+    if (i >= Q.wt[l] && i < Q.wt[l] + kp * n) {
+      int k = (i - Q.wt[l]) / n, j = (i - Q.wt[l]) % n;
+      float v = 0.f;
+      if (k < K) {
+        v = params[P.w[l] + j * K + k];
+        if (l == 0 && feature_norm) v *= params[P.fn_w + k];
+      }
+      prep[i] = v;
+      return;
+    }
+    if (i >= Q.bias[l] && i < Q.bias[l] + n) {
+      int j = i - Q.bias[l];
+      float v = params[P.b[l] + j];
+      if (l == 0 && feature_norm)
+        for (int k = 0; k < K; ++k) v += params[P.w[0] + j * K + k] * params[P.fn_b + k];
+      prep[i] = v;
+      return;
+    }
+    if (i >= Q.lnw[l] && i < Q.lnw[l] + n) { prep[i] = params[P.lnw[l] + i - Q.lnw[l]]; return; }
+    if (i >= Q.lnb[l] && i < Q.lnb[l] + n) { prep[i] = params[P.lnb[l] + i - Q.lnb[l]]; return; }
+  }
+  int h = Q.n[Q.n_layers - 1];
+  if (i >= Q.hw && i < Q.hw + out_dim * h) { prep[i] = params[P.hw + i - Q.hw]; return; }
+  if (i >= Q.hbias && i < Q.hbias + out_dim) { prep[i] = params[P.hbias + i - Q.hbias]; return; }
+  if (head == HB_HEAD_BOX && i >= Q.log_std && i < Q.log_std + out_dim) { prep[i] = params[P.log_std + i - Q.log_std]; return; }
+  prep[i] = 0.f;
+}
+
+int prepare_launch(const hb_net_desc* d, const float* params, float* prepared, cudaStream_t st) {
+  ParamLayout P;
+  PrepLayout Q;
+  int rc = make_layouts(d, &P, &Q, nullptr);
+  if (rc) return rc;
+  prepare_kernel<<<(Q.total + 255) / 256, 256, 0, st>>>(P, Q, d->feature_norm, d->head, d->out_dim, params, prepared);
+  HB_LAUNCH_CHECK("hb_net_prepare");
+  return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" {
+
+int hb_version(void) { return HB_VERSION; }
+const char* hb_last_error(void) { return hb::g_err; }
+int hb_sync_check(void) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return hb::cuda_fail(e, "hb_sync_check");
+  return HB_OK;
+}
+
+int hb_net_layout_of(const hb_net_desc* d, hb_net_layout* out) {
+  HB_CHECK_ARG(out != nullptr, "out is NULL");
+  return hb::make_layouts(d, nullptr, nullptr, out);
+}
+
+int hb_net_prepare(const hb_net_desc* d, const float* params, float* prepared, void* stream) {
+  HB_CHECK_ARG(params && prepared, "NULL buffer");
+  return hb::prepare_launch(d, params, prepared, (cudaStream_t)stream);
+}
+}

@@ -1,0 +1,167 @@
+// Gradient finalisation (feature-norm fold), clip_grad_norm_ + Adam, rollout-insert masks.
+#include "common.cuh"
+
+namespace hb {
+
+int prepare_launch(const hb_net_desc* d, const float* params, float* prepared, cudaStream_t st);
+
+// The layer-0 GEMM runs on the un-affined normalised input with W' = W diag(gamma0),
+// b' = b + W beta0 (hb_net_prepare).  Map gradients w.r.t. (W', b') -- what dw_accum produced
+// in the W0 / b0 slots -- back to (W0, b0, gamma0, beta0):
+//   dgamma0[k] = sum_n W0[n][k] G[n][k],  dbeta0[k] = sum_n W0[n][k] gb[n],
+//   dW0[n][k]  = gamma0[k] G[n][k] + beta0[k] gb[n],   db0 = gb.
+__global__ void featnorm_grad_fold_kernel(const float* __restrict__ params, float* __restrict__ grad, int w0, int b0,
+                                          int fnw, int fnb, int N, int K) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    const float gam = params[fnw + k], bet = params[fnb + k];
+    float dg = 0.f, dbt = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float w = params[w0 + n * K + k];
+      const float G = grad[w0 + n * K + k];
+      const float gb = grad[b0 + n];
+      dg = fmaf(w, G, dg);
+      dbt = fmaf(w, gb, dbt);
+      grad[w0 + n * K + k] = fmaf(gam, G, bet * gb);
+    }
+    grad[fnw + k] = dg;
+    grad[fnb + k] = dbt;
+  }
+}
+
+int launch_featnorm_fold(const hb_net_desc* d, const float* params, float* grad, cudaStream_t st) {
+  if (!d->feature_norm) return HB_OK;
+  ParamLayout P;
+  int rc = make_layouts(d, &P, nullptr, nullptr);
+  if (rc) return rc;
+  int K = d->in_dim;
+  featnorm_grad_fold_kernel<<<(K + 127) / 128, 128, 0, st>>>(params, grad, P.w[0], P.b[0], P.fn_w, P.fn_b, d->hidden[0], K);
+  HB_LAUNCH_CHECK("featnorm_grad_fold");
+  return HB_OK;
+}
+
+// One CTA: total L2 norm, clip coefficient, Adam (torch single-tensor form).
+__global__ void __launch_bounds__(1024) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v, int n,
+                                                         float step_size, float bc2_sqrt, float b1, float b2, float eps,
+                                                         float wd, float max_norm, int use_clip,
+                                                         float* __restrict__ gnorm_out) {
+  __shared__ double red[32];
+  __shared__ float s_coef;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) { float x = g[i]; acc += (double)x * (double)x; }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = warp_sum_d(red[threadIdx.x]);
+    if (threadIdx.x == 0) {
+      float total = (float)sqrt(t);
+      if (gnorm_out) gnorm_out[0] = total;
+      float c = 1.f;
+      if (use_clip) c = fminf(max_norm / (total + 1e-6f), 1.f);
+      s_coef = c;
+    }
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    float gi = g[i] * coef;
+    float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.f - b1);
+    vi = vi * b2 + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+// on_policy_base_runner.py:358-433
+__global__ void insert_masks_kernel(hb_insert_args a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.n_envs) return;
+  const int A = a.n_agents;
+  bool all_done = true;
+  for (int i = 0; i < A; ++i) all_done = all_done && (a.dones[n * A + i] != 0);
+  const float mk = all_done ? 0.f : 1.f;
+  for (int i = 0; i < A; ++i) {
+    if (a.actor_masks_next[i]) a.actor_masks_next[i][n] = mk;
+    if (a.actor_active_next[i]) a.actor_active_next[i][n] = all_done ? 1.f : (a.dones[n * A + i] ? 0.f : 1.f);
+  }
+  if (a.state_type_fp) {
+    for (int i = 0; i < A; ++i) {
+      if (a.critic_masks_next) a.critic_masks_next[n * A + i] = mk;
+      if (a.critic_bad_next) a.critic_bad_next[n * A + i] = a.bad_transition[n * A + i] ? 0.f : 1.f;
+    }
+  } else {
+    if (a.critic_masks_next) a.critic_masks_next[n] = mk;
+    if (a.critic_bad_next) a.critic_bad_next[n] = a.bad_transition[n * A] ? 0.f : 1.f;
+  }
+}
+
+// zero the hidden-state rows of finished envs (on_policy_base_runner.py:358-386)
+__global__ void insert_rnn_reset_kernel(hb_insert_args a) {
+  const int A = a.n_agents;
+  const int64_t per_env = (int64_t)a.actor_rnn_row * A + (int64_t)a.critic_rnn_row * (a.state_type_fp ? A : 1);
+  const int64_t total = per_env * a.n_envs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per_env);
+    int64_t j = i % per_env;
+    bool all_done = true;
+    for (int q = 0; q < A; ++q) all_done = all_done && (a.dones[n * A + q] != 0);
+    if (!all_done) continue;
+    if (j < (int64_t)a.actor_rnn_row * A) {
+      int ag = (int)(j / a.actor_rnn_row), e = (int)(j % a.actor_rnn_row);
+      if (a.actor_rnn_next[ag]) a.actor_rnn_next[ag][(int64_t)n * a.actor_rnn_row + e] = 0.f;
+    } else {
+      j -= (int64_t)a.actor_rnn_row * A;
+      if (a.critic_rnn_next) {
+        int64_t rows_per_env = a.state_type_fp ? A : 1;
+        a.critic_rnn_next[(int64_t)n * rows_per_env * a.critic_rnn_row + j] = 0.f;
+      }
+    }
+  }
+}
+
+}  // namespace hb
+
+extern "C" {
+
+int hb_clip_adam_step(const hb_net_desc* d, float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
+                      float* prepared, const hb_adam_hyper* h, float* grad_norm_out, void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(d && params && grad && exp_avg && exp_avg_sq && h, "NULL argument");
+  HB_CHECK_ARG(h->step >= 1, "Adam step must be >= 1");
+  hb_net_layout L;
+  int rc = make_layouts(d, nullptr, nullptr, &L);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const double bc1 = 1.0 - pow((double)h->beta1, (double)h->step);
+  const double bc2 = 1.0 - pow((double)h->beta2, (double)h->step);
+  clip_adam_kernel<<<1, 1024, 0, st>>>(params, grad, exp_avg, exp_avg_sq, L.total, (float)((double)h->lr / bc1),
+                                       (float)sqrt(bc2), h->beta1, h->beta2, h->eps, h->weight_decay, h->max_grad_norm,
+                                       h->use_max_grad_norm, grad_norm_out);
+  HB_LAUNCH_CHECK("hb_clip_adam_step");
+  if (prepared) return prepare_launch(d, params, prepared, st);
+  return HB_OK;
+}
+
+int hb_rollout_insert_masks(const hb_insert_args* a, void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(a && a->dones && a->bad_transition, "NULL argument");
+  HB_CHECK_ARG(a->n_envs > 0 && a->n_agents > 0 && a->n_agents <= HB_MAX_AGENTS, "bad n_envs / n_agents");
+  cudaStream_t st = (cudaStream_t)stream;
+  insert_masks_kernel<<<(a->n_envs + 127) / 128, 128, 0, st>>>(*a);
+  HB_LAUNCH_CHECK("hb_rollout_insert_masks");
+  if (a->actor_rnn_row > 0 || a->critic_rnn_row > 0) {
+    int64_t total = ((int64_t)a->actor_rnn_row * a->n_agents + (int64_t)a->critic_rnn_row * (a->state_type_fp ? a->n_agents : 1)) * a->n_envs;
+    int64_t g = (total + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    insert_rnn_reset_kernel<<<(unsigned)g, 256, 0, st>>>(*a);
+    HB_LAUNCH_CHECK("hb_rollout_insert_masks(rnn reset)");
+  }
+  return HB_OK;
+}
+}

@@ -1,0 +1,234 @@
+/*
+ * harl_b200 -- C ABI of the B200-native HAPPO/HATRPO on-policy hot path.
+ *
+ * The reference (PKU-MARL/HARL @ d539bad2) is pure Python/PyTorch and has NO FFI; the
+ * boundary it exposes for this path is the duck-typed Python plugin surface
+ * (RUNNER_REGISTRY / ALGO_REGISTRY / buffer classes).  This header
+ * is the C-ABI a maintainer would bind (ctypes) from those Python
+ * classes: every entry point below names the reference function it replaces.
+ *
+ * Conventions
+ *   - plain C types only: raw device pointers, sizes, POD structs; no torch types.
+ *   - every function returns 0 on success, <0 (hb_status) on error; the message is in
+ *     hb_last_error() (thread-local).  No exceptions / exit() cross the ABI.
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*);
+ *     no call synchronises the device.
+ *   - the caller owns every buffer; scratch comes from a caller-allocated workspace sized
+ *     by hb_workspace_bytes().  The library keeps no device allocation of its own.
+ *   - all tensors are fp32, row-major, contiguous unless a leading dimension is given.
+ *   - unsupported configurations return HB_ERR_UNSUPPORTED (Python raises
+ *     NotImplementedError): there is no CPU fallback.
+ */
+#ifndef HARL_B200_H
+#define HARL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_VERSION 100
+#define HB_MAX_LAYERS 4
+#define HB_MAX_AGENTS 32
+#define HB_MAX_TENSORS 40
+
+typedef enum hb_status {
+  HB_OK = 0,
+  HB_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ...) */
+  HB_ERR_UNSUPPORTED = -2, /* configuration outside the implemented path (no CPU fallback) */
+  HB_ERR_WORKSPACE = -3,   /* workspace too small */
+  HB_ERR_CUDA = -4         /* CUDA runtime error (launch failure, ...) */
+} hb_status;
+
+typedef enum hb_activation { /* harl/utils/models_tools.py:28-50 get_active_func */
+  HB_ACT_RELU = 0,
+  HB_ACT_TANH = 1,
+  HB_ACT_SIGMOID = 2,
+  HB_ACT_LEAKY_RELU = 3,
+  HB_ACT_SELU = 4,
+  HB_ACT_HARDSWISH = 5,
+  HB_ACT_IDENTITY = 6
+} hb_activation;
+
+typedef enum hb_head {
+  HB_HEAD_DISCRETE = 0, /* Categorical, harl/models/base/distributions.py:37-55 */
+  HB_HEAD_BOX = 1,      /* DiagGaussian, distributions.py:58-89 */
+  HB_HEAD_VALUE = 2     /* v_out Linear(h,1), harl/models/value_function_models/v_net.py:41-44 */
+} hb_head;
+
+/* One actor (StochasticPolicy, stochastic_policy.py:12-53) or critic (VNet, v_net.py:10-46):
+ * [LN(in)] -> [Linear -> act -> LN] x n_layers -> [GRU x rnn_layers -> LN] -> head. */
+typedef struct hb_net_desc {
+  int32_t in_dim;               /* obs / share-obs dim */
+  int32_t n_layers;             /* len(hidden_sizes), 1..HB_MAX_LAYERS */
+  int32_t hidden[HB_MAX_LAYERS];/* hidden_sizes; each a multiple of 4, <= 256 */
+  int32_t feature_norm;         /* model.use_feature_normalization */
+  int32_t activation;           /* hb_activation */
+  int32_t rnn_layers;           /* 0 = MLP, else model.recurrent_n */
+  int32_t head;                 /* hb_head */
+  int32_t out_dim;              /* n actions (Discrete), act_dim (Box), 1 (value) */
+  float std_x_coef;             /* model.std_x_coef (Box) */
+  float std_y_coef;             /* model.std_y_coef (Box) */
+} hb_net_desc;
+
+/* Flat parameter layout: tensors in the reference state_dict order, each start aligned to
+ * 4 floats.  names[i] is the reference state_dict key. */
+typedef struct hb_net_layout {
+  int32_t n_tensors;
+  int32_t total;                       /* floats, including alignment padding */
+  int32_t offset[HB_MAX_TENSORS];
+  int32_t rows[HB_MAX_TENSORS];        /* 2-D tensors: [rows, cols]; 1-D: rows = 1 */
+  int32_t cols[HB_MAX_TENSORS];
+  char names[HB_MAX_TENSORS][48];
+  int32_t prepared_total;              /* floats of the derived ("prepared") weight buffer */
+} hb_net_layout;
+
+/* ---- library ------------------------------------------------------------------------ */
+int hb_version(void);
+const char* hb_last_error(void);
+/* Asynchronous-error probe: cudaGetLastError on the calling thread (no sync). */
+int hb_sync_check(void);
+
+/* ---- network parameter plumbing ------------------------------------------------------ */
+int hb_net_layout_of(const hb_net_desc* d, hb_net_layout* out);
+/* Derived weights the kernels read (transposed Linear weights, feature-norm affine folded
+ * into layer 1).  Must be re-run after every parameter change; hb_clip_adam_step does so. */
+int hb_net_prepare(const hb_net_desc* d, const float* params, float* prepared, void* stream);
+/* Scratch needed for `rows` rows.  mode: 0 = inference/evaluate (forward only), 1 = gradient. */
+size_t hb_workspace_bytes(const hb_net_desc* d, int64_t rows, int mode);
+
+/* ---- rollout side ------------------------------------------------------------------- */
+/* OnPolicyBaseRunner.insert mask derivation, harl/runners/on_policy_base_runner.py:358-433.
+ * dones [N,A] u8, bad_transition [N,A] u8.  Writes, for every agent a, masks_next[a][N],
+ * active_next[a][N]; critic masks [N] (EP) / [N,A] (FP) and bad_masks likewise; zeroes the
+ * rows of finished envs in the given rnn-state slots (nullable tables / pointers are skipped). */
+typedef struct hb_insert_args {
+  int32_t n_envs, n_agents, state_type_fp;
+  int32_t actor_rnn_row, critic_rnn_row;      /* floats per env row (R*h); 0 = none */
+  const uint8_t* dones;
+  const uint8_t* bad_transition;
+  float* actor_masks_next[HB_MAX_AGENTS];
+  float* actor_active_next[HB_MAX_AGENTS];
+  float* actor_rnn_next[HB_MAX_AGENTS];
+  float* critic_masks_next;
+  float* critic_bad_next;
+  float* critic_rnn_next;
+} hb_insert_args;
+int hb_rollout_insert_masks(const hb_insert_args* a, void* stream);
+
+/* StochasticPolicy.forward (get_actions / act), stochastic_policy.py:55-91 + act.py:44-80.
+ * Samples with Philox4x32-10 keyed by (seed, offset, row); deterministic=1 takes the mode.
+ * actions [rows, ad] (Discrete: ad=1, the index as float), logp [rows, ad]. */
+int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows,
+                  const float* avail, int deterministic, uint64_t seed, uint64_t offset,
+                  float* actions, float* logp, void* ws, size_t ws_bytes, void* stream);
+
+/* VNet.forward (VCritic.get_values), v_net.py:48-67. values [rows,1]. */
+int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs,
+                     int64_t rows, float* values, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- returns / advantages ----------------------------------------------------------- */
+/* OnPolicyCriticBuffer{EP,FP}.compute_returns, on_policy_critic_buffer_ep.py:97-200, fused
+ * with the advantage computation of on_policy_ha_runner.py:26-33.
+ * rewards [T,C], value_preds/masks/bad_masks/returns [T+1,C] (C = N or N*A), next_value [C].
+ * vn_state: device float[3] = (running_mean, running_mean_sq, debiasing_term) or NULL.
+ * advantages [T,C] nullable.  Bit-exact with the reference (separately rounded mul/add). */
+int hb_gae_returns(const float* rewards, float* value_preds, const float* masks,
+                   const float* bad_masks, const float* next_value, float* returns,
+                   float* advantages, int32_t T, int64_t C, float gamma, float gamma_lambda,
+                   int use_gae, int use_proper_time_limits, const float* vn_state, void* stream);
+
+/* Masked moments for happo.py:122-127 / on_policy_ha_runner.py:36-45:
+ * out3 (device double[3]) += (sum x*w, sum x*x*w, sum w) with w = (weight != 0) or 1. */
+int hb_masked_moments(const float* x, const float* weight, int64_t n, double* out3, void* stream);
+/* x_out = (x - mean) / (std + 1e-5) from moments3 (population std). */
+int hb_normalize_by_moments(const float* x, float* x_out, int64_t n, const double* moments3,
+                            void* stream);
+
+/* ValueNorm.update, harl/common/valuenorm.py:47-64, from moments3 = (sum, sumsq, count). */
+int hb_valuenorm_update(float* vn_state, const double* moments3, double beta, void* stream);
+/* ValueNorm.normalize / denormalize, valuenorm.py:66-92 (elementwise). */
+int hb_valuenorm_apply(const float* vn_state, const float* x, float* y, int64_t n,
+                       int denormalize, void* stream);
+
+/* ---- sequential-agent update -------------------------------------------------------- */
+typedef struct hb_ppo_hyper {  /* harl/configs/algos_cfgs/happo.yaml algo.* */
+  float clip_param;
+  float entropy_coef;
+  int32_t use_policy_active_masks;
+  int32_t action_aggregation_prod;  /* 1 = prod, 0 = mean */
+  int32_t use_clip;                 /* 1 = HAPPO, 0 = HAA2C (no clipping) */
+} hb_ppo_hyper;
+
+/* Buffer-resident batch for one actor.  `index` (nullable) maps batch row -> buffer row
+ * (time-major flat index t*N+n, Appendix D of SURVEY.md); NULL = identity. */
+typedef struct hb_actor_batch {
+  const float* obs;          /* [R, in_dim] */
+  const float* actions;      /* [R, ad] */
+  const float* old_logp;     /* [R, ad] */
+  const float* adv;          /* [R] */
+  const float* factor;       /* [R] or NULL (= 1) */
+  const float* active;       /* [R] */
+  const float* avail;        /* [R, n_act] or NULL */
+  const int32_t* index;      /* [rows] or NULL */
+  int64_t rows;
+} hb_actor_batch;
+
+/* StochasticPolicy.evaluate_actions over buffer rows (the old/new log-prob sweeps of
+ * on_policy_ha_runner.py:66-113).  logp_out [rows, ad].  If factor_inout != NULL also applies
+ * on_policy_ha_runner.py:116-124:  factor *= agg_d exp(logp_new - logp_ref[rows, ad]). */
+int hb_policy_evaluate(const hb_net_desc* d, const float* prepared, const hb_actor_batch* b,
+                       float* logp_out, const float* logp_ref, float* factor_inout,
+                       int action_aggregation_prod, void* ws, size_t ws_bytes, void* stream);
+
+/* HAPPO.update forward + loss + backward, harl/algorithms/actors/happo.py:28-91.
+ * grad (layout of hb_net_layout, zeroed inside) receives d(policy_loss - entropy_coef*H)/dparams.
+ * norm3: device double[3]; norm3[2] = sum(active) over the WHOLE minibatch (all ranks) if
+ * use_policy_active_masks else the row count -- the caller reduces it before the call.
+ * scalars (device double[4]) += (sum -factor*min(s1,s2)*w, sum entropy*w, sum ratio, rows). */
+int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* prepared,
+                      const hb_actor_batch* b, const hb_ppo_hyper* h, const double* norm3,
+                      float* grad, double* scalars, void* ws, size_t ws_bytes, void* stream);
+
+typedef struct hb_value_hyper { /* happo.yaml algo.*: VCritic, v_critic.py:24-37 */
+  float clip_param;
+  float huber_delta;
+  float value_loss_coef;
+  int32_t use_huber_loss;
+  int32_t use_clipped_value_loss;
+} hb_value_hyper;
+
+typedef struct hb_critic_batch {
+  const float* share_obs;    /* [R, in_dim] */
+  const float* value_preds;  /* [R] */
+  const float* returns;      /* [R] */
+  const int32_t* index;      /* nullable */
+  int64_t rows;
+} hb_critic_batch;
+
+/* VCritic.update forward + cal_value_loss + backward, v_critic.py:75-146.
+ * vn_state nullable (already updated with this batch, v_critic.py:90-95).
+ * inv_count = 1 / (global number of rows in the minibatch).
+ * scalars (device double[4]) += (sum value_loss_elem, rows, 0, 0). */
+int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepared,
+                  const hb_critic_batch* b, const hb_value_hyper* h, const float* vn_state,
+                  double inv_count, float* grad, double* scalars, void* ws, size_t ws_bytes,
+                  void* stream);
+
+/* clip_grad_norm_ (happo.py:93-98) + torch.optim.Adam step (on_policy_base.py:37-42), then
+ * hb_net_prepare.  grad_norm_out: device float[1] (pre-clip total norm). */
+typedef struct hb_adam_hyper {
+  float lr, beta1, beta2, eps, weight_decay, max_grad_norm;
+  int32_t use_max_grad_norm;
+  int32_t step;              /* 1-based Adam step count of this update */
+} hb_adam_hyper;
+int hb_clip_adam_step(const hb_net_desc* d, float* params, const float* grad, float* exp_avg,
+                      float* exp_avg_sq, float* prepared, const hb_adam_hyper* h,
+                      float* grad_norm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HARL_B200_H */
