@@ -1,0 +1,5 @@
+"""Actor registry (reference: harl/algorithms/actors/__init__.py:13-24); on-policy HA algorithms only."""
+from .haa2c import HAA2C
+from .happo import HAPPO
+
+ALGO_REGISTRY = {"happo": HAPPO, "haa2c": HAA2C}

@@ -1,0 +1,118 @@
+"""HAPPO actor (reference: harl/algorithms/actors/happo.py:10-158).
+
+``train`` runs entirely on the device: masked advantage normalisation, then
+``ppo_epoch x actor_num_mini_batch`` updates, each = fused forward + clip loss (x the running
+importance-ratio ``factor``) + entropy + backward (hb_ppo_actor_grad), a sum-allreduce of the
+flat gradient when the rollout is sharded over GPUs, and clip-norm + Adam (hb_clip_adam_step).
+Scalars come back once per call, not per minibatch.
+"""
+import torch
+
+from ... import _lib as L
+from ... import dist
+from ...nets import DeviceNet
+from .on_policy_base import OnPolicyBase, to_device
+
+
+class HAPPO(OnPolicyBase):
+    use_clip = True  # HAA2C switches the clipping off
+
+    def __init__(self, args, obs_space, act_space, device=torch.device("cpu")):
+        super().__init__(args, obs_space, act_space, device)
+        self.clip_param = args["clip_param"]
+        self.ppo_epoch = args.get("ppo_epoch", args.get("a2c_epoch"))
+        self.actor_num_mini_batch = args["actor_num_mini_batch"]
+        self.entropy_coef = args["entropy_coef"]
+        self.use_max_grad_norm = args["use_max_grad_norm"]
+        self.max_grad_norm = args["max_grad_norm"]
+
+    def _hyper(self):
+        return L.PPOHyper(float(self.clip_param), float(self.entropy_coef), int(bool(self.use_policy_active_masks)),
+                          int(self.action_aggregation == "prod"), int(self.use_clip))
+
+    def _step(self, batch, norm3, scalars_row):
+        """One update on a device batch: grad -> (allreduce) -> clip + Adam. Returns nothing (async)."""
+        self.actor.actor_grad(batch, self._hyper(), norm3, scalars_row)
+        dist.all_reduce_sum_(self.actor.grad)
+        self.actor.adam_step(self.cur_lr, self.opti_eps, self.weight_decay, self.max_grad_norm, self.use_max_grad_norm)
+
+    def update(self, sample):
+        """Reference-compatible single update on a materialised minibatch tuple (happo.py:28-102).
+
+        Returns (policy_loss, dist_entropy, actor_grad_norm, imp_weights_mean) as floats."""
+        (obs, _rnn, actions, _masks, active, old_lp, adv, avail, factor) = sample
+        d = self.device
+        obs, actions, active, old_lp, adv, factor, avail = (to_device(x, d) for x in
+                                                             (obs, actions, active, old_lp, adv, factor, avail))
+        batch = DeviceNet.actor_batch(obs, actions, old_lp, adv.reshape(-1), factor.reshape(-1), active.reshape(-1), avail)
+        norm3 = torch.zeros(3, dtype=torch.float64, device=d)
+        norm3[2] = active.sum().double() if self.use_policy_active_masks else float(obs.shape[0])
+        dist.all_reduce_sum_(norm3)
+        scal = torch.zeros(4, dtype=torch.float64, device=d)
+        self._step(batch, norm3, scal)
+        dist.all_reduce_sum_(scal)
+        s, n = scal.cpu().numpy(), norm3[2].item()
+        return s[0] / n, s[1] / n, self.actor.grad_norm.item(), s[2] / s[3]
+
+    def train(self, actor_buffer, advantages, state_type):
+        """Reference happo.py:104-158.  ``advantages``: [T, N, 1] (tensor on the device or NumPy)."""
+        info = dict(policy_loss=0.0, dist_entropy=0.0, actor_grad_norm=0.0, ratio=0.0)
+        d = self.device
+        buf = actor_buffer
+        T, N = buf.actions.shape[:2]
+        rows = T * N
+        adv = to_device(advantages, d).reshape(rows)
+        active = buf.active_masks[:-1].reshape(rows)
+        m3 = torch.zeros(3, dtype=torch.float64, device=d)
+        L.call("hb_masked_moments", L.ptr(adv), L.ptr(active), rows, L.ptr(m3), L.stream_ptr())
+        dist.all_reduce_sum_(m3)
+        n_active = m3[2].item()  # the one host read before the update loop (reference early-out, happo.py:119)
+        if n_active == 0:
+            return info
+        if state_type == "EP":
+            adv_n = torch.empty_like(adv)
+            L.call("hb_normalize_by_moments", L.ptr(adv), L.ptr(adv_n), rows, L.ptr(m3), L.stream_ptr())
+            adv = adv_n
+        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
+            raise NotImplementedError("recurrent (GRU) policies are not implemented in this build")
+        nmb = self.actor_num_mini_batch
+        n_up = self.ppo_epoch * nmb
+        scal = torch.zeros(n_up, 4, dtype=torch.float64, device=d)
+        gnorm = torch.zeros(n_up, dtype=torch.float32, device=d)
+        norms = torch.zeros(n_up, 3, dtype=torch.float64, device=d)
+        fl = lambda a: a.reshape(rows, *a.shape[2:])
+        obs, actions, old_lp = fl(buf.obs[:-1]), fl(buf.actions), fl(buf.action_log_probs)
+        avail = None if buf.available_actions is None else fl(buf.available_actions[:-1])
+        factor = None if buf.factor is None else buf.factor.reshape(rows)
+        global_rows = float(rows * dist.world_size())
+        u = 0
+        for _ in range(self.ppo_epoch):
+            if nmb == 1:
+                # a single minibatch is the whole buffer: the shuffle only reorders a mean, skip it
+                parts = [None]
+            else:
+                mb = rows // nmb
+                perm = torch.randperm(rows, device=d).to(torch.int32)
+                parts = [perm[i * mb:(i + 1) * mb].contiguous() for i in range(nmb)]
+            for idx in parts:
+                if idx is None:
+                    norms[u, 2] = n_active if self.use_policy_active_masks else global_rows
+                else:
+                    if self.use_policy_active_masks:
+                        norms[u, 2] = active[idx.long()].sum().double()
+                    else:
+                        norms[u, 2] = float(idx.numel())
+                    dist.all_reduce_sum_(norms[u])
+                batch = DeviceNet.actor_batch(obs, actions, old_lp, adv, factor, active, avail, idx,
+                                              rows if idx is None else idx.numel())
+                self._step(batch, norms[u], scal[u])
+                gnorm[u] = self.actor.grad_norm[0]
+                u += 1
+        dist.all_reduce_sum_(scal)
+        s = scal.cpu().numpy()
+        nr = norms[:, 2].cpu().numpy()
+        info["policy_loss"] = float((s[:, 0] / nr).mean())
+        info["dist_entropy"] = float((s[:, 1] / nr).mean())
+        info["ratio"] = float((s[:, 2] / s[:, 3]).mean())
+        info["actor_grad_norm"] = float(gnorm.mean().item())
+        return info

@@ -1,0 +1,127 @@
+"""Shared V-critic (reference: harl/algorithms/critics/v_critic.py:14-208).
+
+``train`` = ``critic_epoch x critic_num_mini_batch`` updates on the device, each: ValueNorm
+statistics update from the batch returns (BEFORE normalising them, v_critic.py:90-95), fused
+forward + clipped Huber/MSE value loss + backward (hb_value_grad), gradient sum-allreduce over
+ranks (the "shared V-critic gradients" exchange of BASELINE.json), clip-norm + Adam.
+"""
+import torch
+
+from ... import _lib as L
+from ... import dist
+from ...nets import DeviceNet
+from ...utils.envs_tools import get_shape_from_obs_space
+from ...utils.models_tools import linear_schedule_lr
+from ..actors.on_policy_base import to_device
+
+
+class VCritic:
+    def __init__(self, args, cent_obs_space, device=torch.device("cpu")):
+        self.args = args
+        self.device = torch.device(device)
+        self.tpdv = dict(dtype=torch.float32, device=self.device)
+        self.clip_param = args["clip_param"]
+        self.critic_epoch = args["critic_epoch"]
+        self.critic_num_mini_batch = args["critic_num_mini_batch"]
+        self.data_chunk_length = args["data_chunk_length"]
+        self.value_loss_coef = args["value_loss_coef"]
+        self.max_grad_norm = args["max_grad_norm"]
+        self.huber_delta = args["huber_delta"]
+        self.use_recurrent_policy = args["use_recurrent_policy"]
+        self.use_naive_recurrent_policy = args["use_naive_recurrent_policy"]
+        self.use_max_grad_norm = args["use_max_grad_norm"]
+        self.use_clipped_value_loss = args["use_clipped_value_loss"]
+        self.use_huber_loss = args["use_huber_loss"]
+        self.use_policy_active_masks = args["use_policy_active_masks"]  # stored, never used (as in the reference)
+        self.critic_lr = args["critic_lr"]
+        self.opti_eps = args["opti_eps"]
+        self.weight_decay = args["weight_decay"]
+        self.share_obs_space = cent_obs_space
+        shp = get_shape_from_obs_space(cent_obs_space)
+        if len(shp) == 3:
+            raise NotImplementedError("CNN state trunks are outside the B200 hot path")
+        self.critic = DeviceNet(args, shp[0], L.HEAD_VALUE, 1, self.device)
+        self.cur_lr = self.critic_lr
+
+    def lr_decay(self, episode, episodes):
+        self.cur_lr = linear_schedule_lr(episode, episodes, self.critic_lr)
+
+    def _no_rnn(self):
+        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
+            raise NotImplementedError("recurrent (GRU) critics are not implemented in this build")
+
+    def get_values(self, cent_obs, rnn_states_critic, masks, values_out=None):
+        """Value predictions [B, 1] and (pass-through) rnn states, as device tensors."""
+        self._no_rnn()
+        x = to_device(cent_obs, self.device)
+        v = values_out if values_out is not None else torch.empty(x.shape[0], 1, **self.tpdv)
+        self.critic.values(x, v)
+        rnn = rnn_states_critic if torch.is_tensor(rnn_states_critic) else to_device(rnn_states_critic, self.device)
+        return v, rnn
+
+    def _hyper(self):
+        return L.ValueHyper(float(self.clip_param), float(self.huber_delta), float(self.value_loss_coef),
+                            int(bool(self.use_huber_loss)), int(bool(self.use_clipped_value_loss)))
+
+    def _step(self, share_obs, value_preds, returns, index, rows, global_rows, value_normalizer, scalars_row):
+        d = self.device
+        if value_normalizer is not None:
+            m3 = torch.zeros(3, dtype=torch.float64, device=d)
+            src = returns if index is None else returns[index.long()]
+            L.call("hb_masked_moments", L.ptr(src.contiguous()), None, rows, L.ptr(m3), L.stream_ptr())
+            dist.all_reduce_sum_(m3)
+            value_normalizer.update_from_moments(m3)
+        cb = DeviceNet.critic_batch(share_obs, value_preds, returns, index, rows)
+        vn = value_normalizer.state if value_normalizer is not None else None
+        self.critic.value_grad(cb, self._hyper(), vn, 1.0 / global_rows, scalars_row)
+        dist.all_reduce_sum_(self.critic.grad)
+        self.critic.adam_step(self.cur_lr, self.opti_eps, self.weight_decay, self.max_grad_norm, self.use_max_grad_norm)
+
+    def update(self, sample, value_normalizer=None):
+        """Reference-compatible single update on a materialised minibatch tuple (v_critic.py:116-157)."""
+        share_obs, _rnn, value_preds, returns, _masks = sample
+        d = self.device
+        so, vp, rt = (to_device(x, d) for x in (share_obs, value_preds, returns))
+        rows = so.shape[0]
+        scal = torch.zeros(4, dtype=torch.float64, device=d)
+        self._step(so, vp.reshape(-1), rt.reshape(-1), None, rows, float(rows * dist.world_size()), value_normalizer, scal)
+        dist.all_reduce_sum_(scal)
+        s = scal.cpu().numpy()
+        return s[0] / s[1], self.critic.grad_norm.item()
+
+    def train(self, critic_buffer, value_normalizer=None):
+        """Reference v_critic.py:159-200."""
+        self._no_rnn()
+        d = self.device
+        buf = critic_buffer
+        T = buf.episode_length
+        rows = buf.value_preds[:-1].numel()
+        so = buf.share_obs[:-1].reshape(rows, -1)
+        vp = buf.value_preds[:-1].reshape(rows)
+        rt = buf.returns[:-1].reshape(rows)
+        nmb = self.critic_num_mini_batch
+        n_up = self.critic_epoch * nmb
+        scal = torch.zeros(n_up, 4, dtype=torch.float64, device=d)
+        gnorm = torch.zeros(n_up, dtype=torch.float32, device=d)
+        u = 0
+        for _ in range(self.critic_epoch):
+            if nmb == 1:
+                parts = [None]
+            else:
+                mb = rows // nmb
+                perm = torch.randperm(rows, device=d).to(torch.int32)
+                parts = [perm[i * mb:(i + 1) * mb].contiguous() for i in range(nmb)]
+            for idx in parts:
+                n = rows if idx is None else idx.numel()
+                self._step(so, vp, rt, idx, n, float(n * dist.world_size()), value_normalizer, scal[u])
+                gnorm[u] = self.critic.grad_norm[0]
+                u += 1
+        dist.all_reduce_sum_(scal)
+        s = scal.cpu().numpy()
+        return dict(value_loss=float((s[:, 0] / s[:, 1]).mean()), critic_grad_norm=float(gnorm.mean().item()))
+
+    def prep_training(self):
+        pass
+
+    def prep_rollout(self):
+        pass

@@ -29,7 +29,7 @@ static size_t work_floats(const PrepLayout& Q, int64_t ch, int mode) {
   size_t f = (size_t)ch * Q.kpad[0];
   const size_t hm = hmax_of(Q);
   if (mode == 0) return f + 2 * (size_t)ch * hm;
-  for (int l = 0; l < Q.n_layers; ++l) f += 2 * (size_t)ch * Q.n[l] + 2 * (size_t)ch;
+  for (int l = 0; l < Q.n_layers; ++l) f += 2 * (size_t)ch * Q.n[l] + (size_t)round_up((int)(2 * ch), 4);
   return f + 2 * (size_t)ch * hm;
 }
 
@@ -50,7 +50,7 @@ static int carve(const PrepLayout& Q, int64_t ch, int mode, void* ws, size_t ws_
   for (int l = 0; l < Q.n_layers; ++l) {
     w->Z[l] = p; p += (size_t)ch * Q.n[l];
     w->Y[l] = p; p += (size_t)ch * Q.n[l];
-    w->stats[l] = p; p += 2 * (size_t)ch;
+    w->stats[l] = p; p += (size_t)round_up((int)(2 * ch), 4);
   }
   w->dA = p; p += (size_t)ch * hm;
   w->dB = p;

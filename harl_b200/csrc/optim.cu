@@ -14,17 +14,17 @@ __global__ void featnorm_grad_fold_kernel(const float* __restrict__ params, floa
                                           int fnw, int fnb, int N, int K) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
     const float gam = params[fnw + k], bet = params[fnb + k];
-    float dg = 0.f, dbt = 0.f;
+    double dg = 0.0, dbt = 0.0;  // these sums cancel heavily: accumulate in fp64 (N <= 256 terms)
     for (int n = 0; n < N; ++n) {
       const float w = params[w0 + n * K + k];
       const float G = grad[w0 + n * K + k];
       const float gb = grad[b0 + n];
-      dg = fmaf(w, G, dg);
-      dbt = fmaf(w, gb, dbt);
+      dg += (double)w * (double)G;
+      dbt += (double)w * (double)gb;
       grad[w0 + n * K + k] = fmaf(gam, G, bet * gb);
     }
-    grad[fnw + k] = dg;
-    grad[fnb + k] = dbt;
+    grad[fnw + k] = (float)dg;
+    grad[fnb + k] = (float)dbt;
   }
 }
 

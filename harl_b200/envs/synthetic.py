@@ -1,0 +1,161 @@
+"""Seeded synthetic batched environment: serves pre-generated tensors of a task's shapes.
+
+This is the measurement env of SURVEY.md section 8(d): observations / states ~ N(0,1), one
+team reward broadcast to all agents, episode ends by truncation at ``episode_limit`` (with
+``bad_transition``), optional random terminations, persistent agent deaths and SMAC-style
+available-action masks.  It follows the reference's batched-env call contract
+(harl/envs/dexhands/dexhands_env.py:29-43 is the reference's own batched env; contract in
+SURVEY.md section 1 "L4 -> L0") but returns tensors resident on the training device, so the rollout
+never crosses the host.  Per-step cost is a pool lookup; the pool is generated once.
+"""
+import numpy as np
+import torch
+
+from .spaces import Box, Discrete
+
+# shapes of the BASELINE.json configs
+PRESETS = {
+    ("pettingzoo_mpe", "simple_spread_v2"): dict(n_agents=3, obs_dim=18, share_obs_dim=54, action_dim=5, episode_limit=25),
+    ("mamujoco", "HalfCheetah-v2", "6x1"): dict(n_agents=6, obs_dim=23, share_obs_dim=17, action_type="Box", action_dim=1, episode_limit=1000),
+    ("mamujoco", "HalfCheetah-v2", "2x3"): dict(n_agents=2, obs_dim=19, share_obs_dim=17, action_type="Box", action_dim=3, episode_limit=1000),
+    ("mamujoco", "Humanoid-v2", "17x1"): dict(n_agents=17, obs_dim=393, share_obs_dim=376, action_type="Box", action_dim=1, episode_limit=1000),
+    ("mamujoco", "Walker2d-v2", "6x1"): dict(n_agents=6, obs_dim=23, share_obs_dim=17, action_type="Box", action_dim=1, episode_limit=1000),
+    ("smac", "5m_vs_6m"): dict(n_agents=5, obs_dim=128, share_obs_dim=128, action_type="Discrete", action_dim=12, episode_limit=70,
+                               state_type="FP", death_prob=0.02, terminate_prob=0.01, avail_prob=0.6),
+}
+
+
+def resolve_shapes(env_name, env_args):
+    """Synthetic-env parameters for a reference env name + env_args (falls back to explicit keys)."""
+    cfg = dict(n_agents=3, obs_dim=18, share_obs_dim=54, action_type="Discrete", action_dim=5, state_type="EP",
+               episode_limit=25, death_prob=0.0, terminate_prob=0.0, avail_prob=1.0)
+    if env_name == "pettingzoo_mpe":
+        cfg.update(PRESETS.get((env_name, env_args.get("scenario")), {}))
+        cfg["action_type"] = "Box" if env_args.get("continuous_actions") else "Discrete"
+    elif env_name == "mamujoco":
+        cfg.update(PRESETS.get((env_name, env_args.get("scenario"), env_args.get("agent_conf")), {}))
+    elif env_name in ("smac", "smacv2"):
+        cfg.update(PRESETS.get(("smac", env_args.get("map_name")), PRESETS[("smac", "5m_vs_6m")]))
+    for k in list(cfg):
+        if k in env_args:
+            cfg[k] = env_args[k]
+    return cfg
+
+
+class LazyInfos:
+    """``infos[n][a]`` dicts built on demand from the last step's bad_transition flags (host copy made once)."""
+
+    def __init__(self, bad):
+        self._bad_dev, self._bad = bad, None
+
+    def __len__(self):
+        return self._bad_dev.shape[0]
+
+    def __getitem__(self, n):
+        if self._bad is None:
+            self._bad = self._bad_dev.cpu().numpy()
+        return [({"bad_transition": True} if b else {}) for b in self._bad[n]]
+
+
+class SyntheticBatchedEnv:
+    def __init__(self, env_name, seed, n_threads, env_args, device=None, pool=16):
+        c = resolve_shapes(env_name, env_args)
+        self.cfg = c
+        self.device = torch.device(device if device is not None else "cpu")
+        self.n_threads = N = int(n_threads)
+        self.n_agents = A = int(c["n_agents"])
+        self.state_type = c["state_type"]
+        od, sd, ad = int(c["obs_dim"]), int(c["share_obs_dim"]), int(c["action_dim"])
+        self.discrete = c["action_type"] == "Discrete"
+        self.observation_space = [Box(shape=(od,)) for _ in range(A)]
+        self.share_observation_space = [Box(shape=(sd,)) for _ in range(A)]
+        self.action_space = [Discrete(ad) if self.discrete else Box(shape=(ad,)) for _ in range(A)]
+        self.episode_limit = int(c["episode_limit"])
+        self.death_prob, self.terminate_prob, self.avail_prob = (float(c[k]) for k in ("death_prob", "terminate_prob", "avail_prob"))
+        self.pool = K = int(pool)
+        g = torch.Generator(device="cpu").manual_seed(int(seed) * 7919 + 1234)
+        rn = lambda *s: torch.randn(*s, generator=g).to(self.device)
+        # agent-major pools so that obs[:, a] is contiguous for the per-agent buffers
+        self._obs = rn(K, A, N, od)
+        self._state = rn(K, N, sd) if self.state_type == "EP" else rn(K, N, A, sd)
+        self._rew = rn(K, N, 1, 1)
+        self._rand = torch.rand(K, N, A + 1, generator=g).to(self.device)
+        self._avail = None
+        if self.discrete:
+            if self.avail_prob >= 1.0:
+                self._avail = torch.ones(1, N, A, ad, device=self.device)
+            else:
+                av = (torch.rand(K, N, A, ad, generator=g) < self.avail_prob).float()
+                av[..., 0] = 0.0  # SMAC rule: no-op unavailable while alive, "stop" always available
+                av[..., 1] = 1.0
+                self._avail = av.to(self.device)
+        self._t = 0
+        self._ep_step = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self._dead = torch.zeros(N, A, dtype=torch.bool, device=self.device)
+        self._simple = self.death_prob == 0.0 and self.terminate_prob == 0.0
+        self._ep_step_host = 0
+        self._true = torch.ones(N, A, dtype=torch.bool, device=self.device)
+        self._false = torch.zeros(N, A, dtype=torch.bool, device=self.device)
+        self.last_bad_transition = self._false
+        self.steps_served = 0
+
+    def _views(self, k):
+        obs = self._obs[k].permute(1, 0, 2)  # [N, A, od] view; obs[:, a] contiguous
+        if self.state_type == "EP":
+            share = self._state[k].unsqueeze(1).expand(-1, self.n_agents, -1)
+        else:
+            share = self._state[k]
+        return obs, share
+
+    def _avail_view(self, k, dead=None):
+        if self._avail is None:
+            return None
+        av = self._avail[k % self._avail.shape[0]]
+        if dead is not None and bool(self.death_prob > 0):
+            av = av.clone()
+            av[dead] = 0.0
+            av[..., 0] = torch.where(dead, torch.ones_like(av[..., 0]), av[..., 0])  # dead agents: only no-op
+        return av
+
+    def reset(self):
+        self._t = 0
+        self._ep_step.zero_()
+        self._ep_step_host = 0
+        self._dead.zero_()
+        obs, share = self._views(0)
+        return obs, share, self._avail_view(0)
+
+    def step(self, actions):
+        """actions [N, A, ad] (ignored by the synthetic dynamics). Returns the reference 6-tuple."""
+        self._t += 1
+        self.steps_served += 1
+        k = self._t % self.pool
+        obs, share = self._views(k)
+        rewards = self._rew[k].expand(-1, self.n_agents, -1)
+        if self._simple:
+            self._ep_step_host += 1
+            if self._ep_step_host >= self.episode_limit:
+                self._ep_step_host = 0
+                dones, bad = self._true, self._true
+            else:
+                dones, bad = self._false, self._false
+            avail = self._avail_view(k)
+        else:
+            r = self._rand[k]
+            self._ep_step += 1
+            trunc = self._ep_step >= self.episode_limit
+            self._dead |= r[:, : self.n_agents] < self.death_prob
+            env_done = trunc | self._dead.all(1) | (r[:, self.n_agents] < self.terminate_prob)
+            dones = self._dead | env_done[:, None]
+            bad = (trunc & env_done)[:, None].expand(-1, self.n_agents)
+            self._ep_step = torch.where(env_done, torch.zeros_like(self._ep_step), self._ep_step)
+            self._dead = self._dead & ~env_done[:, None]
+            avail = self._avail_view(k, dones & ~env_done[:, None])
+        self.last_bad_transition = bad
+        return obs, share, rewards, dones, LazyInfos(bad), avail
+
+    def seed(self, seed):
+        pass
+
+    def close(self):
+        pass

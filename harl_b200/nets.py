@@ -205,6 +205,14 @@ class DeviceNet:
         b.obs, b.actions, b.old_logp, b.adv = L.ptr(obs), L.ptr(actions), L.ptr(old_logp), L.ptr(adv)
         b.factor, b.active, b.avail, b.index = L.ptr(factor), L.ptr(active), L.ptr(avail), L.ptr(index)
         b.rows = int(rows if rows is not None else (index.shape[0] if index is not None else actions.shape[0]))
+        b._keep = (obs, actions, old_logp, adv, factor, active, avail, index)  # the struct holds raw pointers only
+        return b
+
+    @staticmethod
+    def critic_batch(share_obs, value_preds, returns, index=None, rows=None):
+        b = L.CriticBatch(L.ptr(share_obs), L.ptr(value_preds), L.ptr(returns), L.ptr(index),
+                          int(rows if rows is not None else (index.shape[0] if index is not None else value_preds.numel())))
+        b._keep = (share_obs, value_preds, returns, index)
         return b
 
     def evaluate(self, batch, logp_out=None, logp_ref=None, factor_inout=None, agg_prod=True):

@@ -1,0 +1,321 @@
+"""On-policy runner (reference: harl/runners/on_policy_base_runner.py:26-775).
+
+Same constructor signature, attributes and method names (run / warmup / collect / insert /
+compute / train / after_update / eval / save / restore / close), same config keys.  What
+changes is where the data lives: buffers, networks, optimiser state, ValueNorm statistics and
+the env outputs are device tensors for the whole run; ``collect`` writes actions, log-probs and
+values straight into their buffer slots, ``insert`` derives the masks with one kernel, and the
+update never materialises a minibatch.  With ``torch.distributed`` initialised the rollout
+threads are sharded over the ranks (one process per GPU) and gradients / normalisers are
+sum-allreduced.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .. import dist
+from ..algorithms.actors import ALGO_REGISTRY
+from ..algorithms.critics.v_critic import VCritic
+from ..common.buffers.on_policy_actor_buffer import OnPolicyActorBuffer
+from ..common.buffers.on_policy_critic_buffer_ep import OnPolicyCriticBufferEP
+from ..common.buffers.on_policy_critic_buffer_fp import OnPolicyCriticBufferFP
+from ..common.valuenorm import ValueNorm
+from ..envs import LOGGER_REGISTRY
+from ..utils.configs_tools import init_dir, save_config
+from ..utils.envs_tools import get_num_agents, make_eval_env, make_train_env, set_seed
+from ..utils.models_tools import init_device
+from ..utils.trans_tools import _t2n
+
+
+class OnPolicyBaseRunner:
+    def __init__(self, args, algo_args, env_args):
+        self.args, self.algo_args, self.env_args = args, algo_args, env_args
+        self.hidden_sizes = algo_args["model"]["hidden_sizes"]
+        self.rnn_hidden_size = self.hidden_sizes[-1]
+        self.recurrent_n = algo_args["model"]["recurrent_n"]
+        self.action_aggregation = algo_args["algo"]["action_aggregation"]
+        self.state_type = env_args.get("state_type", "EP")
+        self.share_param = algo_args["algo"]["share_param"]
+        self.fixed_order = algo_args["algo"]["fixed_order"]
+        set_seed(algo_args["seed"])
+        self.device = init_device(algo_args["device"])
+        if algo_args["render"]["use_render"]:
+            raise NotImplementedError("rendering needs the third-party simulators, which are out of scope")
+        self.world, self.rank = dist.world_size(), dist.rank()
+        self.n_global = algo_args["train"]["n_rollout_threads"]
+        lo, hi = dist.shard_bounds(self.n_global, self.world, self.rank)
+        self.n_local = hi - lo
+        self.run_dir, self.log_dir, self.save_dir, self.writter = init_dir(
+            args["env"], env_args, args["algo"], args["exp_name"] + (f"-rank{self.rank}" if self.world > 1 else ""),
+            algo_args["seed"]["seed"], logger_path=algo_args["logger"]["log_dir"])
+        save_config(args, algo_args, env_args, self.run_dir)
+        try:
+            import setproctitle
+
+            setproctitle.setproctitle(f"{args['algo']}-{args['env']}-{args['exp_name']}")
+        except ImportError:
+            pass
+
+        seed = algo_args["seed"]["seed"]
+        self.envs = make_train_env(args["env"], seed + 1000 * self.rank, self.n_local, env_args, self.device)
+        self.eval_envs = (make_eval_env(args["env"], seed, algo_args["eval"]["n_eval_rollout_threads"], env_args,
+                                        self.device) if algo_args["eval"]["use_eval"] else None)
+        self.num_agents = get_num_agents(args["env"], env_args, self.envs)
+        if self.num_agents > L.HB_MAX_AGENTS:
+            raise NotImplementedError(f"more than {L.HB_MAX_AGENTS} agents")
+        if self.rank == 0:
+            print("share_observation_space: ", self.envs.share_observation_space)
+            print("observation_space: ", self.envs.observation_space)
+            print("action_space: ", self.envs.action_space)
+
+        actor_args = {**algo_args["model"], **algo_args["algo"]}
+        if self.share_param:
+            first = ALGO_REGISTRY[args["algo"]](actor_args, self.envs.observation_space[0], self.envs.action_space[0],
+                                                device=self.device)
+            for a in range(1, self.num_agents):
+                assert self.envs.observation_space[a] == self.envs.observation_space[0], \
+                    "Agents have heterogeneous observation spaces, parameter sharing is not valid."
+                assert self.envs.action_space[a] == self.envs.action_space[0], \
+                    "Agents have heterogeneous action spaces, parameter sharing is not valid."
+            self.actor = [first] * self.num_agents
+        else:
+            self.actor = [ALGO_REGISTRY[args["algo"]](actor_args, self.envs.observation_space[a],
+                                                      self.envs.action_space[a], device=self.device)
+                          for a in range(self.num_agents)]
+
+        train_local = {**algo_args["train"], "n_rollout_threads": self.n_local}
+        self.actor_buffer = [OnPolicyActorBuffer({**train_local, **algo_args["model"]}, self.envs.observation_space[a],
+                                                 self.envs.action_space[a], device=self.device)
+                             for a in range(self.num_agents)]
+        share_space = self.envs.share_observation_space[0]
+        self.critic = VCritic(actor_args, share_space, device=self.device)
+        cb_args = {**train_local, **algo_args["model"], **algo_args["algo"]}
+        if self.state_type == "EP":
+            self.critic_buffer = OnPolicyCriticBufferEP(cb_args, share_space, device=self.device)
+        elif self.state_type == "FP":
+            self.critic_buffer = OnPolicyCriticBufferFP(cb_args, share_space, self.num_agents, device=self.device)
+        else:
+            raise NotImplementedError
+        self.value_normalizer = ValueNorm(1, device=self.device) if algo_args["train"]["use_valuenorm"] else None
+        self.logger = LOGGER_REGISTRY[args["env"]](args, algo_args, env_args, self.num_agents, self.writter, self.run_dir)
+        self.timers = {}
+        if algo_args["train"]["model_dir"] is not None:
+            self.restore()
+
+    # ------------------------------------------------------------------ main loop
+    def run(self):
+        if self.rank == 0:
+            print("start running")
+        self.warmup()
+        T = self.algo_args["train"]["episode_length"]
+        episodes = int(self.algo_args["train"]["num_env_steps"]) // T // self.n_global
+        self.logger.init(episodes)
+        for episode in range(1, episodes + 1):
+            self.run_iteration(episode, episodes)
+
+    def run_iteration(self, episode, episodes):
+        """One training iteration: T x (collect -> env.step -> insert) -> compute -> train -> after_update."""
+        tr = self.algo_args["train"]
+        if tr["use_linear_lr_decay"]:
+            for a in (self.actor[:1] if self.share_param else self.actor):
+                a.lr_decay(episode, episodes)
+            self.critic.lr_decay(episode, episodes)
+        self.logger.episode_init(episode)
+        self.prep_rollout()
+        for step in range(tr["episode_length"]):
+            values, actions, action_log_probs, rnn_states, rnn_states_critic = self.collect(step)
+            obs, share_obs, rewards, dones, infos, available_actions = self.envs.step(actions)
+            data = (obs, share_obs, rewards, dones, infos, available_actions, values, actions, action_log_probs,
+                    rnn_states, rnn_states_critic)
+            self.logger.per_step(data)
+            self.insert(data)
+        self.compute()
+        self.prep_training()
+        actor_train_infos, critic_train_info = self.train()
+        if episode % tr["log_interval"] == 0 and self.rank == 0:
+            self.logger.episode_log(actor_train_infos, critic_train_info, self.actor_buffer, self.critic_buffer)
+        if episode % tr["eval_interval"] == 0:
+            if self.algo_args["eval"]["use_eval"]:
+                self.prep_rollout()
+                self.eval()
+            if self.rank == 0:
+                self.save()
+        self.after_update()
+        self.last_train_infos = (actor_train_infos, critic_train_info)
+
+    def warmup(self):
+        """Reset the envs and fill slot 0 (reference :269-283)."""
+        obs, share_obs, available_actions = self.envs.reset()
+        obs = torch.as_tensor(obs, device=self.device)
+        share_obs = torch.as_tensor(share_obs, device=self.device)
+        for a in range(self.num_agents):
+            self.actor_buffer[a].obs[0].copy_(obs[:, a])
+            if self.actor_buffer[a].available_actions is not None:
+                self.actor_buffer[a].available_actions[0].copy_(torch.as_tensor(available_actions, device=self.device)[:, a])
+        if self.state_type == "EP":
+            self.critic_buffer.share_obs[0].copy_(share_obs[:, 0])
+        else:
+            self.critic_buffer.share_obs[0].copy_(share_obs)
+
+    @torch.no_grad()
+    def collect(self, step):
+        """Actions / log-probs / values for one rollout step, written straight into slot ``step``
+        of the buffers (reference :285-340).  Returns the reference 5-tuple as device tensors."""
+        for a in range(self.num_agents):
+            b = self.actor_buffer[a]
+            self.actor[a].get_actions(b.obs[step], b.rnn_states[step], b.masks[step],
+                                      b.available_actions[step] if b.available_actions is not None else None,
+                                      actions_out=b.actions[step], logp_out=b.action_log_probs[step])
+        actions = torch.stack([b.actions[step] for b in self.actor_buffer], dim=1)
+        action_log_probs = torch.stack([b.action_log_probs[step] for b in self.actor_buffer], dim=1)
+        rnn_states = torch.stack([b.rnn_states[step] for b in self.actor_buffer], dim=1) \
+            if self.actor_buffer[0].recurrent else None
+        cb = self.critic_buffer
+        sd = cb.share_obs.shape[-1]
+        values, _ = self.critic.get_values(cb.share_obs[step].reshape(-1, sd), None, None,
+                                           values_out=cb.value_preds[step].reshape(-1, 1))
+        values = cb.value_preds[step]
+        rnn_states_critic = cb.rnn_states_critic[step] if cb.recurrent else None
+        self._in_place = (actions, action_log_probs)  # already sitting in their buffer slots
+        return values, actions, action_log_probs, rnn_states, rnn_states_critic
+
+    def _bad_transition_flags(self, infos):
+        """[N, A] uint8 ``bad_transition`` flags from a batched env (device tensor) or a list of dict lists."""
+        bad = getattr(infos, "_bad_dev", None)
+        if bad is None:
+            bad = torch.tensor([[bool(i.get("bad_transition", False)) for i in row] for row in infos])
+        return bad.to(device=self.device, dtype=torch.uint8).contiguous()
+
+    def insert(self, data):
+        """Mask derivation (one kernel) + slot writes (reference :342-460)."""
+        (obs, share_obs, rewards, dones, infos, available_actions, values, actions, action_log_probs, rnn_states,
+         rnn_states_critic) = data
+        dev = self.device
+        cb = self.critic_buffer
+        s = cb.step
+        dones_u8 = torch.as_tensor(dones).to(device=dev, dtype=torch.uint8).contiguous()
+        bad_u8 = self._bad_transition_flags(infos)
+        a = L.InsertArgs()
+        a.n_envs, a.n_agents, a.state_type_fp = self.n_local, self.num_agents, int(self.state_type == "FP")
+        rec = self.actor_buffer[0].recurrent
+        a.actor_rnn_row = self.recurrent_n * self.rnn_hidden_size if rec else 0
+        a.critic_rnn_row = self.recurrent_n * self.rnn_hidden_size if cb.recurrent else 0
+        a.dones, a.bad_transition = L.ptr(dones_u8), L.ptr(bad_u8)
+        for i, b in enumerate(self.actor_buffer):
+            if rec and rnn_states is not None:
+                b.rnn_states[s + 1].copy_(torch.as_tensor(rnn_states, device=dev)[:, i])
+            a.actor_masks_next[i] = L.ptr(b.masks[s + 1])
+            a.actor_active_next[i] = L.ptr(b.active_masks[s + 1])
+            a.actor_rnn_next[i] = L.ptr(b.rnn_states[s + 1]) if rec else None
+        if cb.recurrent and rnn_states_critic is not None:
+            cb.rnn_states_critic[s + 1].copy_(torch.as_tensor(rnn_states_critic, device=dev))
+        a.critic_masks_next, a.critic_bad_next = L.ptr(cb.masks[s + 1]), L.ptr(cb.bad_masks[s + 1])
+        a.critic_rnn_next = L.ptr(cb.rnn_states_critic[s + 1]) if cb.recurrent else None
+        L.call("hb_rollout_insert_masks", C.byref(a), L.stream_ptr())
+        obs = torch.as_tensor(obs, device=dev)
+        avail = None if available_actions is None or (not torch.is_tensor(available_actions)
+                                                      and available_actions[0] is None) \
+            else torch.as_tensor(available_actions, device=dev)
+        in_place = getattr(self, "_in_place", (None, None))
+        skip = actions is in_place[0] and action_log_probs is in_place[1]
+        for i, b in enumerate(self.actor_buffer):
+            b.insert(obs[:, i], None, None if skip else torch.as_tensor(actions, device=dev)[:, i],
+                     None if skip else torch.as_tensor(action_log_probs, device=dev)[:, i], None, None,
+                     avail[:, i] if avail is not None else None)
+        share_obs = torch.as_tensor(share_obs, device=dev)
+        rewards = torch.as_tensor(rewards, device=dev)
+        if self.state_type == "EP":
+            cb.insert(share_obs[:, 0], None, values, rewards[:, 0], None, None)
+        else:
+            cb.insert(share_obs, None, values, rewards, None, None)
+
+    @torch.no_grad()
+    def compute(self):
+        """Bootstrap value of slot T, then the GAE / return kernel (reference :462-484)."""
+        cb = self.critic_buffer
+        sd = cb.share_obs.shape[-1]
+        next_value, _ = self.critic.get_values(cb.share_obs[-1].reshape(-1, sd), None, None)
+        cb.compute_returns(next_value, self.value_normalizer)
+
+    def train(self):
+        raise NotImplementedError
+
+    def after_update(self):
+        for b in self.actor_buffer:
+            b.after_update()
+        self.critic_buffer.after_update()
+
+    # ------------------------------------------------------------------ evaluation / checkpoints
+    @torch.no_grad()
+    def eval(self):
+        """Deterministic evaluation on ``eval_envs`` until ``eval_episodes`` finish (reference :500-591)."""
+        if self.eval_envs is None:
+            return
+        self.logger.eval_init()
+        n = self.algo_args["eval"]["n_eval_rollout_threads"]
+        eval_episode = 0
+        obs, share_obs, avail = self.eval_envs.reset()
+        while True:
+            acts = []
+            obs_t = torch.as_tensor(obs, device=self.device)
+            for a in range(self.num_agents):
+                av = None if avail is None else torch.as_tensor(avail, device=self.device)[:, a].contiguous()
+                act, _ = self.actor[a].act(obs_t[:, a].contiguous(), None, None, av, deterministic=True)
+                acts.append(act)
+            actions = torch.stack(acts, dim=1)
+            obs, share_obs, rewards, dones, infos, avail = self.eval_envs.step(actions)
+            self.logger.eval_per_step((obs, share_obs, rewards, dones, infos, avail))
+            dones_env = _t2n(torch.as_tensor(dones)).all(axis=1)
+            for i in range(n):
+                if dones_env[i]:
+                    eval_episode += 1
+                    self.logger.eval_thread_done(i)
+            if eval_episode >= self.algo_args["eval"]["eval_episodes"]:
+                self.logger.eval_log(eval_episode)
+                break
+
+    def prep_rollout(self):
+        for a in self.actor:
+            a.prep_rollout()
+        self.critic.prep_rollout()
+
+    def prep_training(self):
+        for a in self.actor:
+            a.prep_training()
+        self.critic.prep_training()
+
+    def save(self):
+        """Reference file names and state_dict keys (:724-740), so checkpoints interchange."""
+        for a in range(self.num_agents):
+            torch.save({k: v.cpu() for k, v in self.actor[a].actor.state_dict().items()},
+                       os.path.join(self.save_dir, f"actor_agent{a}.pt"))
+        torch.save({k: v.cpu() for k, v in self.critic.critic.state_dict().items()},
+                   os.path.join(self.save_dir, "critic_agent.pt"))
+        if self.value_normalizer is not None:
+            torch.save({k: v.cpu() for k, v in self.value_normalizer.state_dict().items()},
+                       os.path.join(self.save_dir, "value_normalizer.pt"))
+
+    def restore(self):
+        """Reference :742-763."""
+        md = str(self.algo_args["train"]["model_dir"])
+        for a in range(self.num_agents):
+            self.actor[a].actor.load_state_dict(torch.load(os.path.join(md, f"actor_agent{a}.pt"), map_location="cpu"))
+        self.critic.critic.load_state_dict(torch.load(os.path.join(md, "critic_agent.pt"), map_location="cpu"))
+        vp = os.path.join(md, "value_normalizer.pt")
+        if self.value_normalizer is not None and os.path.exists(vp):
+            self.value_normalizer.load_state_dict(torch.load(vp, map_location="cpu"))
+
+    def close(self):
+        self.envs.close()
+        if self.eval_envs is not None and self.eval_envs is not self.envs:
+            self.eval_envs.close()
+        try:
+            self.writter.export_scalars_to_json(os.path.join(self.log_dir, "summary.json"))
+        except Exception:
+            pass
+        self.writter.close()
+        self.logger.close()

@@ -1,0 +1,57 @@
+"""Sequential-agent ("HA") update (reference: harl/runners/on_policy_ha_runner.py:8-130).
+
+Agents are updated one after another in a random order; agent i's clip loss is re-weighted by
+``factor`` = the running product of the importance ratios of the agents updated before it.
+Everything stays on the device: advantages come from the GAE kernel, the old / new log-prob
+sweeps are forward-only kernel passes over the buffer (the second one multiplies ``factor`` in
+place), and the critic update follows.
+"""
+import torch
+
+from .. import _lib as L
+from .. import dist
+from ..nets import DeviceNet
+from .on_policy_base_runner import OnPolicyBaseRunner
+
+
+class OnPolicyHARunner(OnPolicyBaseRunner):
+    def train(self):
+        T = self.algo_args["train"]["episode_length"]
+        N = self.n_local
+        dev = self.device
+        rows = T * N
+        cb = self.critic_buffer
+        factor = torch.ones(T, N, 1, dtype=torch.float32, device=dev)
+        advantages = cb.advantages  # returns[:-1] - denorm(value_preds[:-1]), written by hb_gae_returns (:26-33)
+        if self.state_type == "FP":  # global masked normalisation across agents (:36-45)
+            active = torch.stack([b.active_masks[:-1] for b in self.actor_buffer], dim=2).contiguous()
+            m3 = torch.zeros(3, dtype=torch.float64, device=dev)
+            L.call("hb_masked_moments", L.ptr(advantages), L.ptr(active), advantages.numel(), L.ptr(m3), L.stream_ptr())
+            dist.all_reduce_sum_(m3)
+            adv_n = torch.empty_like(advantages)
+            L.call("hb_normalize_by_moments", L.ptr(advantages), L.ptr(adv_n), advantages.numel(), L.ptr(m3), L.stream_ptr())
+            advantages = adv_n
+        if self.fixed_order:
+            agent_order = list(range(self.num_agents))
+        else:
+            agent_order = list(torch.randperm(self.num_agents).numpy())
+        self.last_agent_order = agent_order
+        infos = []
+        agg_prod = self.action_aggregation == "prod"
+        for agent_id in agent_order:
+            buf, actor = self.actor_buffer[agent_id], self.actor[agent_id]
+            buf.update_factor(factor)
+            fl = lambda a: a.reshape(rows, *a.shape[2:])
+            avail = None if buf.available_actions is None else fl(buf.available_actions[:-1])
+            sweep = DeviceNet.actor_batch(fl(buf.obs[:-1]), fl(buf.actions), avail=avail)
+            old_logp = torch.empty(rows, actor.actor.act_width, dtype=torch.float32, device=dev)
+            actor.actor.evaluate(sweep, logp_out=old_logp)                       # :66-83
+            adv_a = advantages if self.state_type == "EP" else advantages[:, :, agent_id].contiguous()
+            infos.append(actor.train(buf, adv_a, self.state_type))               # :86-93
+            actor.actor.evaluate(sweep, logp_ref=old_logp, factor_inout=factor.reshape(rows), agg_prod=agg_prod)  # :96-124
+        critic_info = self.critic.train(cb, self.value_normalizer)               # :128
+        # per-agent infos are reported in agent-id order
+        ordered = [None] * self.num_agents
+        for pos, agent_id in enumerate(agent_order):
+            ordered[agent_id] = infos[pos]
+        return ordered, critic_info

@@ -1,0 +1,143 @@
+"""GPU end-to-end parity: a whole training iteration through the public Runner vs the CPU oracle,
+and the reference's own ``OnPolicyHARunner.train()`` golden vectors replayed on the device.
+
+Tolerances: masks / returns / advantages bit-exact; factors 3e-4 rel; train-info scalars 2e-4;
+weights after the update 3e-5 abs (Adam steps are lr-sized, 5e-4).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import util as U
+from tests.smoke_check import check_iteration, small_config
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("action_type,state_type,over", [
+    ("Discrete", "EP", {}),
+    ("Box", "EP", dict(clip_param=0.05)),
+    ("Discrete", "FP", dict(gamma=0.95)),
+    ("Box", "FP", dict(action_aggregation="mean")),
+    ("Discrete", "EP", dict(use_policy_active_masks=False, use_huber_loss=False, use_clipped_value_loss=False)),
+])
+def test_iteration_vs_oracle(action_type, state_type, over):
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    args, algo_args, env_args = small_config(action_type=action_type, state_type=state_type, **over)
+    runner = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+    runner.warmup()
+    runner.logger.init(2)
+    check_iteration(runner)
+    check_iteration(runner)  # second iteration: slot T -> 0 carry-over, Adam moments, ValueNorm state
+    runner.close()
+
+
+@pytest.mark.parametrize("use_gae,ptl,vn", [(True, False, False), (False, True, True), (False, False, False)])
+def test_iteration_return_branches(use_gae, ptl, vn):
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    args, algo_args, env_args = small_config(use_gae=use_gae)
+    algo_args["train"]["use_proper_time_limits"] = ptl
+    algo_args["train"]["use_valuenorm"] = vn
+    runner = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+    runner.warmup()
+    runner.logger.init(1)
+    check_iteration(runner)
+    runner.close()
+
+
+def test_haa2c_iteration():
+    from harl_b200.runners import RUNNER_REGISTRY
+    from oracle import algo as oa
+
+    args, algo_args, env_args = small_config(algo="haa2c")
+    runner = RUNNER_REGISTRY["haa2c"](args, algo_args, env_args)
+    runner.warmup()
+    runner.logger.init(1)
+    # oracle without clipping = an unreachable clip range
+    orig = oa.ppo_loss
+
+    def no_clip(logp, old, adv, active, factor, ent, cfg):
+        return orig(logp, old, adv, active, factor, ent, {**cfg, "clip_param": 1e30})
+
+    oa.ppo_loss = no_clip
+    try:
+        check_iteration(runner)
+    finally:
+        oa.ppo_loss = orig
+    runner.close()
+
+
+def _load_runner_from_golden(g, cfg, m):
+    """A runner shell (no env / dirs) holding the golden buffers and weights."""
+    from harl_b200.algorithms.actors.happo import HAPPO
+    from harl_b200.algorithms.critics.v_critic import VCritic
+    from harl_b200.common.buffers.on_policy_actor_buffer import OnPolicyActorBuffer
+    from harl_b200.common.buffers.on_policy_critic_buffer_ep import OnPolicyCriticBufferEP
+    from harl_b200.common.valuenorm import ValueNorm
+    from harl_b200.envs.spaces import Box, Discrete
+    from harl_b200.runners.on_policy_ha_runner import OnPolicyHARunner
+
+    dev = torch.device("cuda:0")
+    A = m["A"]
+    act_space = Discrete(m["act_dim"]) if m["head"] == "Discrete" else Box(shape=(m["act_dim"],))
+    r = object.__new__(OnPolicyHARunner)
+    r.algo_args = {"train": cfg, "algo": cfg, "model": cfg}
+    r.device, r.n_local, r.num_agents, r.state_type = dev, cfg["n_rollout_threads"], A, m["state_type"]
+    r.fixed_order, r.action_aggregation = True, cfg["action_aggregation"]
+    r.actor, r.actor_buffer = [], []
+    for a in range(A):
+        ac = HAPPO(cfg, Box(shape=(m["od"],)), act_space, device=dev)
+        ac.actor.load_state_dict(U.params_of(g, f"actor{a}/"))
+        r.actor.append(ac)
+        b = OnPolicyActorBuffer(cfg, Box(shape=(m["od"],)), act_space, device=dev)
+        for k in ("obs", "actions", "action_log_probs", "masks", "active_masks"):
+            getattr(b, k).copy_(torch.from_numpy(g[f"a{a}.{k}"]))
+        if b.available_actions is not None:
+            b.available_actions.copy_(torch.from_numpy(g[f"a{a}.available_actions"]))
+        r.actor_buffer.append(b)
+    r.critic = VCritic(cfg, Box(shape=(m["sd"],)), device=dev)
+    r.critic.critic.load_state_dict(U.params_of(g, "critic/"))
+    cb = OnPolicyCriticBufferEP(cfg, Box(shape=(m["sd"],)), device=dev)
+    for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks"):
+        getattr(cb, k).copy_(torch.from_numpy(g["c." + k]))
+    r.critic_buffer = cb
+    r.value_normalizer = ValueNorm(1, device=dev)
+    r.value_normalizer.state.copy_(torch.from_numpy(g["vn_in"]))
+    # advantages as the runner would have them after compute(): returns[:-1] - denorm(value_preds[:-1])
+    den = r.value_normalizer.denormalize(cb.value_preds[:-1])
+    cb.advantages.copy_(cb.returns[:-1] - torch.from_numpy(den).to(dev))
+    return r
+
+
+@pytest.mark.parametrize("name", ["ha_train_mlp_disc_EP", "ha_train_mlp_box_EP"])
+def test_reference_ha_train_golden(name):
+    """The unmodified reference's OnPolicyHARunner.train() outputs, reproduced by the device path."""
+    g = U.load(name)
+    cfg, m = U.cfg_of(g), U.meta_of(g)
+    r = _load_runner_from_golden(g, cfg, m)
+    infos, cinfo = r.train()
+    torch.cuda.synchronize()
+    for a in range(m["A"]):
+        np.testing.assert_allclose(r.actor_buffer[a].factor.cpu().numpy(), g[f"out.factor{a}"], rtol=3e-4, atol=3e-5)
+        got = [infos[a][k] for k in ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio")]
+        np.testing.assert_allclose(got, g[f"out.info{a}"], rtol=3e-4, atol=3e-5)
+        for k, v in r.actor[a].actor.state_dict().items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"out.actor{a}/" + k], rtol=0, atol=3e-5, err_msg=k)
+    np.testing.assert_allclose([cinfo["value_loss"], cinfo["critic_grad_norm"]], g["out.cinfo"], rtol=3e-4)
+    for k, v in r.critic.critic.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), g["out.critic/" + k], rtol=0, atol=3e-5, err_msg=k)
+    np.testing.assert_allclose(r.value_normalizer.state.cpu().numpy(), g["out.vn"], rtol=1e-5)
+
+
+def test_unsupported_recurrent_fails_loudly():
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    args, algo_args, env_args = small_config()
+    algo_args["model"]["use_recurrent_policy"] = True
+    runner = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+    runner.warmup()
+    with pytest.raises(NotImplementedError):
+        runner.collect(0)
+    runner.close()

@@ -260,7 +260,7 @@ def test_sampler_statistics(head, na):
     else:
         mean, std = on.gaussian_params(p, cfg, feat)
         s = a.cpu().numpy()
-        np.testing.assert_allclose(s.mean(0), mean[0].numpy(), atol=5 * std[0].numpy() / np.sqrt(B) + 1e-4)
+        np.testing.assert_allclose(s.mean(0), mean[0].numpy(), atol=float(5 * std[0].numpy().max() / np.sqrt(B) + 1e-4))
         np.testing.assert_allclose(s.std(0), std[0].numpy(), rtol=0.02)
 
 
@@ -312,7 +312,7 @@ def test_single_update_golden(name):
     m3 = torch.zeros(3, dtype=torch.float64, device=_dev())
     L.call("hb_masked_moments", L.ptr(ret), None, ret.numel(), L.ptr(m3), L.stream_ptr())
     L.call("hb_valuenorm_update", L.ptr(vn), L.ptr(m3), 0.99999, L.stream_ptr())
-    cb = L.CriticBatch(L.ptr(fl(g["c.share_obs"][:-1])), L.ptr(fl(g["c.value_preds"][:-1])), L.ptr(ret), None, T * N)
+    cb = DeviceNet.critic_batch(fl(g["c.share_obs"][:-1]), fl(g["c.value_preds"][:-1]), ret, None, T * N)
     vh = L.ValueHyper(cfg["clip_param"], cfg["huber_delta"], cfg["value_loss_coef"], 1, 1)
     cs = torch.zeros(4, dtype=torch.float64, device=_dev())
     cnet.value_grad(cb, vh, vn, 1.0 / (T * N), cs)
@@ -385,7 +385,8 @@ def test_actor_grad_vs_oracle_baseline_shapes(shape):
     np.testing.assert_allclose([s[0] / norm3[2].item(), s[1] / norm3[2].item(), s[2] / s[3]],
                                [pl.item(), ent.item(), imp.mean().item()], rtol=5e-5, atol=5e-6)
     for k, v in net.views(net.grad).items():
-        _tol_grad(v.cpu().numpy(), ref[k].numpy(), rel=5e-4)
+        # feature-norm affine grads are sums with heavy cancellation over up to 70k rows: 1e-3 of the max
+        _tol_grad(v.cpu().numpy(), ref[k].numpy(), rel=1e-3 if "feature_norm" in k else 5e-4)
     # log-prob sweep on the same rows + factor update (identity batch)
     lp_dev = torch.zeros(Rbuf, ad, device=_dev())
     fac = _cu(factor.copy())
