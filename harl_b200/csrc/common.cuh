@@ -21,10 +21,14 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                                    \
   } while (0)
 
-#define HB_LAUNCH_CHECK(what)                            \
+// Called right after every kernel launch: error check, launch counter, optional profiling event.
+void note_launch(const char* what, cudaStream_t st);
+
+#define HB_LAUNCH_DONE(st, what)                         \
   do {                                                   \
     cudaError_t _e = cudaGetLastError();                 \
     if (_e != cudaSuccess) return hb::cuda_fail(_e, what); \
+    hb::note_launch(what, st);                           \
   } while (0)
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -267,7 +267,7 @@ int hb_gae_returns(const float* rewards, float* value_preds, const float* masks,
                                                                      use_gae, use_proper_time_limits, vn_state);
   }
 #undef HB_GAE_TILED
-  HB_LAUNCH_CHECK("hb_gae_returns");
+  HB_LAUNCH_DONE((cudaStream_t)stream,"hb_gae_returns");
   return HB_OK;
 }
 
@@ -275,7 +275,7 @@ int hb_masked_moments(const float* x, const float* weight, int64_t n, double* ou
   HB_CHECK_ARG(x && out3 && n >= 0, "bad argument");
   if (n == 0) return HB_OK;
   hb::masked_moments_kernel<<<hb::stream_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(x, weight, n, out3);
-  HB_LAUNCH_CHECK("hb_masked_moments");
+  HB_LAUNCH_DONE((cudaStream_t)stream,"hb_masked_moments");
   return HB_OK;
 }
 
@@ -283,7 +283,7 @@ int hb_normalize_by_moments(const float* x, float* x_out, int64_t n, const doubl
   HB_CHECK_ARG(x && x_out && moments3 && n >= 0, "bad argument");
   if (n == 0) return HB_OK;
   hb::normalize_kernel<<<hb::stream_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(x, x_out, n, moments3);
-  HB_LAUNCH_CHECK("hb_normalize_by_moments");
+  HB_LAUNCH_DONE((cudaStream_t)stream,"hb_normalize_by_moments");
   return HB_OK;
 }
 
@@ -291,7 +291,7 @@ int hb_valuenorm_update(float* vn_state, const double* moments3, double beta, vo
   HB_CHECK_ARG(vn_state && moments3, "NULL buffer");
   // the reference multiplies by the Python doubles beta and (1 - beta), each rounded to fp32 (valuenorm.py:62-64)
   hb::valuenorm_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(vn_state, moments3, (float)beta, (float)(1.0 - beta));
-  HB_LAUNCH_CHECK("hb_valuenorm_update");
+  HB_LAUNCH_DONE((cudaStream_t)stream,"hb_valuenorm_update");
   return HB_OK;
 }
 
@@ -299,7 +299,7 @@ int hb_valuenorm_apply(const float* vn_state, const float* x, float* y, int64_t 
   HB_CHECK_ARG(vn_state && x && y && n >= 0, "bad argument");
   if (n == 0) return HB_OK;
   hb::valuenorm_apply_kernel<<<hb::stream_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(vn_state, x, y, n, denormalize);
-  HB_LAUNCH_CHECK("hb_valuenorm_apply");
+  HB_LAUNCH_DONE((cudaStream_t)stream,"hb_valuenorm_apply");
   return HB_OK;
 }
 }

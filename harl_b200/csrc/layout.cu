@@ -154,7 +154,7 @@ int prepare_launch(const hb_net_desc* d, const float* params, float* prepared, c
   int rc = make_layouts(d, &P, &Q, nullptr);
   if (rc) return rc;
   prepare_kernel<<<(Q.total + 255) / 256, 256, 0, st>>>(P, Q, d->feature_norm, d->head, d->out_dim, params, prepared);
-  HB_LAUNCH_CHECK("hb_net_prepare");
+  HB_LAUNCH_DONE(st,"hb_net_prepare");
   return HB_OK;
 }
 

@@ -35,7 +35,7 @@ int launch_featnorm_fold(const hb_net_desc* d, const float* params, float* grad,
   if (rc) return rc;
   int K = d->in_dim;
   featnorm_grad_fold_kernel<<<(K + 127) / 128, 128, 0, st>>>(params, grad, P.w[0], P.b[0], P.fn_w, P.fn_b, d->hidden[0], K);
-  HB_LAUNCH_CHECK("featnorm_grad_fold");
+  HB_LAUNCH_DONE(st,"featnorm_grad_fold");
   return HB_OK;
 }
 
@@ -143,7 +143,7 @@ int hb_clip_adam_step(const hb_net_desc* d, float* params, const float* grad, fl
   clip_adam_kernel<<<1, 1024, 0, st>>>(params, grad, exp_avg, exp_avg_sq, L.total, (float)((double)h->lr / bc1),
                                        (float)sqrt(bc2), h->beta1, h->beta2, h->eps, h->weight_decay, h->max_grad_norm,
                                        h->use_max_grad_norm, grad_norm_out);
-  HB_LAUNCH_CHECK("hb_clip_adam_step");
+  HB_LAUNCH_DONE(st,"hb_clip_adam_step");
   if (prepared) return prepare_launch(d, params, prepared, st);
   return HB_OK;
 }
@@ -154,13 +154,13 @@ int hb_rollout_insert_masks(const hb_insert_args* a, void* stream) {
   HB_CHECK_ARG(a->n_envs > 0 && a->n_agents > 0 && a->n_agents <= HB_MAX_AGENTS, "bad n_envs / n_agents");
   cudaStream_t st = (cudaStream_t)stream;
   insert_masks_kernel<<<(a->n_envs + 127) / 128, 128, 0, st>>>(*a);
-  HB_LAUNCH_CHECK("hb_rollout_insert_masks");
+  HB_LAUNCH_DONE(st,"hb_rollout_insert_masks");
   if (a->actor_rnn_row > 0 || a->critic_rnn_row > 0) {
     int64_t total = ((int64_t)a->actor_rnn_row * a->n_agents + (int64_t)a->critic_rnn_row * (a->state_type_fp ? a->n_agents : 1)) * a->n_envs;
     int64_t g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
     insert_rnn_reset_kernel<<<(unsigned)g, 256, 0, st>>>(*a);
-    HB_LAUNCH_CHECK("hb_rollout_insert_masks(rnn reset)");
+    HB_LAUNCH_DONE(st,"hb_rollout_insert_masks(rnn reset)");
   }
   return HB_OK;
 }

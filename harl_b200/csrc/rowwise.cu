@@ -48,7 +48,7 @@ int launch_feat_norm(const float* obs, int in_dim, const int32_t* index, int64_t
                      int ldx, cudaStream_t st) {
   if (rows <= 0) return HB_OK;
   feat_norm_kernel<<<row_grid(rows), ROW_THREADS, 0, st>>>(obs, in_dim, index, rows, feature_norm, xout, ldx);
-  HB_LAUNCH_CHECK("feat_norm");
+  HB_LAUNCH_DONE(st,"feat_norm");
   return HB_OK;
 }
 
@@ -109,7 +109,7 @@ int launch_ln_act_bwd(const float* dY, const float* Z, const float* stats, const
                       float* g_lnb, int64_t rows, int N, int act, cudaStream_t st) {
   if (rows <= 0) return HB_OK;
   ln_act_bwd_kernel<<<row_grid(rows), ROW_THREADS, 0, st>>>(dY, Z, stats, lnw, dZ, g_lnw, g_lnb, rows, N, act);
-  HB_LAUNCH_CHECK("ln_act_bwd");
+  HB_LAUNCH_DONE(st,"ln_act_bwd");
   return HB_OK;
 }
 
@@ -445,7 +445,7 @@ static int launch_head_mode(int head, const HeadArgs& a, cudaStream_t st) {
   if (head == HB_HEAD_DISCRETE) { HB_HEAD_DISPATCH(discrete_head_kernel) }
   else { HB_HEAD_DISPATCH(box_head_kernel) }
 #undef HB_HEAD_DISPATCH
-  HB_LAUNCH_CHECK("policy head");
+  HB_LAUNCH_DONE(st,"policy head");
   return HB_OK;
 }
 
@@ -542,7 +542,7 @@ int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st) {
     break;
   switch (hpl) { HB_V(1) HB_V(2) HB_V(4) HB_V(8) }
 #undef HB_V
-  HB_LAUNCH_CHECK("value head");
+  HB_LAUNCH_DONE(st,"value head");
   return HB_OK;
 }
 

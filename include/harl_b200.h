@@ -91,6 +91,14 @@ const char* hb_last_error(void);
 /* Asynchronous-error probe: cudaGetLastError on the calling thread (no sync). */
 int hb_sync_check(void);
 
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t hb_kernel_launch_count(void);
+/* Per-kernel timing for the roofline pass: after hb_profile_begin an event is recorded on the
+ * launching stream after every kernel; hb_profile_end synchronises and writes "label count total_ms"
+ * lines (sorted by time) into out, returning the byte count. */
+int hb_profile_begin(void* stream);
+int hb_profile_end(char* out, int out_size);
+
 /* ---- network parameter plumbing ------------------------------------------------------ */
 int hb_net_layout_of(const hb_net_desc* d, hb_net_layout* out);
 /* Derived weights the kernels read (transposed Linear weights, feature-norm affine folded

@@ -41,8 +41,12 @@ def snapshot(runner):
     cb = runner.critic_buffer
     cbuf = {k: n(getattr(cb, k)) for k in ("share_obs", "rnn_states_critic", "value_preds", "returns", "rewards", "masks",
                                            "bad_masks")}
-    actors = [{k: v.cpu().clone() for k, v in a.actor.state_dict().items()} for a in runner.actor]
-    critic = {k: v.cpu().clone() for k, v in runner.critic.critic.state_dict().items()}
+    def net_state(net):  # weights + Adam moments + step count
+        cp = lambda flat: {k: v.cpu().clone() for k, v in net.views(flat).items()}
+        return dict(p=cp(net.params), m=cp(net.exp_avg), v=cp(net.exp_avg_sq), t=net.adam_steps)
+
+    actors = [net_state(a.actor) for a in runner.actor]
+    critic = net_state(runner.critic.critic)
     vn = None if runner.value_normalizer is None else n(runner.value_normalizer.state)
     return abufs, cbuf, actors, critic, vn
 
@@ -59,12 +63,14 @@ def oracle_iteration(runner, snap, agent_order):
         vn = ob.ValueNormState()
         vn.running_mean, vn.running_mean_sq, vn.debiasing_term = (np.float32(x) for x in vn_state)
     heads = [sp.__class__.__name__ for sp in runner.envs.action_space]
-    o_actors = []
-    for p in actors:
-        p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-        o_actors.append((p, oa.Adam(p, cfg["lr"], cfg["opti_eps"], cfg["weight_decay"])))
-    pc = {k: v.clone().requires_grad_(True) for k, v in critic.items()}
-    o_critic = (pc, oa.Adam(pc, cfg["critic_lr"], cfg["opti_eps"], cfg["weight_decay"]))
+    def oracle_net(st, lr):
+        p = {k: v.clone().requires_grad_(True) for k, v in st["p"].items()}
+        opt = oa.Adam(p, lr, cfg["opti_eps"], cfg["weight_decay"])
+        opt.m, opt.v, opt.t = {k: v.clone() for k, v in st["m"].items()}, {k: v.clone() for k, v in st["v"].items()}, st["t"]
+        return p, opt
+
+    o_actors = [oracle_net(st, cfg["lr"]) for st in actors]
+    o_critic = oracle_net(critic, cfg["critic_lr"])
     ident = lambda m: np.arange(m)
     infos, cinfo, factors, _ = oa.ha_train(o_actors, o_critic, cfg, heads, abufs, cbuf, vn, runner.state_type,
                                            agent_order, ident)
@@ -102,8 +108,10 @@ def check_iteration(runner, tol_w=3e-5, tol_info=2e-4):
         vn = ob.ValueNormState()
         vn.running_mean, vn.running_mean_sq, vn.debiasing_term = (np.float32(x) for x in vn_state)
     algo = runner.algo_args["algo"]
+    # the bootstrap value sits in value_preds[-1] (GAE branches) or returns[-1] (plain returns)
+    next_value = cbuf["value_preds"][-1] if algo["use_gae"] else cbuf["returns"][-1]
     ret, _ = ob.compute_returns(cbuf["rewards"], cbuf["value_preds"], cbuf["masks"], cbuf["bad_masks"],
-                                cbuf["value_preds"][-1], algo["gamma"], algo["gae_lambda"], algo["use_gae"],
+                                next_value, algo["gamma"], algo["gae_lambda"], algo["use_gae"],
                                 runner.algo_args["train"]["use_proper_time_limits"], vn)
     assert np.array_equal(ret[:-1], cbuf["returns"][:-1]), "returns differ from the oracle"
     adv = ob.advantages(ret, cbuf["value_preds"], vn)
@@ -114,22 +122,29 @@ def check_iteration(runner, tol_w=3e-5, tol_info=2e-4):
     torch.cuda.synchronize()
     order = [int(a) for a in runner.last_agent_order]
     o_infos, o_cinfo, o_factors, o_actors, o_critic, o_vn = oracle_iteration(runner, snap, order)
+    errs = []
+
+    def cmp(got, want, msg, **kw):
+        try:
+            np.testing.assert_allclose(got, want, err_msg=msg, **kw)
+        except AssertionError as e:
+            lines = str(e).strip().splitlines()
+            errs.append(f"{msg}: " + " | ".join(l.strip() for l in lines[3:6]))
+
     for a in range(runner.num_agents):
-        np.testing.assert_allclose(runner.actor_buffer[a].factor.cpu().numpy(), o_factors[a], rtol=3e-4, atol=3e-5,
-                                   err_msg=f"factor of agent {a}")
+        cmp(runner.actor_buffer[a].factor.cpu().numpy(), o_factors[a], f"factor[{a}]", rtol=3e-4, atol=3e-5)
         for k in ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio"):
-            np.testing.assert_allclose(infos[a][k], o_infos[a][k], rtol=tol_info, atol=tol_info, err_msg=f"{k}[{a}]")
+            cmp(infos[a][k], o_infos[a][k], f"{k}[{a}]", rtol=tol_info, atol=tol_info)
         for k, v in runner.actor[a].actor.state_dict().items():
-            np.testing.assert_allclose(v.cpu().numpy(), o_actors[a][0][k].detach().numpy(), rtol=0, atol=tol_w,
-                                       err_msg=f"actor{a}/{k}")
-    np.testing.assert_allclose([cinfo["value_loss"], cinfo["critic_grad_norm"]],
-                               [o_cinfo["value_loss"], o_cinfo["critic_grad_norm"]], rtol=tol_info)
+            cmp(v.cpu().numpy(), o_actors[a][0][k].detach().numpy(), f"actor{a}/{k}", rtol=0, atol=tol_w)
+    cmp([cinfo["value_loss"], cinfo["critic_grad_norm"]], [o_cinfo["value_loss"], o_cinfo["critic_grad_norm"]],
+        "critic info", rtol=tol_info)
     for k, v in runner.critic.critic.state_dict().items():
-        np.testing.assert_allclose(v.cpu().numpy(), o_critic[0][k].detach().numpy(), rtol=0, atol=tol_w,
-                                   err_msg=f"critic/{k}")
+        cmp(v.cpu().numpy(), o_critic[0][k].detach().numpy(), f"critic/{k}", rtol=0, atol=tol_w)
     if o_vn is not None:
-        np.testing.assert_allclose(runner.value_normalizer.state.cpu().numpy(),
-                                   [o_vn.running_mean, o_vn.running_mean_sq, o_vn.debiasing_term], rtol=1e-5)
+        cmp(runner.value_normalizer.state.cpu().numpy(), [o_vn.running_mean, o_vn.running_mean_sq, o_vn.debiasing_term],
+            "valuenorm state", rtol=1e-5)
+    assert not errs, f"agent order {order}; {len(errs)} mismatches:\n" + "\n".join(errs)
     runner.after_update()
     return infos, cinfo
 
