@@ -1,0 +1,313 @@
+"""Benchmark of the HAPPO on-policy hot path (BASELINE.json metric: env-steps/sec, whole box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W     (N > 1)
+
+One "step" = one full training iteration of the runner on synthetic tensors of the workload's
+shapes: T x (collect -> env.step -> insert) -> GAE -> sequential-agent HAPPO update -> critic update
+-> after_update.  value = T * N_global / seconds per iteration, the reference's own FPS formula
+(harl/common/base_logger.py:70-87; agents do not multiply the count).  Weak scaling: every GPU
+keeps the workload's n_rollout_threads, so N_global = N * n_rollout_threads.
+
+Rank 0 prints ONE JSON line.  Extra objects (see DESIGN.md "Measurement"):
+  roofline      dominant kernel of the step, timed live with CUDA events on the launching stream
+  cpu_baseline  the CPU oracle port of the reference, timed on this box's host cores (N=1 only)
+  e2e           same metric with the env on the HOST: pinned H2D of every env output and D2H of the
+                actions each rollout step, plus the D2H of the train infos, inside the timed region
+--impl reference times the oracle CPU port (the reference is pure Python/PyTorch; it is not
+installable on the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# BASELINE.json configs.  C2 is the configuration the metric is quoted on.
+WORKLOADS = {
+    "C1": dict(desc="HAPPO pettingzoo_mpe simple_spread_v2 3 agents n_rollout_threads=8 (synthetic tensors)",
+               env="pettingzoo_mpe", env_args=dict(scenario="simple_spread_v2", continuous_actions=False), n=8, T=200,
+               hidden=[128, 128], algo={}),
+    "C2": dict(desc="HAPPO synthetic-MPE obs_dim=18 act_dim=5 3 agents n_rollout_threads=4096 T=200",
+               env="pettingzoo_mpe", env_args=dict(scenario="simple_spread_v2", continuous_actions=False), n=4096, T=200,
+               hidden=[128, 128], algo={}),
+    "C3": dict(desc="HAPPO MAMuJoCo HalfCheetah-v2 6x1 continuous n_rollout_threads=1024 T=200",
+               env="mamujoco", env_args=dict(scenario="HalfCheetah-v2", agent_conf="6x1"), n=1024, T=200,
+               hidden=[128, 128, 128], algo=dict(clip_param=0.05, ppo_epoch=15, critic_epoch=15)),
+    "C5": dict(desc="HAPPO MAMuJoCo Humanoid-v2 17x1 n_rollout_threads=1024 per GPU T=200",
+               env="mamujoco", env_args=dict(scenario="Humanoid-v2", agent_conf="17x1"), n=1024, T=200,
+               hidden=[128, 128, 128], algo=dict(clip_param=0.1, entropy_coef=0.0)),
+}
+
+
+def make_args(wl, world, host_env=False, n_override=None):
+    from harl_b200.utils.configs_tools import get_defaults_yaml_args
+
+    w = WORKLOADS[wl]
+    algo_args, env_args = get_defaults_yaml_args("happo", w["env"])
+    env_args.update(w["env_args"])
+    env_args["host"] = host_env
+    n = n_override or w["n"]
+    algo_args["train"].update(n_rollout_threads=n * world, episode_length=w["T"], num_env_steps=10**12,
+                              log_interval=10**9, eval_interval=10**9)
+    algo_args["eval"]["use_eval"] = False
+    algo_args["model"]["hidden_sizes"] = list(w["hidden"])
+    algo_args["algo"].update(w["algo"])
+    algo_args["logger"]["log_dir"] = tempfile.mkdtemp(prefix="harl_b200_bench_")
+    args = dict(algo="happo", env=w["env"], exp_name="bench", load_config="")
+    return args, algo_args, env_args
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def timed_iterations(runner, steps, warmup, torch, dist_on, sample_clocks=False):
+    """W untimed + K timed iterations, CUDA events, barrier + synchronize on both sides, max over ranks."""
+    ep = getattr(runner, "_bench_episode", 0)
+    for _ in range(warmup):
+        ep += 1
+        runner.run_iteration(ep, 10**9)
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    sampler = None
+    if sample_clocks:
+        sampler = ClockSampler(torch.cuda.current_device())
+        sampler.start()
+    from harl_b200 import _lib as L
+
+    l0 = L.lib.hb_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        ep += 1
+        runner.run_iteration(ep, 10**9)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = L.lib.hb_kernel_launch_count() - l0
+    if dist_on:
+        torch.distributed.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if dist_on:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    runner._bench_episode = ep
+    return ms.item(), launches, (sampler.summary() if sampler else None)
+
+
+def kernel_profile(runner, torch):
+    """One extra iteration with an event after every kernel launch -> [(label, count, total_ms)]."""
+    from harl_b200 import _lib as L
+
+    torch.cuda.synchronize()
+    L.call("hb_profile_begin", L.stream_ptr())
+    runner._bench_episode += 1
+    runner.run_iteration(runner._bench_episode, 10**9)
+    buf = C.create_string_buffer(1 << 16)
+    n = L.lib.hb_profile_end(buf, len(buf))
+    rows = []
+    for line in buf.raw[:max(n, 0)].decode().strip().splitlines():
+        label, cnt, ms = line.rsplit(" ", 2)
+        rows.append((label, int(cnt), float(ms)))
+    return rows
+
+
+def roofline_of(rows, peaks):
+    """Roofline entry for the kernel label with the largest share of the step.
+
+    GEMM kernels (the MLP layers -- tensor-pipe work by BASELINE.json's own classification) are rated
+    in FLOP/s against the measured dense bf16 peak; everything else in algorithmic bytes against HBM."""
+    import re
+
+    total = sum(r[2] for r in rows) or 1.0
+    label, cnt, ms = rows[0]
+    out = {"kernel": label, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share_of_step": ms / total,
+           "top5": [{"kernel": r[0], "launches": r[1], "share": round(r[2] / total, 4)} for r in rows[:5]]}
+    m = re.match(r"(\w+)\[M(\d+),N(\d+),K(\d+)\]", label)
+    tf_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+    if m:
+        M, N, K = int(m.group(2)), int(m.group(3)), int(m.group(4))
+        flops = 2.0 * M * N * K
+        ach = flops / (1e-3 * ms / cnt) / 1e12
+        out.update(bound="tensor", achieved=ach, peak=tf_peak, unit="TFLOP/s", frac=ach / tf_peak,
+                   flops_per_launch=flops, peak_source=peaks["_source"] + " (bf16 dense, sustained)",
+                   note="fp32 SIMT FFMA kernel; rated against the tensor-pipe peak the MLP GEMMs are bound by")
+    else:
+        out.update(bound="hbm", achieved=None, peak=peaks.get("hbm_gbs"), unit="GB/s", frac=None,
+                   peak_source=peaks["_source"])
+    tr = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    out["traffic"] = None
+    if os.path.exists(tr):
+        try:
+            out["traffic"] = json.load(open(tr)).get(label.split("[")[0])
+        except Exception:
+            pass
+    return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "MEASURED_PEAKS.json (of measured)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def cpu_reference_run(wl, steps, warmup, n_sample):
+    """The CPU oracle port on a bounded sample (n_sample rollout threads) of the workload."""
+    import torch
+
+    from harl_b200.envs.synthetic import resolve_shapes
+    from oracle.runner import NumpySyntheticEnv, OracleRunner
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args, algo_args, env_args = make_args(wl, 1, n_override=n_sample)
+    cfg = {**algo_args["model"], **algo_args["algo"], **algo_args["train"]}
+    shapes = resolve_shapes(args["env"], env_args)
+    env = NumpySyntheticEnv(shapes, n_sample, seed=1)
+    r = OracleRunner(cfg, env, state_type=shapes["state_type"], seed=1)
+    r.warmup()
+    for _ in range(warmup):
+        r.run_iteration()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r.run_iteration()
+    dt = (time.perf_counter() - t0) / steps
+    T = cfg["episode_length"]
+    return dict(value=T * n_sample / dt, unit="env-steps/s", cores=cores, kind="port", seconds_per_step=dt,
+                sample=f"{WORKLOADS[wl]['desc']} with n_rollout_threads reduced to {n_sample} "
+                       f"(cost is linear in n_rollout_threads); {steps} full iteration(s) of the oracle CPU port, "
+                       f"torch threads={cores}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=256, help="n_rollout_threads of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    wl = WORKLOADS[a.workload]
+    T = wl["T"]
+    base = dict(metric="env-steps/sec (whole box) HAPPO update loop", unit="env-steps/s", n_gpus=a.gpus, steps=a.steps,
+                warmup=a.warmup, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config={"workload": f"{a.workload}: {wl['desc']}", "n_rollout_threads_per_gpu": wl["n"],
+                        "episode_length": T, "algo": "happo",
+                        "l2_policy": "rollout buffers + activations per iteration exceed the 126 MB L2 (no flush needed)"})
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        n_sample = min(a.cpu_sample * 2, wl["n"])
+        res = cpu_reference_run(a.workload, max(1, a.steps), min(a.warmup, 1), n_sample)
+        line = dict(base, impl="reference", value=res["value"], ms_per_step=1e3 * res["seconds_per_step"],
+                    cpu_baseline=res, gpu_launches=0,
+                    e2e={"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        line["config"]["reference_note"] = ("PKU-MARL/HARL is pure Python and /root/reference is not on the GPU box; this arm "
+                                            "times the oracle CPU port of the same path (kind=port)")
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: harl_b200 has no CPU fallback")
+    dist_on = world > 1
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    args, algo_args, env_args = make_args(a.workload, world)
+    runner = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+    runner.warmup()
+    runner.logger.init(10**9)
+    ms, launches, clocks = timed_iterations(runner, a.steps, a.warmup, torch, dist_on, sample_clocks=(rank == 0))
+    n_global = wl["n"] * world
+    value = T * n_global * a.steps / (ms / 1e3)
+    line = dict(base, value=value, ms_per_step=ms / a.steps, gpu_launches=int(launches), clocks=clocks)
+    # ---- roofline of the dominant kernel (separate profiled iteration, same stream)
+    rows = kernel_profile(runner, torch)
+    if rank == 0 and rows:
+        line["roofline"] = roofline_of(rows, load_peaks())
+    env_ms = None
+    runner.close()
+    del runner
+    torch.cuda.empty_cache()
+    # ---- end to end: host-resident env (pinned H2D of env outputs, D2H of actions, every rollout step)
+    if not a.no_e2e:
+        args, algo_args, env_args = make_args(a.workload, world, host_env=True)
+        r2 = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+        r2.warmup()
+        r2.logger.init(10**9)
+        ms2, _, _ = timed_iterations(r2, max(1, min(a.steps, 3)), 1, torch, dist_on)
+        k2 = max(1, min(a.steps, 3))
+        A, N = r2.num_agents, wl["n"]
+        od = r2.envs.observation_space[0].shape[0]
+        sd = r2.envs.share_observation_space[0].shape[0]
+        aw = r2.actor[0].actor.act_width
+        na = r2.actor[0].actor.out_dim if r2.actor_buffer[0].available_actions is not None else 0
+        h2d = T * N * (A * od * 4 + sd * 4 + 4 + A + A + A * na * 4)  # obs, state, reward, dones, bad flags, avail
+        d2h = T * N * A * aw * 4 + (4 * A + 2) * 8
+        line["e2e"] = {"value": T * n_global * k2 / (ms2 / 1e3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / k2,
+                       "what": "runner.run_iteration with the env on the host: pinned H2D of obs/state/reward/done/avail and "
+                               "D2H of the actions every rollout step, D2H of the train infos every iteration"}
+        r2.close()
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_run(a.workload, 1, 1, min(a.cpu_sample, wl["n"]))
+    if rank == 0:
+        print(json.dumps(line))
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

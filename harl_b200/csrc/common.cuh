@@ -23,6 +23,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // Called right after every kernel launch: error check, launch counter, optional profiling event.
 void note_launch(const char* what, cudaStream_t st);
+const char* shape_label(const char* base, int64_t m, int n, int k);
 
 #define HB_LAUNCH_DONE(st, what)                         \
   do {                                                   \

@@ -371,7 +371,7 @@ static int launch_fwd_nt(int act, const float* X, int ldx, const float* WT, cons
     default: set_error("activation %d", act); return HB_ERR_UNSUPPORTED;
   }
 #undef HB_FWD_CASE
-  HB_LAUNCH_DONE(st,"linear_ln_fwd");
+  HB_LAUNCH_DONE(st, shape_label("linear_ln_fwd", M, N, Kred));
   return HB_OK;
 }
 
@@ -400,7 +400,7 @@ static int launch_dx_nt(int act, const float* dZ, int N, const float* W, const f
     default: set_error("activation %d", act); return HB_ERR_UNSUPPORTED;
   }
 #undef HB_DX_CASE
-  HB_LAUNCH_DONE(st,"dx_ln_bwd");
+  HB_LAUNCH_DONE(st, shape_label("dx_ln_bwd", M, Np, N));
   return HB_OK;
 }
 
@@ -427,7 +427,7 @@ int launch_dw_accum(const float* dZ, int N, const float* X, int ldx, int K, floa
   dim3 grid((unsigned)splits, nb, kb);
   if (small) dw_accum_kernel<32><<<grid, 256, 0, st>>>(dZ, N, X, ldx, K, dW, db, M, rows_per);
   else dw_accum_kernel<128><<<grid, 256, 0, st>>>(dZ, N, X, ldx, K, dW, db, M, rows_per);
-  HB_LAUNCH_DONE(st,"dw_accum");
+  HB_LAUNCH_DONE(st, shape_label("dw_accum", M, N, K));
   return HB_OK;
 }
 

@@ -31,6 +31,20 @@ void note_launch(const char* what, cudaStream_t st) {
   g_marks.push_back({ev, what});
 }
 
+// Shape-qualified label, interned for the process lifetime; plain `base` when profiling is off.
+const char* shape_label(const char* base, int64_t m, int n, int k) {
+  if (!g_profiling.load(std::memory_order_relaxed)) return base;
+  static std::map<std::string, const char*> interned;
+  char buf[96];
+  snprintf(buf, sizeof buf, "%s[M%lld,N%d,K%d]", base, (long long)m, n, k);
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = interned.find(buf);
+  if (it != interned.end()) return it->second;
+  char* keep = strdup(buf);
+  interned[buf] = keep;
+  return keep;
+}
+
 }  // namespace hb
 
 extern "C" {

@@ -61,7 +61,10 @@ class SyntheticBatchedEnv:
     def __init__(self, env_name, seed, n_threads, env_args, device=None, pool=16):
         c = resolve_shapes(env_name, env_args)
         self.cfg = c
-        self.device = torch.device(device if device is not None else "cpu")
+        # host=True: behave like a CPU simulator -- outputs live in pinned host memory and the actions
+        # are pulled to the host every step (bench.py's end-to-end measurement).
+        self.host = bool(env_args.get("host", False))
+        self.device = torch.device("cpu" if self.host or device is None else device)
         self.n_threads = N = int(n_threads)
         self.n_agents = A = int(c["n_agents"])
         self.state_type = c["state_type"]
@@ -74,7 +77,8 @@ class SyntheticBatchedEnv:
         self.death_prob, self.terminate_prob, self.avail_prob = (float(c[k]) for k in ("death_prob", "terminate_prob", "avail_prob"))
         self.pool = K = int(pool)
         g = torch.Generator(device="cpu").manual_seed(int(seed) * 7919 + 1234)
-        rn = lambda *s: torch.randn(*s, generator=g).to(self.device)
+        pin = (lambda t: t.pin_memory()) if self.host and torch.cuda.is_available() else (lambda t: t)
+        rn = lambda *s: pin(torch.randn(*s, generator=g)).to(self.device)
         # agent-major pools so that obs[:, a] is contiguous for the per-agent buffers
         self._obs = rn(K, A, N, od)
         self._state = rn(K, N, sd) if self.state_type == "EP" else rn(K, N, A, sd)
@@ -129,6 +133,8 @@ class SyntheticBatchedEnv:
         """actions [N, A, ad] (ignored by the synthetic dynamics). Returns the reference 6-tuple."""
         self._t += 1
         self.steps_served += 1
+        if self.host and torch.is_tensor(actions):
+            self.last_actions = actions.to("cpu")  # the simulator consumes the actions on the host
         k = self._t % self.pool
         obs, share = self._views(k)
         rewards = self._rew[k].expand(-1, self.n_agents, -1)
