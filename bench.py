@@ -136,11 +136,26 @@ def kernel_profile(runner, torch):
     from harl_b200 import _lib as L
 
     torch.cuda.synchronize()
-    L.call("hb_profile_begin", L.stream_ptr())
+    runner.time_phases = True
     runner._bench_episode += 1
-    runner.run_iteration(runner._bench_episode, 10**9)
+    runner.run_iteration(runner._bench_episode, 10**9)  # phase timers without per-kernel events
+    runner.time_phases = False
+    # Profile the update phase only: there the host runs far ahead of the device, so the gap between
+    # consecutive post-launch events is the kernel's own duration.  (In the rollout the device waits for
+    # Python between steps and the gaps would be charged to the kernels.)
+    runner._bench_episode += 1
+    runner.logger.episode_init(runner._bench_episode)
+    for step in range(runner.algo_args["train"]["episode_length"]):
+        values, actions, logp, rnn, rnn_c = runner.collect(step)
+        obs, share_obs, rewards, dones, infos, avail = runner.envs.step(actions)
+        runner.insert((obs, share_obs, rewards, dones, infos, avail, values, actions, logp, rnn, rnn_c))
+    runner.compute()
+    torch.cuda.synchronize()
+    L.call("hb_profile_begin", L.stream_ptr())
+    runner.train()
     buf = C.create_string_buffer(1 << 16)
     n = L.lib.hb_profile_end(buf, len(buf))
+    runner.after_update()
     rows = []
     for line in buf.raw[:max(n, 0)].decode().strip().splitlines():
         label, cnt, ms = line.rsplit(" ", 2)
@@ -157,7 +172,8 @@ def roofline_of(rows, peaks):
 
     total = sum(r[2] for r in rows) or 1.0
     label, cnt, ms = rows[0]
-    out = {"kernel": label, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share_of_step": ms / total,
+    out = {"kernel": label, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share_of_update_phase": ms / total,
+           "scope": "update phase (runner.train) of one iteration; phases in config.phases_ms",
            "top5": [{"kernel": r[0], "launches": r[1], "share": round(r[2] / total, 4)} for r in rows[:5]]}
     m = re.match(r"(\w+)\[M(\d+),N(\d+),K(\d+)\]", label)
     tf_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
@@ -197,15 +213,24 @@ def cpu_reference_run(wl, steps, warmup, n_sample):
     from harl_b200.envs.synthetic import resolve_shapes
     from oracle.runner import NumpySyntheticEnv, OracleRunner
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     args, algo_args, env_args = make_args(wl, 1, n_override=n_sample)
     cfg = {**algo_args["model"], **algo_args["algo"], **algo_args["train"]}
     shapes = resolve_shapes(args["env"], env_args)
     env = NumpySyntheticEnv(shapes, n_sample, seed=1)
     r = OracleRunner(cfg, env, state_type=shapes["state_type"], seed=1)
     r.warmup()
-    for _ in range(warmup):
+    # thread count: the reference default (torch_threads=4, happo.yaml:13) and wider settings are probed on one
+    # iteration each; the fastest is used (tiny per-step tensors make "all cores" slower than a few threads)
+    ncpu = os.cpu_count() or 1
+    probe = {}
+    for th in sorted({4, min(16, ncpu), min(32, ncpu)}):
+        torch.set_num_threads(th)
+        t0 = time.perf_counter()
+        r.run_iteration()
+        probe[th] = time.perf_counter() - t0
+    cores = min(probe, key=probe.get)
+    torch.set_num_threads(cores)
+    for _ in range(max(0, warmup - 1)):
         r.run_iteration()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -213,9 +238,10 @@ def cpu_reference_run(wl, steps, warmup, n_sample):
     dt = (time.perf_counter() - t0) / steps
     T = cfg["episode_length"]
     return dict(value=T * n_sample / dt, unit="env-steps/s", cores=cores, kind="port", seconds_per_step=dt,
+                host_cpus=ncpu, thread_probe_s={str(k): round(v, 3) for k, v in probe.items()},
                 sample=f"{WORKLOADS[wl]['desc']} with n_rollout_threads reduced to {n_sample} "
                        f"(cost is linear in n_rollout_threads); {steps} full iteration(s) of the oracle CPU port, "
-                       f"torch threads={cores}")
+                       f"torch threads={cores} (fastest of {sorted(probe)})")
 
 
 def main():
@@ -228,6 +254,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256, help="n_rollout_threads of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write the per-kernel event profile of one iteration here")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -276,6 +303,15 @@ def main():
     rows = kernel_profile(runner, torch)
     if rank == 0 and rows:
         line["roofline"] = roofline_of(rows, load_peaks())
+        line["config"]["phases_ms"] = {k: round(v, 3) for k, v in getattr(runner, "phase_ms", {}).items()}
+        if a.profile_out:
+            tot = sum(r[2] for r in rows)
+            with open(a.profile_out, "w") as fh:
+                fh.write(f"# per-kernel CUDA-event profile of the update phase of one {a.workload} iteration (event after every launch)\n")
+                fh.write(f"# total {tot:.3f} ms over {sum(r[1] for r in rows)} launches\n")
+                for lab, cnt, ms_ in rows:
+                    fh.write(f"{lab:48s} n={cnt:6d} total={ms_:9.3f} ms avg={1e3 * ms_ / cnt:8.2f} us share={ms_ / tot:6.3f}\n")
+                fh.write("# phases (ms, one iteration): " + json.dumps(getattr(runner, "phase_ms", {})) + "\n")
     env_ms = None
     runner.close()
     del runner

@@ -44,11 +44,55 @@ __global__ void __launch_bounds__(ROW_THREADS) feat_norm_kernel(const float* __r
   }
 }
 
+// Narrow rows (in_dim <= 44: MPE / MAMuJoCo observations): one thread per row.  A CTA stages 256 rows through
+// shared memory with fully coalesced global loads / stores (row pitch in_dim+1 -> conflict-free per-thread walks).
+__global__ void __launch_bounds__(256) feat_norm_narrow_kernel(const float* __restrict__ obs, int in_dim,
+                                                               const int32_t* __restrict__ index, int64_t rows,
+                                                               int feature_norm, float* __restrict__ xout, int ldx) {
+  extern __shared__ float srow[];
+  const int pitch = (in_dim > ldx ? in_dim : ldx) + 1;
+  const int64_t r0 = (int64_t)blockIdx.x * 256;
+  const int nrows = (int)(rows - r0 < 256 ? rows - r0 : 256);
+  if (index == nullptr) {
+    const float* base = obs + r0 * in_dim;
+    for (int f = threadIdx.x; f < nrows * in_dim; f += 256) srow[(f / in_dim) * pitch + f % in_dim] = base[f];
+  } else {
+    for (int f = threadIdx.x; f < nrows * in_dim; f += 256) {
+      int r = f / in_dim, k = f % in_dim;
+      srow[r * pitch + k] = obs[(int64_t)index[r0 + r] * in_dim + k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nrows) {
+    float* o = srow + threadIdx.x * pitch;
+    float mean = 0.f, rstd = 1.f;
+    if (feature_norm) {
+      float s = 0.f;
+      for (int k = 0; k < in_dim; ++k) s += o[k];
+      mean = s / (float)in_dim;
+      float q = 0.f;
+      for (int k = 0; k < in_dim; ++k) { float dlt = o[k] - mean; q = fmaf(dlt, dlt, q); }
+      rstd = rsqrtf(q / (float)in_dim + 1e-5f);
+    }
+    for (int k = 0; k < ldx; ++k) o[k] = k < in_dim ? (o[k] - mean) * rstd : 0.f;
+  }
+  __syncthreads();
+  float* out = xout + r0 * ldx;
+  for (int f = threadIdx.x; f < nrows * ldx; f += 256) out[f] = srow[(f / ldx) * pitch + f % ldx];
+}
+
 int launch_feat_norm(const float* obs, int in_dim, const int32_t* index, int64_t rows, int feature_norm, float* xout,
                      int ldx, cudaStream_t st) {
   if (rows <= 0) return HB_OK;
+  if (in_dim <= 44) {
+    size_t smem = (size_t)256 * ((in_dim > ldx ? in_dim : ldx) + 1) * sizeof(float);
+    feat_norm_narrow_kernel<<<(unsigned)ceil_div64(rows, 256), 256, smem, st>>>(obs, in_dim, index, rows, feature_norm,
+                                                                              xout, ldx);
+    HB_LAUNCH_DONE(st, shape_label("feat_norm", rows, ldx, in_dim));
+    return HB_OK;
+  }
   feat_norm_kernel<<<row_grid(rows), ROW_THREADS, 0, st>>>(obs, in_dim, index, rows, feature_norm, xout, ldx);
-  HB_LAUNCH_DONE(st,"feat_norm");
+  HB_LAUNCH_DONE(st, shape_label("feat_norm", rows, ldx, in_dim));
   return HB_OK;
 }
 
@@ -109,7 +153,7 @@ int launch_ln_act_bwd(const float* dY, const float* Z, const float* stats, const
                       float* g_lnb, int64_t rows, int N, int act, cudaStream_t st) {
   if (rows <= 0) return HB_OK;
   ln_act_bwd_kernel<<<row_grid(rows), ROW_THREADS, 0, st>>>(dY, Z, stats, lnw, dZ, g_lnw, g_lnb, rows, N, act);
-  HB_LAUNCH_DONE(st,"ln_act_bwd");
+  HB_LAUNCH_DONE(st, shape_label("ln_act_bwd", rows, N, 0));
   return HB_OK;
 }
 
@@ -445,7 +489,7 @@ static int launch_head_mode(int head, const HeadArgs& a, cudaStream_t st) {
   if (head == HB_HEAD_DISCRETE) { HB_HEAD_DISPATCH(discrete_head_kernel) }
   else { HB_HEAD_DISPATCH(box_head_kernel) }
 #undef HB_HEAD_DISPATCH
-  HB_LAUNCH_DONE(st,"policy head");
+  HB_LAUNCH_DONE(st, shape_label(MODE == MODE_GRAD ? "policy_head_grad" : MODE == MODE_EVAL ? "policy_head_eval" : "policy_head_act", a.rows, a.out, a.h));
   return HB_OK;
 }
 
@@ -542,7 +586,7 @@ int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st) {
     break;
   switch (hpl) { HB_V(1) HB_V(2) HB_V(4) HB_V(8) }
 #undef HB_V
-  HB_LAUNCH_DONE(st,"value head");
+  HB_LAUNCH_DONE(st, shape_label(grad ? "value_head_grad" : "value_head_fwd", a.rows, 1, a.h));
   return HB_OK;
 }
 

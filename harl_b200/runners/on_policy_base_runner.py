@@ -126,6 +126,7 @@ class OnPolicyBaseRunner:
             self.critic.lr_decay(episode, episodes)
         self.logger.episode_init(episode)
         self.prep_rollout()
+        marks = self._phase_mark(None, None)
         for step in range(tr["episode_length"]):
             values, actions, action_log_probs, rnn_states, rnn_states_critic = self.collect(step)
             obs, share_obs, rewards, dones, infos, available_actions = self.envs.step(actions)
@@ -133,9 +134,12 @@ class OnPolicyBaseRunner:
                     rnn_states, rnn_states_critic)
             self.logger.per_step(data)
             self.insert(data)
+        marks = self._phase_mark(marks, "rollout")
         self.compute()
+        marks = self._phase_mark(marks, "compute")
         self.prep_training()
         actor_train_infos, critic_train_info = self.train()
+        marks = self._phase_mark(marks, "train")
         if episode % tr["log_interval"] == 0 and self.rank == 0:
             self.logger.episode_log(actor_train_infos, critic_train_info, self.actor_buffer, self.critic_buffer)
         if episode % tr["eval_interval"] == 0:
@@ -145,7 +149,20 @@ class OnPolicyBaseRunner:
             if self.rank == 0:
                 self.save()
         self.after_update()
+        self._phase_mark(marks, "after_update", final=True)
         self.last_train_infos = (actor_train_infos, critic_train_info)
+
+    def _phase_mark(self, marks, name, final=False):
+        """CUDA-event phase timers (only when ``self.time_phases`` is set; one sync at the end of the iteration)."""
+        if not getattr(self, "time_phases", False) or self.device.type != "cuda":
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks = (marks or []) + [(name, ev)]
+        if final:
+            torch.cuda.synchronize()
+            self.phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+        return marks
 
     def warmup(self):
         """Reset the envs and fill slot 0 (reference :269-283)."""
