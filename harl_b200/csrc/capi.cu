@@ -67,8 +67,14 @@ static int trunk_forward(const hb_net_desc* d, const PrepLayout& Q, const float*
   const float* x = w.x0;
   int ldx = Q.kpad[0];
   for (int l = 0; l < Q.n_layers; ++l) {
-    rc = launch_linear_ln_fwd(d->activation, x, ldx, prep + Q.wt[l], prep + Q.bias[l], prep + Q.lnw[l], prep + Q.lnb[l],
-                              w.Z[l], w.Y[l], w.stats[l], rows, Q.n[l], Q.kpad[l], st);
+    const int impl = gemm_impl();
+    if (impl != 0)
+      rc = launch_tc_linear_ln_fwd(impl == 1 ? 3 : 1, d->activation, x, ldx, prep + Q.tk[l], Q.tk_chunks[l],
+                                   prep + Q.bias[l], prep + Q.lnw[l], prep + Q.lnb[l], w.Z[l], w.Y[l], w.stats[l], rows,
+                                   Q.n[l], Q.kpad[l], st);
+    else
+      rc = launch_linear_ln_fwd(d->activation, x, ldx, prep + Q.wt[l], prep + Q.bias[l], prep + Q.lnw[l], prep + Q.lnb[l],
+                                w.Z[l], w.Y[l], w.stats[l], rows, Q.n[l], Q.kpad[l], st);
     if (rc) return rc;
     x = w.Y[l];
     ldx = Q.n[l];
@@ -85,14 +91,26 @@ static int trunk_backward(const hb_net_desc* d, const ParamLayout& P, const Prep
   int rc = launch_ln_act_bwd(dcur, w.Z[L - 1], w.stats[L - 1], prep + Q.lnw[L - 1], dcur, grad + P.lnw[L - 1],
                              grad + P.lnb[L - 1], rows, Q.n[L - 1], d->activation, st);
   if (rc) return rc;
+  const int impl = gemm_impl();
+  const int passes = impl == 1 ? 3 : 1;
   for (int l = L - 1; l >= 1; --l) {
-    rc = launch_dw_accum(dcur, Q.n[l], w.Y[l - 1], Q.n[l - 1], Q.k[l], grad + P.w[l], grad + P.b[l], rows, st);
+    if (impl != 0)
+      rc = launch_tc_dw_accum(passes, dcur, Q.n[l], w.Y[l - 1], Q.n[l - 1], Q.k[l], grad + P.w[l], grad + P.b[l], rows, st);
+    else
+      rc = launch_dw_accum(dcur, Q.n[l], w.Y[l - 1], Q.n[l - 1], Q.k[l], grad + P.w[l], grad + P.b[l], rows, st);
     if (rc) return rc;
-    rc = launch_dx_ln_bwd(d->activation, dcur, Q.n[l], params + P.w[l], w.Z[l - 1], w.stats[l - 1], prep + Q.lnw[l - 1],
-                          dnext, grad + P.lnw[l - 1], grad + P.lnb[l - 1], rows, Q.n[l - 1], st);
+    if (impl != 0)
+      rc = launch_tc_dx_ln_bwd(passes, d->activation, dcur, Q.n[l], prep + Q.tkt[l], Q.tkt_chunks[l], w.Z[l - 1],
+                               w.stats[l - 1], prep + Q.lnw[l - 1], dnext, grad + P.lnw[l - 1], grad + P.lnb[l - 1], rows,
+                               Q.n[l - 1], st);
+    else
+      rc = launch_dx_ln_bwd(d->activation, dcur, Q.n[l], params + P.w[l], w.Z[l - 1], w.stats[l - 1], prep + Q.lnw[l - 1],
+                            dnext, grad + P.lnw[l - 1], grad + P.lnb[l - 1], rows, Q.n[l - 1], st);
     if (rc) return rc;
     float* t = dcur; dcur = dnext; dnext = t;
   }
+  if (impl != 0)
+    return launch_tc_dw_accum(passes, dcur, Q.n[0], w.x0, Q.kpad[0], Q.k[0], grad + P.w[0], grad + P.b[0], rows, st);
   return launch_dw_accum(dcur, Q.n[0], w.x0, Q.kpad[0], Q.k[0], grad + P.w[0], grad + P.b[0], rows, st);
 }
 

@@ -46,6 +46,10 @@ struct PrepLayout {
   int k[HB_MAX_LAYERS], kpad[HB_MAX_LAYERS], n[HB_MAX_LAYERS];
   int wt[HB_MAX_LAYERS], bias[HB_MAX_LAYERS], lnw[HB_MAX_LAYERS], lnb[HB_MAX_LAYERS];
   int hw, hbias, log_std;
+  // tcgen05 operand images (tc_gemm.cu): per layer, per 32-wide k-chunk: hi image [nt][32] then lo image
+  int tk[HB_MAX_LAYERS], tk_chunks[HB_MAX_LAYERS], tk_nt[HB_MAX_LAYERS];
+  // images of W^T for the backward dX GEMM (layers >= 1)
+  int tkt[HB_MAX_LAYERS], tkt_chunks[HB_MAX_LAYERS], tkt_nt[HB_MAX_LAYERS];
   int total;
 };
 
@@ -58,6 +62,7 @@ struct ParamLayout {
 };
 
 int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_layout* out);
+int gemm_impl();  // 0 = FP32 SIMT, 1 = tcgen05 3xTF32 (fp32-accurate), 2 = tcgen05 TF32
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

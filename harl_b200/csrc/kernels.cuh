@@ -66,6 +66,16 @@ int launch_ln_act_bwd(const float* dY, const float* Z, const float* stats, const
                       float* g_lnb, int64_t rows, int N, int act, cudaStream_t st);
 int launch_featnorm_fold(const hb_net_desc* d, const float* params, float* grad, cudaStream_t st);
 
+int launch_tc_linear_ln_fwd(int passes, int act, const float* X, int ldx, const float* tiles, int nchunks,
+                            const float* bias, const float* lnw, const float* lnb, float* Z, float* Y, float* stats,
+                            int64_t M, int N, int Kred, cudaStream_t st);
+
+int launch_tc_dx_ln_bwd(int passes, int act, const float* dZ, int N, const float* tiles, int nchunks, const float* Zp,
+                        const float* stats_p, const float* lnw_p, float* dZp, float* g_lnw_p, float* g_lnb_p, int64_t M,
+                        int Np, cudaStream_t st);
+int launch_tc_dw_accum(int passes, const float* dZ, int N, const float* X, int ldx, int K, float* dW, float* db,
+                       int64_t M, cudaStream_t st);
+
 int launch_policy_head(int head, int mode, const HeadArgs& a, cudaStream_t st);
 int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st);
 

@@ -1,6 +1,8 @@
 // Parameter layout (reference state_dict order), derived-weight preparation, error plumbing.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace hb {
@@ -38,6 +40,13 @@ static int add_tensor(hb_net_layout* L, int* cursor, const char* name, int rows,
 // feature_norm, mlp.fc.{3l, 3l+2};  RNNLayer (rnn.py:14-21): rnn.rnn.*, rnn.norm;
 // DiagGaussian (distributions.py:80-82): fc_mean registered before log_std is assigned, but
 // nn.Module yields own parameters (log_std) before sub-modules (fc_mean);  VNet: v_out.
+int tc_nt_of(int n);
+int launch_pack_umma_tiles(const float* W, int ldn, int ldk, const float* scale, int N, int K, int NT, int nchunks,
+                           float* dst, cudaStream_t st);
+
+static std::atomic<int> g_gemm_impl{0};
+int gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
+
 int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_layout* out) {
   if (!d) { set_error("net desc is NULL"); return HB_ERR_INVALID; }
   if (d->n_layers < 1 || d->n_layers > HB_MAX_LAYERS) { set_error("n_layers %d outside 1..%d", d->n_layers, HB_MAX_LAYERS); return HB_ERR_UNSUPPORTED; }
@@ -107,6 +116,18 @@ int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_l
   Q.hw = c;    c += round_up(d->out_dim * prev, 4);
   Q.hbias = c; c += round_up(d->out_dim, 4);
   Q.log_std = c; c += round_up(d->out_dim, 4);
+  for (int l = 0; l < d->n_layers; ++l) {
+    Q.tk_nt[l] = tc_nt_of(Q.n[l]);
+    Q.tk_chunks[l] = (Q.kpad[l] + 31) / 32;
+    Q.tk[l] = c;
+    c += Q.tk_chunks[l] * 2 * Q.tk_nt[l] * 32;
+  }
+  for (int l = 1; l < d->n_layers; ++l) {
+    Q.tkt_nt[l] = tc_nt_of(Q.k[l]);
+    Q.tkt_chunks[l] = (Q.n[l] + 31) / 32;
+    Q.tkt[l] = c;
+    c += Q.tkt_chunks[l] * 2 * Q.tkt_nt[l] * 32;
+  }
   Q.total = c;
   if (pl) *pl = P;
   if (pp) *pp = Q;
@@ -141,6 +162,7 @@ __global__ void prepare_kernel(ParamLayout P, PrepLayout Q, int feature_norm, in
     if (i >= Q.lnw[l] && i < Q.lnw[l] + n) { prep[i] = params[P.lnw[l] + i - Q.lnw[l]]; return; }
     if (i >= Q.lnb[l] && i < Q.lnb[l] + n) { prep[i] = params[P.lnb[l] + i - Q.lnb[l]]; return; }
   }
+  if (i >= Q.tk[0]) return;  // tensor-core operand images are written by pack_umma_tiles
   int h = Q.n[Q.n_layers - 1];
   if (i >= Q.hw && i < Q.hw + out_dim * h) { prep[i] = params[P.hw + i - Q.hw]; return; }
   if (i >= Q.hbias && i < Q.hbias + out_dim) { prep[i] = params[P.hbias + i - Q.hbias]; return; }
@@ -153,8 +175,20 @@ int prepare_launch(const hb_net_desc* d, const float* params, float* prepared, c
   PrepLayout Q;
   int rc = make_layouts(d, &P, &Q, nullptr);
   if (rc) return rc;
-  prepare_kernel<<<(Q.total + 255) / 256, 256, 0, st>>>(P, Q, d->feature_norm, d->head, d->out_dim, params, prepared);
+  prepare_kernel<<<(Q.tk[0] + 255) / 256, 256, 0, st>>>(P, Q, d->feature_norm, d->head, d->out_dim, params, prepared);
   HB_LAUNCH_DONE(st,"hb_net_prepare");
+  if (gemm_impl() != 0) {
+    for (int l = 0; l < Q.n_layers; ++l) {
+      rc = launch_pack_umma_tiles(params + P.w[l], Q.k[l], 1, (l == 0 && d->feature_norm) ? params + P.fn_w : nullptr,
+                                  Q.n[l], Q.k[l], Q.tk_nt[l], Q.tk_chunks[l], prepared + Q.tk[l], st);
+      if (rc) return rc;
+      if (l >= 1) {  // W^T images: rows = input feature k, reduction = output feature n
+        rc = launch_pack_umma_tiles(params + P.w[l], 1, Q.k[l], nullptr, Q.k[l], Q.n[l], Q.tkt_nt[l], Q.tkt_chunks[l],
+                                    prepared + Q.tkt[l], st);
+        if (rc) return rc;
+      }
+    }
+  }
   return HB_OK;
 }
 
@@ -169,6 +203,13 @@ int hb_sync_check(void) {
   if (e != cudaSuccess) return hb::cuda_fail(e, "hb_sync_check");
   return HB_OK;
 }
+
+int hb_set_gemm_impl(int impl) {
+  HB_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (fp32 simt), 1 (tcgen05 3xtf32) or 2 (tcgen05 tf32)");
+  hb::g_gemm_impl.store(impl);
+  return HB_OK;
+}
+int hb_get_gemm_impl(void) { return hb::gemm_impl(); }
 
 int hb_net_layout_of(const hb_net_desc* d, hb_net_layout* out) {
   HB_CHECK_ARG(out != nullptr, "out is NULL");
