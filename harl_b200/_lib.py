@@ -43,6 +43,20 @@ class InsertArgs(C.Structure):
         ("actor_masks_next", C.c_void_p * HB_MAX_AGENTS), ("actor_active_next", C.c_void_p * HB_MAX_AGENTS),
         ("actor_rnn_next", C.c_void_p * HB_MAX_AGENTS),
         ("critic_masks_next", C.c_void_p), ("critic_bad_next", C.c_void_p), ("critic_rnn_next", C.c_void_p),
+        ("rewards", C.c_void_p), ("reward_stride_n", C.c_int64), ("reward_stride_a", C.c_int64),
+        ("ep_return", C.c_void_p), ("done_sum", C.c_void_p),
+    ]
+
+
+class CollectArgs(C.Structure):
+    _fields_ = [
+        ("n_agents", C.c_int32), ("deterministic", C.c_int32), ("rows", C.c_int64), ("offset", C.c_uint64),
+        ("actor_desc", C.POINTER(NetDesc) * HB_MAX_AGENTS), ("actor_prepared", C.c_void_p * HB_MAX_AGENTS),
+        ("obs", C.c_void_p * HB_MAX_AGENTS), ("avail", C.c_void_p * HB_MAX_AGENTS),
+        ("actions", C.c_void_p * HB_MAX_AGENTS), ("logp", C.c_void_p * HB_MAX_AGENTS),
+        ("seed", C.c_uint64 * HB_MAX_AGENTS),
+        ("critic_desc", C.POINTER(NetDesc)), ("critic_prepared", C.c_void_p), ("share_obs", C.c_void_p),
+        ("critic_rows", C.c_int64), ("values", C.c_void_p),
     ]
 
 
@@ -88,6 +102,7 @@ SIGNATURES = {
     "hb_net_prepare": (C.c_int, [C.POINTER(NetDesc), P, P, P]),
     "hb_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64, C.c_int]),
     "hb_rollout_insert_masks": (C.c_int, [C.POINTER(InsertArgs), P]),
+    "hb_rollout_collect": (C.c_int, [C.POINTER(CollectArgs), P, C.c_size_t, P]),
     "hb_policy_act": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, C.c_int, C.c_uint64, C.c_uint64, P, P, P,
                                 C.c_size_t, P]),
     "hb_value_forward": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, C.c_size_t, P]),

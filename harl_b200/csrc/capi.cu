@@ -17,6 +17,8 @@ struct Work {
   float* stats[HB_MAX_LAYERS];
   float* dA;
   float* dB;
+  float* dwpart;   // [tc_dw_splits()][param total] split buffer of the tensor-core dW kernel (gradient mode)
+  int ptotal;
 };
 
 static int hmax_of(const PrepLayout& Q) {
@@ -25,19 +27,21 @@ static int hmax_of(const PrepLayout& Q) {
   return m;
 }
 
-static size_t work_floats(const PrepLayout& Q, int64_t ch, int mode) {
+static size_t work_floats(const PrepLayout& Q, int64_t ch, int mode, int ptotal) {
   size_t f = (size_t)ch * Q.kpad[0];
   const size_t hm = hmax_of(Q);
   if (mode == 0) return f + 2 * (size_t)ch * hm;
   for (int l = 0; l < Q.n_layers; ++l) f += 2 * (size_t)ch * Q.n[l] + (size_t)round_up((int)(2 * ch), 4);
-  return f + 2 * (size_t)ch * hm;
+  return f + 2 * (size_t)ch * hm + (size_t)tc_dw_splits() * ptotal;
 }
 
-static int carve(const PrepLayout& Q, int64_t ch, int mode, void* ws, size_t ws_bytes, Work* w) {
-  if (work_floats(Q, ch, mode) * sizeof(float) > ws_bytes || ws == nullptr) {
-    set_error("workspace too small: need %zu bytes, have %zu", work_floats(Q, ch, mode) * sizeof(float), ws_bytes);
+static int carve(const PrepLayout& Q, int64_t ch, int mode, void* ws, size_t ws_bytes, Work* w, int ptotal = 0) {
+  if (work_floats(Q, ch, mode, ptotal) * sizeof(float) > ws_bytes || ws == nullptr) {
+    set_error("workspace too small: need %zu bytes, have %zu", work_floats(Q, ch, mode, ptotal) * sizeof(float), ws_bytes);
     return HB_ERR_WORKSPACE;
   }
+  w->ptotal = ptotal;
+  w->dwpart = nullptr;
   float* p = (float*)ws;
   const size_t hm = hmax_of(Q);
   w->x0 = p; p += (size_t)ch * Q.kpad[0];
@@ -53,7 +57,8 @@ static int carve(const PrepLayout& Q, int64_t ch, int mode, void* ws, size_t ws_
     w->stats[l] = p; p += (size_t)round_up((int)(2 * ch), 4);
   }
   w->dA = p; p += (size_t)ch * hm;
-  w->dB = p;
+  w->dB = p; p += (size_t)ch * hm;
+  w->dwpart = p;
   return HB_OK;
 }
 
@@ -88,14 +93,13 @@ static int trunk_backward(const hb_net_desc* d, const ParamLayout& P, const Prep
   const int L = Q.n_layers;
   float* dcur = w.dA;
   float* dnext = w.dB;
-  int rc = launch_ln_act_bwd(dcur, w.Z[L - 1], w.stats[L - 1], prep + Q.lnw[L - 1], dcur, grad + P.lnw[L - 1],
-                             grad + P.lnb[L - 1], rows, Q.n[L - 1], d->activation, st);
-  if (rc) return rc;
+  int rc = HB_OK;  // the LN + activation backward of the last block is fused into the head kernel (w.dA already holds dZ_L)
   const int impl = gemm_impl();
   const int passes = impl == 1 ? 3 : 1;
   for (int l = L - 1; l >= 1; --l) {
     if (impl != 0)
-      rc = launch_tc_dw_accum(passes, dcur, Q.n[l], w.Y[l - 1], Q.n[l - 1], Q.k[l], grad + P.w[l], grad + P.b[l], rows, st);
+      rc = launch_tc_dw_accum(passes, dcur, Q.n[l], w.Y[l - 1], Q.n[l - 1], Q.k[l], w.dwpart + P.w[l], grad + P.b[l], rows,
+                              w.ptotal, st);
     else
       rc = launch_dw_accum(dcur, Q.n[l], w.Y[l - 1], Q.n[l - 1], Q.k[l], grad + P.w[l], grad + P.b[l], rows, st);
     if (rc) return rc;
@@ -110,7 +114,7 @@ static int trunk_backward(const hb_net_desc* d, const ParamLayout& P, const Prep
     float* t = dcur; dcur = dnext; dnext = t;
   }
   if (impl != 0)
-    return launch_tc_dw_accum(passes, dcur, Q.n[0], w.x0, Q.kpad[0], Q.k[0], grad + P.w[0], grad + P.b[0], rows, st);
+    return launch_tc_dw_accum(passes, dcur, Q.n[0], w.x0, Q.kpad[0], Q.k[0], w.dwpart + P.w[0], grad + P.b[0], rows, w.ptotal, st);
   return launch_dw_accum(dcur, Q.n[0], w.x0, Q.kpad[0], Q.k[0], grad + P.w[0], grad + P.b[0], rows, st);
 }
 
@@ -154,10 +158,11 @@ extern "C" {
 
 size_t hb_workspace_bytes(const hb_net_desc* d, int64_t rows, int mode) {
   hb::PrepLayout Q;
-  if (hb::make_layouts(d, nullptr, &Q, nullptr)) return 0;
+  hb::ParamLayout P;
+  if (hb::make_layouts(d, &P, &Q, nullptr)) return 0;
   int64_t ch = rows < hb::CHUNK_ROWS ? rows : hb::CHUNK_ROWS;
   if (ch < 1) ch = 1;
-  return hb::work_floats(Q, ch, mode) * sizeof(float);
+  return hb::work_floats(Q, ch, mode, P.total) * sizeof(float);
 }
 
 int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
@@ -189,6 +194,25 @@ int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs,
     a.logp_out = logp + c0 * ad;
     if ((rc = launch_policy_head(d->head, MODE_ACT, a, st))) return rc;
   }
+  return HB_OK;
+}
+
+int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
+                  int deterministic, uint64_t seed, uint64_t offset, float* actions, float* logp, void* ws,
+                  size_t ws_bytes, void* stream);
+int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows, float* values,
+                     void* ws, size_t ws_bytes, void* stream);
+
+int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_bytes, void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(a && a->n_agents > 0 && a->n_agents <= HB_MAX_AGENTS && a->rows > 0, "bad argument");
+  for (int i = 0; i < a->n_agents; ++i) {
+    int rc = hb_policy_act(a->actor_desc[i], a->actor_prepared[i], a->obs[i], a->rows, a->avail[i], a->deterministic,
+                           a->seed[i], a->offset, a->actions[i], a->logp[i], ws, ws_bytes, stream);
+    if (rc) return rc;
+  }
+  if (a->critic_desc != nullptr)
+    return hb_value_forward(a->critic_desc, a->critic_prepared, a->share_obs, a->critic_rows, a->values, ws, ws_bytes, stream);
   return HB_OK;
 }
 
@@ -270,7 +294,11 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
   if (rows == 0) return HB_OK;
   const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
   Work w;
-  if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w))) return rc;
+  if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w, L.total))) return rc;
+  if (gemm_impl() != 0) {
+    ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "hb_ppo_actor_grad(memset split buffer)");
+  }
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
     if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
@@ -289,9 +317,12 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
     a.g_hbias = grad + P.hbias;
     a.g_log_std = d->head == HB_HEAD_BOX ? grad + P.log_std : nullptr;
     a.scalars = scalars;
+    a.ln_z = w.Z[Q.n_layers - 1]; a.ln_stats = w.stats[Q.n_layers - 1]; a.ln_w = prepared + Q.lnw[Q.n_layers - 1];
+    a.g_ln_w = grad + P.lnw[Q.n_layers - 1]; a.g_ln_b = grad + P.lnb[Q.n_layers - 1]; a.ln_act = d->activation;
     if ((rc = launch_policy_head(d->head, MODE_GRAD, a, st))) return rc;
     if ((rc = trunk_backward(d, P, Q, params, prepared, grad, n, w, st))) return rc;
   }
+  if (gemm_impl() != 0 && (rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
   return launch_featnorm_fold(d, params, grad, st);
 }
 
@@ -313,7 +344,11 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
   if (rows == 0) return HB_OK;
   const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
   Work w;
-  if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w))) return rc;
+  if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w, L.total))) return rc;
+  if (gemm_impl() != 0) {
+    ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "hb_value_grad(memset split buffer)");
+  }
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
     if ((rc = trunk_forward(d, Q, prepared, b->share_obs, b->index, c0, n, w, st))) return rc;
@@ -338,9 +373,12 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
     a.g_hw = grad + P.hw;
     a.g_hbias = grad + P.hbias;
     a.scalars = scalars;
+    a.ln_z = w.Z[Q.n_layers - 1]; a.ln_stats = w.stats[Q.n_layers - 1]; a.ln_w = prepared + Q.lnw[Q.n_layers - 1];
+    a.g_ln_w = grad + P.lnw[Q.n_layers - 1]; a.g_ln_b = grad + P.lnb[Q.n_layers - 1]; a.ln_act = d->activation;
     if ((rc = launch_value_head(1, a, st))) return rc;
     if ((rc = trunk_backward(d, P, Q, params, prepared, grad, n, w, st))) return rc;
   }
+  if (gemm_impl() != 0 && (rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
   return launch_featnorm_fold(d, params, grad, st);
 }
 }

@@ -39,6 +39,9 @@ struct HeadArgs {
   float* g_hbias;        // [out]
   float* g_log_std;      // [out]
   double* scalars;       // += (loss_num, entropy_num, ratio_sum, rows)
+  // fused LayerNorm + activation backward of the last trunk block (grad mode, when ln_z != nullptr):
+  // dfeat then receives dZ_L instead of d/d features, and the LN affine gradients are accumulated here
+  const float* ln_z; const float* ln_stats; const float* ln_w; float* g_ln_w; float* g_ln_b; int ln_act;
 };
 
 struct ValueArgs {
@@ -51,6 +54,7 @@ struct ValueArgs {
   float clip, huber_delta, coef;  // coef = value_loss_coef * inv_count
   int use_huber, use_clipped;
   float* dfeat; float* g_hw; float* g_hbias; double* scalars;  // scalars += (loss_sum, rows)
+  const float* ln_z; const float* ln_stats; const float* ln_w; float* g_ln_w; float* g_ln_b; int ln_act;  // as in HeadArgs
 };
 
 // launchers (gemm_simt.cu, rowwise.cu, optim.cu)
@@ -74,7 +78,9 @@ int launch_tc_dx_ln_bwd(int passes, int act, const float* dZ, int N, const float
                         const float* stats_p, const float* lnw_p, float* dZp, float* g_lnw_p, float* g_lnb_p, int64_t M,
                         int Np, cudaStream_t st);
 int launch_tc_dw_accum(int passes, const float* dZ, int N, const float* X, int ldx, int K, float* dW, float* db,
-                       int64_t M, cudaStream_t st);
+                       int64_t M, int64_t part_stride, cudaStream_t st);
+int tc_dw_splits();
+int launch_dw_reduce(float* grad, const float* part, int total, cudaStream_t st);
 
 int launch_policy_head(int head, int mode, const HeadArgs& a, cudaStream_t st);
 int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st);

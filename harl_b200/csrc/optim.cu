@@ -90,6 +90,16 @@ __global__ void insert_masks_kernel(hb_insert_args a) {
     if (a.actor_masks_next[i]) a.actor_masks_next[i][n] = mk;
     if (a.actor_active_next[i]) a.actor_active_next[i][n] = all_done ? 1.f : (a.dones[n * A + i] ? 0.f : 1.f);
   }
+  if (a.rewards != nullptr && a.ep_return != nullptr) {
+    float r = 0.f;
+    for (int i = 0; i < A; ++i) r += a.rewards[(int64_t)n * a.reward_stride_n + (int64_t)i * a.reward_stride_a];
+    float acc = a.ep_return[n] + r / (float)A;
+    if (all_done) {
+      if (a.done_sum) { atomicAdd(a.done_sum, (double)acc); atomicAdd(a.done_sum + 1, 1.0); }
+      acc = 0.f;
+    }
+    a.ep_return[n] = acc;
+  }
   if (a.state_type_fp) {
     for (int i = 0; i < A; ++i) {
       if (a.critic_masks_next) a.critic_masks_next[n * A + i] = mk;

@@ -204,6 +204,53 @@ __device__ __forceinline__ float dmin_dratio(float ratio, float adv, float clip,
   return 0.f;
 }
 
+
+// LayerNorm + activation backward of one row held lane-strided by a warp (fused tail of the head kernels).
+// df: d loss / d (LN output) for columns lane + 32 q.  Writes dZ to out_row; accumulates dgamma / dbeta partials.
+template <int HPL>
+__device__ __forceinline__ void ln_act_bwd_row(const float (&df)[HPL], const float* __restrict__ zrow, float mu, float rstd,
+                                               const float* __restrict__ lnw, int h, int act, int lane,
+                                               float* __restrict__ out_row, float (&cg)[HPL], float (&cb)[HPL]) {
+  float g[HPL], xh[HPL], da[HPL];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) {
+    const int n = lane + 32 * q;
+    g[q] = xh[q] = da[q] = 0.f;
+    if (n < h) {
+      const float z = zrow[n];
+      const float x = (act_fwd_rt(act, z) - mu) * rstd;
+      cg[q] = fmaf(df[q], x, cg[q]);
+      cb[q] += df[q];
+      g[q] = df[q] * lnw[n];
+      xh[q] = x;
+      da[q] = act_bwd_rt(act, z);
+      s1 += g[q];
+      s2 = fmaf(g[q], x, s2);
+    }
+  }
+  const float inv_n = 1.f / (float)h;
+  const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) {
+    const int n = lane + 32 * q;
+    if (n < h) out_row[n] = rstd * (g[q] - m1 - xh[q] * m2) * da[q];
+  }
+}
+
+// block-level reduction of the per-lane LN-affine partial sums (all warps) into global memory
+template <int HPL>
+__device__ __forceinline__ void ln_affine_flush(const float (&cg)[HPL], const float (&cb)[HPL], int h, int lane,
+                                                float* sacc /* [2][256] shared, zeroed */, float* g_ln_w, float* g_ln_b) {
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) {
+    const int n = lane + 32 * q;
+    if (n < h) { atomicAdd(&sacc[n], cg[q]); atomicAdd(&sacc[256 + n], cb[q]); }
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < h; n += ROW_THREADS) { atomicAdd(g_ln_w + n, sacc[n]); atomicAdd(g_ln_b + n, sacc[256 + n]); }
+}
+
 // ---- Categorical (distributions.py:7-21,37-55; act.py:44-80,143-155)
 template <int HPL, int MAXJ, int MODE>
 __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) {
@@ -221,6 +268,11 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
   const int64_t w0 = (int64_t)blockIdx.x * ROW_WARPS + warp, nw = (int64_t)gridDim.x * ROW_WARPS;
   float gacc[MODE == MODE_GRAD ? MAXJ : 1][HPL];
   float gb = 0.f;
+  float lcg[HPL], lcb[HPL];
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) lcg[q] = lcb[q] = 0.f;
+  __shared__ float s_ln[MODE == MODE_GRAD ? 512 : 1];
+  if (MODE == MODE_GRAD) { for (int i = threadIdx.x; i < 512; i += ROW_THREADS) s_ln[i] = 0.f; }
   double s_loss = 0.0, s_ent = 0.0, s_ratio = 0.0, s_rows = 0.0;
   if (MODE == MODE_GRAD) {
 #pragma unroll
@@ -305,7 +357,10 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
       }
     }
 #pragma unroll
-    for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h) a.dfeat[r * h + n] = df[q]; }
+    for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h && a.ln_z == nullptr) a.dfeat[r * h + n] = df[q]; }
+    if (a.ln_z != nullptr)
+      ln_act_bwd_row<HPL>(df, a.ln_z + r * h, a.ln_stats[r * 2], a.ln_stats[r * 2 + 1], a.ln_w, h, a.ln_act, lane,
+                          a.dfeat + r * h, lcg, lcb);
     }
   }
   if constexpr (MODE == MODE_GRAD) {
@@ -320,6 +375,7 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
     for (int i = threadIdx.x; i < na * h; i += ROW_THREADS) atomicAdd(a.g_hw + i, sg[i]);
     if (threadIdx.x < na) atomicAdd(a.g_hbias + threadIdx.x, sgb[threadIdx.x]);
     block_add_scalars(s_loss, s_ent, s_ratio, s_rows, a.scalars, sred);
+    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b);
   }
 }
 
@@ -347,6 +403,11 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
   const int64_t w0 = (int64_t)blockIdx.x * ROW_WARPS + warp, nw = (int64_t)gridDim.x * ROW_WARPS;
   float gacc[MODE == MODE_GRAD ? MAXJ : 1][HPL];
   float gb = 0.f, gs = 0.f;
+  float lcg[HPL], lcb[HPL];
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) lcg[q] = lcb[q] = 0.f;
+  __shared__ float s_ln[MODE == MODE_GRAD ? 512 : 1];
+  if (MODE == MODE_GRAD) { for (int i = threadIdx.x; i < 512; i += ROW_THREADS) s_ln[i] = 0.f; }
   double s_loss = 0.0, s_ent = 0.0, s_ratio = 0.0, s_rows = 0.0;
   if (MODE == MODE_GRAD) {
 #pragma unroll
@@ -433,7 +494,10 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
       }
     }
 #pragma unroll
-    for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h) a.dfeat[r * h + n] = df[q]; }
+    for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h && a.ln_z == nullptr) a.dfeat[r * h + n] = df[q]; }
+    if (a.ln_z != nullptr)
+      ln_act_bwd_row<HPL>(df, a.ln_z + r * h, a.ln_stats[r * 2], a.ln_stats[r * 2 + 1], a.ln_w, h, a.ln_act, lane,
+                          a.dfeat + r * h, lcg, lcb);
     }
     }
   }
@@ -449,6 +513,7 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
     for (int i = threadIdx.x; i < ad * h; i += ROW_THREADS) atomicAdd(a.g_hw + i, sg[i]);
     if (threadIdx.x < ad) { atomicAdd(a.g_hbias + threadIdx.x, sgb[threadIdx.x]); atomicAdd(a.g_log_std + threadIdx.x, sgb[32 + threadIdx.x]); }
     block_add_scalars(s_loss, s_ent, s_ratio, s_rows, a.scalars, sred);
+    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b);
   }
 }
 
@@ -528,6 +593,11 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
     vstd = sqrtf(fmaxf(msq - mu * mu, 1e-2f));
   }
   float gbias = 0.f;
+  float lcg[HPL], lcb[HPL];
+#pragma unroll
+  for (int q = 0; q < HPL; ++q) lcg[q] = lcb[q] = 0.f;
+  __shared__ float s_ln[GRAD ? 512 : 1];
+  if (GRAD) { for (int i = threadIdx.x; i < 512; i += ROW_THREADS) s_ln[i] = 0.f; }
   double s_loss = 0.0, s_rows = 0.0;
   const int64_t w0 = (int64_t)blockIdx.x * ROW_WARPS + warp, nw = (int64_t)gridDim.x * ROW_WARPS;
   for (int64_t r = w0; r < a.rows; r += nw) {
@@ -558,11 +628,16 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
     g *= a.coef;
     if (lane == 0) { s_loss += (double)loss; s_rows += 1.0; }
     gbias += g;
+    float df[HPL];
 #pragma unroll
     for (int q = 0; q < HPL; ++q) {
       int n = lane + 32 * q;
-      if (n < h) { a.dfeat[r * h + n] = g * wv[q]; gw[q] = fmaf(g, f[q], gw[q]); }
+      df[q] = 0.f;
+      if (n < h) { df[q] = g * wv[q]; gw[q] = fmaf(g, f[q], gw[q]); if (a.ln_z == nullptr) a.dfeat[r * h + n] = df[q]; }
     }
+    if (a.ln_z != nullptr)
+      ln_act_bwd_row<HPL>(df, a.ln_z + r * h, a.ln_stats[r * 2], a.ln_stats[r * 2 + 1], a.ln_w, h, a.ln_act, lane,
+                          a.dfeat + r * h, lcg, lcb);
   }
   if (GRAD) {
 #pragma unroll
@@ -572,6 +647,7 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
     for (int n = threadIdx.x; n < h; n += ROW_THREADS) atomicAdd(a.g_hw + n, sgw[n]);
     if (threadIdx.x == 0) atomicAdd(a.g_hbias, sgb);
     block_add_scalars(s_loss, s_rows, 0.0, 0.0, a.scalars, sred);
+    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b);
   }
 }
 

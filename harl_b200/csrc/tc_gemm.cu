@@ -24,6 +24,9 @@ namespace hb {
 
 constexpr int TC_BM = 128;   // rows per CTA tile (UMMA_M)
 constexpr int TC_KC = 32;    // floats of K per pipeline stage (4 MMA k-steps)
+// One operand stage per CTA (64 KB at NT = 128 with the hi/lo images): three CTAs share an SM, so one CTA's global
+// loads / epilogue overlap the others' MMAs -- inter-CTA instead of intra-CTA pipelining.
+constexpr int TC_STAGES = 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,12 +124,13 @@ int launch_pack_umma_tiles(const float* W, int ldn, int ldk, const float* scale,
 // ------------------------------------------------------------------ forward block on tcgen05
 template <int NT>
 struct TcSmem {
-  float a[2][2][TC_BM * TC_KC];    // [stage][hi/lo] 16 KB each
-  float b[2][2 * NT * TC_KC];      // [stage] hi image then lo image
-  uint64_t full_b[2];              // TMA bytes landed
-  uint64_t empty[2];               // MMAs that read the stage retired
+  float a[TC_STAGES][2][TC_BM * TC_KC];    // [stage][hi/lo] 16 KB each
+  float b[TC_STAGES][2 * NT * TC_KC];      // [stage] hi image then lo image
+  uint64_t full_b[TC_STAGES];              // TMA bytes landed
+  uint64_t empty[TC_STAGES];               // MMAs that read the stage retired
   uint64_t done;                   // all MMAs retired
   uint32_t tmem_base;
+  float pbias[NT], plnw[NT], plnb[NT];   // epilogue parameters
 };
 
 template <int NT, int ACT, int PASSES>
@@ -144,9 +148,13 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
   const int64_t row = row0 + tid;
   constexpr uint32_t B_BYTES = 2u * NT * TC_KC * sizeof(float);
 
+  for (int i = tid; i < NT; i += 128) {
+    s.pbias[i] = i < N ? bias[i] : 0.f;
+    s.plnw[i] = i < N ? lnw[i] : 0.f;
+    s.plnb[i] = i < N ? lnb[i] : 0.f;
+  }
   if (tid == 0) {
-    mbar_init(&s.full_b[0], 1); mbar_init(&s.full_b[1], 1);
-    mbar_init(&s.empty[0], 1);  mbar_init(&s.empty[1], 1);
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full_b[i], 1); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -162,8 +170,8 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
 
   uint32_t ph_full[2] = {0, 0}, ph_empty[2] = {0, 0};
   for (int c = 0; c < nchunks; ++c) {
-    const int st = c & 1;
-    if (c >= 2) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }  // stage free again
+    const int st = c % TC_STAGES;
+    if (c >= TC_STAGES) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }  // stage free again
     if (tid == 0) {
       mbar_expect_tx(&s.full_b[st], B_BYTES);
       tma_bulk_g2s(s.b[st], tiles + (int64_t)c * (2 * NT * TC_KC), B_BYTES, &s.full_b[st]);
@@ -210,6 +218,9 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
   tc_fence_after();
 
   // ---- epilogue: thread = row.  z = acc + b, a = act(z), LayerNorm over the N valid columns.
+  // Parameters come from shared memory; output tiles are transposed through the (now idle) operand stage with an
+  // XOR swizzle on 16-byte chunks so that both the row-per-thread writes and the row-per-warp reads are conflict
+  // free, and the global stores are full 512-byte rows.
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const float inv_n = 1.f / (float)N;
   float sum = 0.f;
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
     tmem_ld32(trow + c0, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (c0 + j < N) sum += act_fwd<ACT>(v[j] + bias[c0 + j]);
+      if (c0 + j < N) sum += act_fwd<ACT>(v[j] + s.pbias[c0 + j]);
   }
   const float mean = sum * inv_n;
   float sq = 0.f;
@@ -227,27 +238,47 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
     tmem_ld32(trow + c0, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (c0 + j < N) { float d = act_fwd<ACT>(v[j] + bias[c0 + j]) - mean; sq = fmaf(d, d, sq); }
+      if (c0 + j < N) { float d = act_fwd<ACT>(v[j] + s.pbias[c0 + j]) - mean; sq = fmaf(d, d, sq); }
   }
   const float rstd = rsqrtf(sq * inv_n + 1e-5f);
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float v[32];
-    tmem_ld32(trow + c0, v);
-    if (row < M) {
+  constexpr int CPR = NT / 4;                       // 16-byte chunks per tile row
+  constexpr bool kViaSmem = (size_t)TC_BM * NT * 4 <= sizeof(s.a) + sizeof(s.b);
+  float4* tile = reinterpret_cast<float4*>(&s.a[0][0][0]);
+  const int nvalid = (int)(M - row0 < TC_BM ? M - row0 : TC_BM);
+#pragma unroll 1
+  for (int pass = (Z != nullptr ? 0 : 1); pass < 2; ++pass) {
+    float* __restrict__ out = pass == 0 ? Z : Y;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(trow + c0, v);
 #pragma unroll
       for (int j4 = 0; j4 < 32; j4 += 4) {
         if (c0 + j4 < N) {  // N is a multiple of 4
-          float z[4], y[4];
+          float o[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            int n = c0 + j4 + q;
-            z[q] = v[j4 + q] + bias[n];
-            y[q] = (act_fwd<ACT>(z[q]) - mean) * rstd * lnw[n] + lnb[n];
+            const int n = c0 + j4 + q;
+            const float z = v[j4 + q] + s.pbias[n];
+            o[q] = pass == 0 ? z : (act_fwd<ACT>(z) - mean) * rstd * s.plnw[n] + s.plnb[n];
           }
-          if (Z != nullptr) *reinterpret_cast<float4*>(Z + row * N + c0 + j4) = make_float4(z[0], z[1], z[2], z[3]);
-          *reinterpret_cast<float4*>(Y + row * N + c0 + j4) = make_float4(y[0], y[1], y[2], y[3]);
+          const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+          if (kViaSmem) {
+            const int ch = (c0 + j4) >> 2;
+            tile[tid * CPR + (ch ^ (tid & (CPR - 1) & 31))] = o4;
+          } else if (row < M) {
+            *reinterpret_cast<float4*>(out + row * N + c0 + j4) = o4;
+          }
         }
       }
+    }
+    if (kViaSmem) {
+      __syncthreads();
+      for (int i = tid; i < TC_BM * CPR; i += 128) {
+        const int r = i / CPR, lc = i % CPR;
+        if (r < nvalid && lc * 4 < N)
+          *reinterpret_cast<float4*>(out + (row0 + r) * N + lc * 4) = tile[r * CPR + (lc ^ (r & (CPR - 1) & 31))];
+      }
+      __syncthreads();
     }
   }
   if (stats != nullptr && row < M) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
@@ -333,8 +364,7 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
   const int64_t row = row0 + tid;
   constexpr uint32_t B_BYTES = 2u * NT * TC_KC * sizeof(float);
   if (tid == 0) {
-    mbar_init(&s.full_b[0], 1); mbar_init(&s.full_b[1], 1);
-    mbar_init(&s.empty[0], 1);  mbar_init(&s.empty[1], 1);
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full_b[i], 1); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -349,8 +379,8 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
   constexpr uint32_t idesc = umma_idesc_tf32(NT);
   uint32_t ph_full[2] = {0, 0}, ph_empty[2] = {0, 0};
   for (int c = 0; c < nchunks; ++c) {
-    const int st = c & 1;
-    if (c >= 2) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }
+    const int st = c % TC_STAGES;
+    if (c >= TC_STAGES) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }
     if (tid == 0) {
       mbar_expect_tx(&s.full_b[st], B_BYTES);
       tma_bulk_g2s(s.b[st], tiles + (int64_t)c * (2 * NT * TC_KC), B_BYTES, &s.full_b[st]);
@@ -395,12 +425,27 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
   mbar_wait(&s.done, 0);
   tc_fence_after();
 
-  // ---- epilogue (operand stages are free now: reuse stage 0 of A for the column-sum staging)
-  float* colsum = reinterpret_cast<float*>(s.a[0][0]);  // [2][NT]
-  for (int i = tid; i < 2 * NT; i += 128) colsum[i] = 0.f;
+  // ---- epilogue.  Parameters / column sums live in the small shared arrays; the Zp tile is staged through the (now
+  // idle) operand stage with coalesced loads and an XOR chunk swizzle, transformed in place into dZp by its row's
+  // thread, and written out with coalesced stores (NT <= 128; wider tiles use direct row accesses).
+  float* colsum = s.pbias;  // [2][NT] (pbias, plnw are contiguous)
+  for (int i = tid; i < NT; i += 128) { s.pbias[i] = 0.f; s.plnw[i] = 0.f; s.plnb[i] = i < Np ? lnw_p[i] : 0.f; }
+  constexpr int CPR = NT / 4;
+  constexpr bool kViaSmem = (size_t)TC_BM * NT * 4 <= sizeof(s.a) + sizeof(s.b);
+  float4* tile = reinterpret_cast<float4*>(&s.a[0][0][0]);
+  const int nvalid = (int)(M - row0 < TC_BM ? M - row0 : TC_BM);
+  if (kViaSmem) {
+    for (int i = tid; i < TC_BM * CPR; i += 128) {
+      const int r = i / CPR, lc = i % CPR;
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nvalid && lc * 4 < Np) z = *reinterpret_cast<const float4*>(Zp + (row0 + r) * Np + lc * 4);
+      tile[r * CPR + (lc ^ (r & (CPR - 1) & 31))] = z;
+    }
+  }
   __syncthreads();
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const bool rok = row < M;
+  const int sw = tid & (CPR - 1) & 31;
   float mu = 0.f, rstd = 0.f;
   if (rok) { mu = stats_p[row * 2]; rstd = stats_p[row * 2 + 1]; }
   const float inv_n = 1.f / (float)Np;
@@ -412,14 +457,15 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
     for (int j4 = 0; j4 < 32; j4 += 4) {
       float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool ok = rok && c0 + j4 < Np;
-      if (ok) z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
+      if (kViaSmem) { if (c0 + j4 < NT) z = tile[tid * CPR + ((((c0 + j4) >> 2)) ^ sw)]; }
+      else if (ok) z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
       const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int n = c0 + j4 + q;
         const float dy = ok ? v[j4 + q] : 0.f;
         const float x = ok ? (act_fwd<ACT>(zz[q]) - mu) * rstd : 0.f;
-        const float g = ok ? dy * lnw_p[n] : 0.f;
+        const float g = ok ? dy * s.plnb[n] : 0.f;
         cg[j4 + q] = dy * x;
         cb[j4 + q] = dy;
         s1 += g;
@@ -433,23 +479,34 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
   for (int c0 = 0; c0 < Np; c0 += 32) {
     float v[32];
     tmem_ld32(trow + c0, v);
-    if (rok) {
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        if (c0 + j4 < Np) {
-          const float4 z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
-          const float zz[4] = {z.x, z.y, z.z, z.w};
-          float o[4];
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+      if (c0 + j4 < Np) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int slot = tid * CPR + (((c0 + j4) >> 2) ^ sw);
+        if (kViaSmem) z = tile[slot];
+        else if (rok) z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        float o[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = c0 + j4 + q;
-            const float x = (act_fwd<ACT>(zz[q]) - mu) * rstd;
-            const float g = v[j4 + q] * lnw_p[n];
-            o[q] = rstd * (g - m1 - x * m2) * act_bwd<ACT>(zz[q]);
-          }
-          *reinterpret_cast<float4*>(dZp + row * Np + c0 + j4) = make_float4(o[0], o[1], o[2], o[3]);
+        for (int q = 0; q < 4; ++q) {
+          const int n = c0 + j4 + q;
+          const float x = (act_fwd<ACT>(zz[q]) - mu) * rstd;
+          const float g = v[j4 + q] * s.plnb[n];
+          o[q] = rstd * (g - m1 - x * m2) * act_bwd<ACT>(zz[q]);
         }
+        const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+        if (kViaSmem) tile[slot] = o4;
+        else if (rok) *reinterpret_cast<float4*>(dZp + row * Np + c0 + j4) = o4;
       }
+    }
+  }
+  if (kViaSmem) {
+    __syncthreads();
+    for (int i = tid; i < TC_BM * CPR; i += 128) {
+      const int r = i / CPR, lc = i % CPR;
+      if (r < nvalid && lc * 4 < Np)
+        *reinterpret_cast<float4*>(dZp + (row0 + r) * Np + lc * 4) = tile[r * CPR + (lc ^ (r & (CPR - 1) & 31))];
     }
   }
   __syncthreads();
@@ -502,9 +559,9 @@ int launch_tc_dx_ln_bwd(int passes, int act, const float* dZ, int N, const float
 // (grid.x); fp32 accumulator in TMEM; epilogue: thread = dZ feature, atomicAdd of its dW row; db from the staging sums.
 template <int NTK>
 struct TcDwSmem {
-  float a[2][2][TC_KC * 128];   // [stage][hi/lo] dZ^T chunk image (128 features x 32 rows)
-  float b[2][2][TC_KC * NTK];   // [stage][hi/lo] X^T chunk image (NTK features x 32 rows)
-  uint64_t empty[2];
+  float a[TC_STAGES][2][TC_KC * 128];   // [stage][hi/lo] dZ^T chunk image (128 features x 32 rows)
+  float b[TC_STAGES][2][TC_KC * NTK];   // [stage][hi/lo] X^T chunk image (NTK features x 32 rows)
+  uint64_t empty[TC_STAGES];
   uint64_t done;
   uint32_t tmem_base;
 };
@@ -513,15 +570,17 @@ template <int NTK, int PASSES>
 __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __restrict__ dZ, int N,
                                                              const float* __restrict__ X, int ldx, int K,
                                                              float* __restrict__ dW, float* __restrict__ db, int64_t M,
-                                                             int64_t rows_per_cta) {
+                                                             int64_t rows_per_cta, int64_t part_stride) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcDwSmem<NTK>& s = *reinterpret_cast<TcDwSmem<NTK>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n0 = blockIdx.y * 128;
+  const int k0 = blockIdx.z * NTK;   // X feature block (input widths > 256, e.g. 393-wide observations)
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
   if (tid == 0) {
-    mbar_init(&s.empty[0], 1); mbar_init(&s.empty[1], 1); mbar_init(&s.done, 1);
+    for (int i = 0; i < TC_STAGES; ++i) mbar_init(&s.empty[i], 1);
+    mbar_init(&s.done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -539,8 +598,8 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
   const int fa = n0 + tid;                                   // this thread's dZ feature
   const int slot = ((tid >> 3) * 8) * 32 + (tid & 7) * 4;    // floats; + kc*32 per 4-row group
   for (int c = 0; c < nchunks; ++c) {
-    const int st = c & 1;
-    if (c >= 2) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }
+    const int st = c % TC_STAGES;
+    if (c >= TC_STAGES) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }
     const int64_t r0 = m0 + (int64_t)c * TC_KC;
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) {
@@ -566,7 +625,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int64_t r = r0 + kc * 4 + q;
-            v[q] = (r < m1 && f < ldx) ? X[r * ldx + f] : 0.f;
+            v[q] = (r < m1 && k0 + f < ldx) ? X[r * ldx + k0 + f] : 0.f;
           }
           const float4 h = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
           *reinterpret_cast<float4*>(&s.b[st][0][bslot + kc * 32]) = h;
@@ -599,54 +658,97 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
     mbar_wait(&s.done, 0);
     tc_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < K; c0 += 32) {
+    // part_stride != 0: this CTA owns slot blockIdx.x of a split buffer [splits][params] -> plain read-modify-write
+    // (deterministic, no atomics; summed into the gradient once per call by dw_reduce_kernel).  Else: atomics into dW.
+    float* dst = dW + (int64_t)blockIdx.x * part_stride + (int64_t)fa * K;
+    for (int c0 = 0; c0 < NTK && k0 + c0 < K; c0 += 32) {
       float v[32];
       tmem_ld32(trow + c0, v);
       if (fa < N) {
+        if (part_stride != 0 && (K & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < K) atomicAdd(dW + (int64_t)fa * K + c0 + j, v[j]);
+          for (int j = 0; j < 32; j += 4) {
+            if (k0 + c0 + j < K) {
+              float4* q = reinterpret_cast<float4*>(dst + k0 + c0 + j);
+              float4 o = *q;
+              o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+              *q = o;
+            }
+          }
+        } else if (part_stride != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k0 + c0 + j < K) dst[k0 + c0 + j] += v[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k0 + c0 + j < K) atomicAdd(dst + k0 + c0 + j, v[j]);
+        }
       }
     }
-    if (db != nullptr && fa < N) atomicAdd(db + fa, bsum);
+    if (db != nullptr && fa < N && blockIdx.z == 0) atomicAdd(db + fa, bsum);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NTK) : "memory");
 }
 
+constexpr int TC_DW_SPLITS = 296;  // slots of the dW split buffer: two CTAs per SM
+
+__global__ void dw_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int splits, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * total + i];
+  grad[i] += acc;
+}
+
+int tc_dw_splits() { return TC_DW_SPLITS; }
+
+int launch_dw_reduce(float* grad, const float* part, int total, cudaStream_t st) {
+  dw_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(grad, part, TC_DW_SPLITS, total);
+  HB_LAUNCH_DONE(st, "dw_reduce");
+  return HB_OK;
+}
+
 template <int NTK>
 static int launch_tc_dw_ntk(int passes, const float* dZ, int N, const float* X, int ldx, int K, float* dW, float* db,
-                            int64_t M, cudaStream_t st) {
-  const int nb = (N + 127) / 128;
-  int64_t splits = (2 * 148 + nb - 1) / nb;
-  int64_t rows_per = ceil_div64(M, splits);
-  rows_per = (rows_per + 31) / 32 * 32;
-  if (rows_per < 128) rows_per = 128;
-  splits = ceil_div64(M, rows_per);
+                            int64_t M, int64_t part_stride, cudaStream_t st) {
+  const int nb = (N + 127) / 128, kb = (ldx + NTK - 1) / NTK;
+  int64_t splits, rows_per;
+  if (part_stride != 0) {
+    splits = TC_DW_SPLITS;
+    rows_per = (ceil_div64(M, splits) + 31) / 32 * 32;
+  } else {
+    splits = (3 * 148 + nb * kb - 1) / (nb * kb);
+    rows_per = (ceil_div64(M, splits) + 31) / 32 * 32;
+    if (rows_per < 128) rows_per = 128;
+    splits = ceil_div64(M, rows_per);
+  }
   const size_t smem = sizeof(TcDwSmem<NTK>) + 1024;
-  dim3 grid((unsigned)splits, nb);
+  dim3 grid((unsigned)splits, nb, kb);
   if (passes == 3) {
     auto kern = tc_dw_accum_kernel<NTK, 3>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, 128, smem, st>>>(dZ, N, X, ldx, K, dW, db, M, rows_per);
+    kern<<<grid, 128, smem, st>>>(dZ, N, X, ldx, K, dW, db, M, rows_per, part_stride);
   } else {
     auto kern = tc_dw_accum_kernel<NTK, 1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, 128, smem, st>>>(dZ, N, X, ldx, K, dW, db, M, rows_per);
+    kern<<<grid, 128, smem, st>>>(dZ, N, X, ldx, K, dW, db, M, rows_per, part_stride);
   }
   HB_LAUNCH_DONE(st, shape_label(passes == 3 ? "tc_dw_accum_3xtf32" : "tc_dw_accum_tf32", M, N, K));
   return HB_OK;
 }
 
 int launch_tc_dw_accum(int passes, const float* dZ, int N, const float* X, int ldx, int K, float* dW, float* db,
-                       int64_t M, cudaStream_t st) {
+                       int64_t M, int64_t part_stride, cudaStream_t st) {
   if (M <= 0) return HB_OK;
   switch (tc_nt_of(ldx)) {
-    case 32: return launch_tc_dw_ntk<32>(passes, dZ, N, X, ldx, K, dW, db, M, st);
-    case 64: return launch_tc_dw_ntk<64>(passes, dZ, N, X, ldx, K, dW, db, M, st);
-    case 128: return launch_tc_dw_ntk<128>(passes, dZ, N, X, ldx, K, dW, db, M, st);
-    default: return launch_tc_dw_ntk<256>(passes, dZ, N, X, ldx, K, dW, db, M, st);
+    case 32: return launch_tc_dw_ntk<32>(passes, dZ, N, X, ldx, K, dW, db, M, part_stride, st);
+    case 64: return launch_tc_dw_ntk<64>(passes, dZ, N, X, ldx, K, dW, db, M, part_stride, st);
+    case 128: return launch_tc_dw_ntk<128>(passes, dZ, N, X, ldx, K, dW, db, M, part_stride, st);
+    default: return launch_tc_dw_ntk<256>(passes, dZ, N, X, ldx, K, dW, db, M, part_stride, st);
   }
 }
 

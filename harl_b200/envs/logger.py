@@ -29,11 +29,16 @@ class OnPolicyLogger:
         self.start = time.time()
         self.episodes = episodes
         self.train_episode_rewards = None
-        self.done_sum = None
+        self.done_sum = getattr(self, "_device_done_sum", None)
         self.fps = 0
 
     def episode_init(self, episode):
         self.episode = episode
+
+    def attach_device_stats(self, done_sum):
+        """The zero-copy rollout keeps (sum of finished episode returns, count) in a device double[2] updated by the
+        insert kernel; ``per_step`` is then not called."""
+        self.done_sum = self._device_done_sum = done_sum
 
     def per_step(self, data):
         """Accumulate per-env episode returns (mean over agents of the summed reward), device-side."""

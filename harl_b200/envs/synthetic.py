@@ -160,6 +160,54 @@ class SyntheticBatchedEnv:
         self.last_bad_transition = bad
         return obs, share, rewards, dones, LazyInfos(bad), avail
 
+    team_reward = True  # one reward per env broadcast to all agents (pettingzoo_mpe_env.py:56-57, StarCraft2_Env.py:681)
+
+    def step_into(self, dst):
+        """Zero-copy variant of ``step``: write this step's outputs straight into the rollout-buffer slots.
+
+        ``dst``: obs (list per agent, [N, od]), share_obs, rewards (critic slot), avail (list or None entries),
+        actions (list per agent -- ignored by the synthetic dynamics), dones / bad ([N, A] uint8)."""
+        self._t += 1
+        self.steps_served += 1
+        k = self._t % self.pool
+        A = self.n_agents
+        for a in range(A):
+            dst["obs"][a].copy_(self._obs[k, a])
+        dst["share_obs"].copy_(self._state[k])
+        rew = self._rew[k, :, 0]
+        dst["rewards"].copy_(rew if self.state_type == "EP" else rew.unsqueeze(1).expand(-1, A, -1))
+        if dst.get("rewards_na") is not None:
+            dst["rewards_na"].copy_(rew.expand(-1, A))
+        if self._simple:
+            self._ep_step_host += 1
+            done = self._ep_step_host >= self.episode_limit
+            if done:
+                self._ep_step_host = 0
+            if getattr(self, "_last_done_written", None) is not done or dst["dones"].data_ptr() != getattr(self, "_last_done_ptr", 0):
+                dst["dones"].fill_(1 if done else 0)
+                dst["bad"].fill_(1 if done else 0)
+                self._last_done_written, self._last_done_ptr = done, dst["dones"].data_ptr()
+            if self._avail is not None and self._avail.shape[0] > 1:
+                av = self._avail_view(k)
+                for a in range(A):
+                    dst["avail"][a].copy_(av[:, a])
+        else:
+            r = self._rand[k]
+            self._ep_step += 1
+            trunc = self._ep_step >= self.episode_limit
+            self._dead |= r[:, :A] < self.death_prob
+            env_done = trunc | self._dead.all(1) | (r[:, A] < self.terminate_prob)
+            dones = self._dead | env_done[:, None]
+            dst["dones"].copy_(dones)
+            dst["bad"].copy_((trunc & env_done)[:, None].expand(-1, A))
+            self._ep_step = torch.where(env_done, torch.zeros_like(self._ep_step), self._ep_step)
+            self._dead = self._dead & ~env_done[:, None]
+            av = self._avail_view(k, dones & ~env_done[:, None])
+            if av is not None:
+                for a in range(A):
+                    dst["avail"][a].copy_(av[:, a])
+            self.last_bad_transition = dst["bad"].bool()
+
     def seed(self, seed):
         pass
 

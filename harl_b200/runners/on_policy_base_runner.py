@@ -87,6 +87,8 @@ class OnPolicyBaseRunner:
                                                       self.envs.action_space[a], device=self.device)
                           for a in range(self.num_agents)]
 
+        for i, a in enumerate(self.actor):  # sampling streams: a function of (seed, rank, agent) only
+            a._seed = ((int(seed) * 1000003 + 7919 * self.rank + i + 1) * 2654435761) & (2**63 - 1)
         train_local = {**algo_args["train"], "n_rollout_threads": self.n_local}
         self.actor_buffer = [OnPolicyActorBuffer({**train_local, **algo_args["model"]}, self.envs.observation_space[a],
                                                  self.envs.action_space[a], device=self.device)
@@ -127,13 +129,16 @@ class OnPolicyBaseRunner:
         self.logger.episode_init(episode)
         self.prep_rollout()
         marks = self._phase_mark(None, None)
-        for step in range(tr["episode_length"]):
+        fast = self._fast_rollout_ready()
+        for step in range(tr["episode_length"] if not fast else 0):
             values, actions, action_log_probs, rnn_states, rnn_states_critic = self.collect(step)
             obs, share_obs, rewards, dones, infos, available_actions = self.envs.step(actions)
             data = (obs, share_obs, rewards, dones, infos, available_actions, values, actions, action_log_probs,
                     rnn_states, rnn_states_critic)
             self.logger.per_step(data)
             self.insert(data)
+        if fast:
+            self._fast_rollout()
         marks = self._phase_mark(marks, "rollout")
         self.compute()
         marks = self._phase_mark(marks, "compute")
@@ -163,6 +168,90 @@ class OnPolicyBaseRunner:
             torch.cuda.synchronize()
             self.phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         return marks
+
+    # ------------------------------------------------------------------ zero-copy rollout (device-resident envs)
+    def _fast_rollout_ready(self):
+        """The lean rollout loop applies when the env lives on the training device and can write its outputs
+        straight into the buffer slots (``step_into``); otherwise the generic collect/step/insert loop runs."""
+        if getattr(self, "_fast", None) is None:
+            ok = (self.device.type == "cuda" and hasattr(self.envs, "step_into")
+                  and getattr(self.envs, "device", None) == self.device and not self.actor_buffer[0].recurrent
+                  and not self.critic_buffer.recurrent and not getattr(self, "disable_fast_rollout", False))
+            self._fast = self._build_fast_path() if ok else False
+        return bool(self._fast)
+
+    def _build_fast_path(self):
+        """Per-step argument structs with every slot pointer baked in (the buffers never move)."""
+        T = self.algo_args["train"]["episode_length"]
+        N, A = self.n_local, self.num_agents
+        cb = self.critic_buffer
+        fp = self.state_type == "FP"
+        team = bool(getattr(self.envs, "team_reward", False))
+        self._ep_return = torch.zeros(N, dtype=torch.float32, device=self.device)
+        self._done_sum = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._dones_u8 = torch.zeros(N, A, dtype=torch.uint8, device=self.device)
+        self._bad_u8 = torch.zeros(N, A, dtype=torch.uint8, device=self.device)
+        self._rewards_na = torch.zeros(N, A, dtype=torch.float32, device=self.device)
+        if hasattr(self.logger, "attach_device_stats"):
+            self.logger.attach_device_stats(self._done_sum)
+        nets = [a.actor for a in self.actor] + [self.critic.critic]
+        ws_bytes = max(L.lib.hb_workspace_bytes(C.byref(n.desc), N * (A if fp else 1), 0) for n in nets)
+        from ..nets import workspace
+
+        self._fast_ws = workspace(self.device, ws_bytes)
+        collect, insert, dst = [], [], []
+        for s in range(T):
+            c = L.CollectArgs()
+            c.n_agents, c.deterministic, c.rows = A, 0, N
+            for i, (actor, b) in enumerate(zip(self.actor, self.actor_buffer)):
+                c.actor_desc[i] = C.pointer(actor.actor.desc)
+                c.actor_prepared[i] = L.ptr(actor.actor.prepared)
+                c.obs[i] = L.ptr(b.obs[s])
+                c.avail[i] = L.ptr(b.available_actions[s]) if b.available_actions is not None else None
+                c.actions[i], c.logp[i] = L.ptr(b.actions[s]), L.ptr(b.action_log_probs[s])
+                c.seed[i] = actor._seed
+            c.critic_desc = C.pointer(self.critic.critic.desc)
+            c.critic_prepared = L.ptr(self.critic.critic.prepared)
+            c.share_obs, c.critic_rows, c.values = L.ptr(cb.share_obs[s]), cb.value_preds[s].numel(), L.ptr(cb.value_preds[s])
+            collect.append(c)
+            a = L.InsertArgs()
+            a.n_envs, a.n_agents, a.state_type_fp = N, A, int(fp)
+            a.dones, a.bad_transition = L.ptr(self._dones_u8), L.ptr(self._bad_u8)
+            for i, b in enumerate(self.actor_buffer):
+                a.actor_masks_next[i], a.actor_active_next[i] = L.ptr(b.masks[s + 1]), L.ptr(b.active_masks[s + 1])
+            a.critic_masks_next, a.critic_bad_next = L.ptr(cb.masks[s + 1]), L.ptr(cb.bad_masks[s + 1])
+            # logger bookkeeping reads the reward where it already is: the critic slot (team reward, or FP per-agent
+            # rewards) or a side buffer for per-agent rewards under an EP critic
+            if fp:
+                a.rewards, a.reward_stride_n, a.reward_stride_a = L.ptr(cb.rewards[s]), A, 1
+            elif team:
+                a.rewards, a.reward_stride_n, a.reward_stride_a = L.ptr(cb.rewards[s]), 1, 0
+            else:
+                a.rewards, a.reward_stride_n, a.reward_stride_a = L.ptr(self._rewards_na), A, 1
+            a.ep_return, a.done_sum = L.ptr(self._ep_return), L.ptr(self._done_sum)
+            insert.append(a)
+            dst.append(dict(obs=[b.obs[s + 1] for b in self.actor_buffer], share_obs=cb.share_obs[s + 1],
+                            rewards=cb.rewards[s], rewards_na=None if (fp or team) else self._rewards_na,
+                            avail=[b.available_actions[s + 1] if b.available_actions is not None else None
+                                   for b in self.actor_buffer],
+                            actions=[b.actions[s] for b in self.actor_buffer], dones=self._dones_u8, bad=self._bad_u8))
+        return dict(collect=collect, insert=insert, dst=dst)
+
+    def _fast_rollout(self):
+        """T x (collect -> env.step_into -> insert): two library calls per step plus the env's own work."""
+        f = self._fast
+        ws, ws_n, st = L.ptr(self._fast_ws), self._fast_ws.numel(), L.stream_ptr()
+        step_into = self.envs.step_into
+        for s in range(len(f["collect"])):
+            c = f["collect"][s]
+            self._draws = getattr(self, "_draws", 0) + 1
+            c.offset = self._draws
+            L.call("hb_rollout_collect", C.byref(c), ws, ws_n, st)
+            step_into(f["dst"][s])
+            L.call("hb_rollout_insert_masks", C.byref(f["insert"][s]), st)
+        for b in self.actor_buffer:
+            b.step = 0
+        self.critic_buffer.step = 0
 
     def warmup(self):
         """Reset the envs and fill slot 0 (reference :269-283)."""

@@ -129,6 +129,12 @@ typedef struct hb_insert_args {
   float* critic_masks_next;
   float* critic_bad_next;
   float* critic_rnn_next;
+  /* optional episode-return bookkeeping of the logger (harl/common/base_logger.py:52-65), device-side:
+   * ep_return[n] += mean_a rewards[n,a]; when env n finishes: done_sum += (ep_return[n], 1), ep_return[n] = 0. */
+  const float* rewards;            /* element (n,a) at rewards[n*reward_stride_n + a*reward_stride_a]; NULL = off */
+  int64_t reward_stride_n, reward_stride_a;
+  float* ep_return;                /* [n_envs] */
+  double* done_sum;                /* [2] */
 } hb_insert_args;
 int hb_rollout_insert_masks(const hb_insert_args* a, void* stream);
 
@@ -138,6 +144,27 @@ int hb_rollout_insert_masks(const hb_insert_args* a, void* stream);
 int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows,
                   const float* avail, int deterministic, uint64_t seed, uint64_t offset,
                   float* actions, float* logp, void* ws, size_t ws_bytes, void* stream);
+
+/* One rollout step of OnPolicyBaseRunner.collect (on_policy_base_runner.py:285-340): get_actions for every agent
+ * and get_values for the critic in one call, each written straight into its rollout-buffer slot. */
+typedef struct hb_collect_args {
+  int32_t n_agents, deterministic;
+  int64_t rows;                                  /* rollout threads */
+  uint64_t offset;                               /* Philox stream offset of this step */
+  const hb_net_desc* actor_desc[HB_MAX_AGENTS];
+  const float* actor_prepared[HB_MAX_AGENTS];
+  const float* obs[HB_MAX_AGENTS];               /* [rows, in_dim_a] */
+  const float* avail[HB_MAX_AGENTS];             /* [rows, n_act] or NULL */
+  float* actions[HB_MAX_AGENTS];                 /* [rows, ad] */
+  float* logp[HB_MAX_AGENTS];                    /* [rows, ad] */
+  uint64_t seed[HB_MAX_AGENTS];
+  const hb_net_desc* critic_desc;                /* NULL = skip the critic */
+  const float* critic_prepared;
+  const float* share_obs;                        /* [critic_rows, sd] */
+  int64_t critic_rows;                           /* rows (EP) or rows * n_agents (FP) */
+  float* values;                                 /* [critic_rows, 1] */
+} hb_collect_args;
+int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_bytes, void* stream);
 
 /* VNet.forward (VCritic.get_values), v_net.py:48-67. values [rows,1]. */
 int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs,
