@@ -106,7 +106,7 @@ static int trunk_backward(const hb_net_desc* d, const ParamLayout& P, const Prep
     if (impl != 0)
       rc = launch_tc_dx_ln_bwd(passes, d->activation, dcur, Q.n[l], prep + Q.tkt[l], Q.tkt_chunks[l], w.Z[l - 1],
                                w.stats[l - 1], prep + Q.lnw[l - 1], dnext, grad + P.lnw[l - 1], grad + P.lnb[l - 1], rows,
-                               Q.n[l - 1], st);
+                               Q.n[l - 1], w.dwpart - grad, w.ptotal, st);
     else
       rc = launch_dx_ln_bwd(d->activation, dcur, Q.n[l], params + P.w[l], w.Z[l - 1], w.stats[l - 1], prep + Q.lnw[l - 1],
                             dnext, grad + P.lnw[l - 1], grad + P.lnb[l - 1], rows, Q.n[l - 1], st);
@@ -203,19 +203,6 @@ int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs,
 int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows, float* values,
                      void* ws, size_t ws_bytes, void* stream);
 
-int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_bytes, void* stream) {
-  using namespace hb;
-  HB_CHECK_ARG(a && a->n_agents > 0 && a->n_agents <= HB_MAX_AGENTS && a->rows > 0, "bad argument");
-  for (int i = 0; i < a->n_agents; ++i) {
-    int rc = hb_policy_act(a->actor_desc[i], a->actor_prepared[i], a->obs[i], a->rows, a->avail[i], a->deterministic,
-                           a->seed[i], a->offset, a->actions[i], a->logp[i], ws, ws_bytes, stream);
-    if (rc) return rc;
-  }
-  if (a->critic_desc != nullptr)
-    return hb_value_forward(a->critic_desc, a->critic_prepared, a->share_obs, a->critic_rows, a->values, ws, ws_bytes, stream);
-  return HB_OK;
-}
-
 int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows, float* values,
                      void* ws, size_t ws_bytes, void* stream) {
   using namespace hb;
@@ -295,7 +282,7 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
   const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
   Work w;
   if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w, L.total))) return rc;
-  if (gemm_impl() != 0) {
+  {
     ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
     if (ce != cudaSuccess) return cuda_fail(ce, "hb_ppo_actor_grad(memset split buffer)");
   }
@@ -319,10 +306,11 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
     a.scalars = scalars;
     a.ln_z = w.Z[Q.n_layers - 1]; a.ln_stats = w.stats[Q.n_layers - 1]; a.ln_w = prepared + Q.lnw[Q.n_layers - 1];
     a.g_ln_w = grad + P.lnw[Q.n_layers - 1]; a.g_ln_b = grad + P.lnb[Q.n_layers - 1]; a.ln_act = d->activation;
+    a.part_delta = w.dwpart - grad; a.part_stride = w.ptotal;
     if ((rc = launch_policy_head(d->head, MODE_GRAD, a, st))) return rc;
     if ((rc = trunk_backward(d, P, Q, params, prepared, grad, n, w, st))) return rc;
   }
-  if (gemm_impl() != 0 && (rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
+  if ((rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
   return launch_featnorm_fold(d, params, grad, st);
 }
 
@@ -345,7 +333,7 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
   const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
   Work w;
   if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w, L.total))) return rc;
-  if (gemm_impl() != 0) {
+  {
     ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
     if (ce != cudaSuccess) return cuda_fail(ce, "hb_value_grad(memset split buffer)");
   }
@@ -375,10 +363,11 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
     a.scalars = scalars;
     a.ln_z = w.Z[Q.n_layers - 1]; a.ln_stats = w.stats[Q.n_layers - 1]; a.ln_w = prepared + Q.lnw[Q.n_layers - 1];
     a.g_ln_w = grad + P.lnw[Q.n_layers - 1]; a.g_ln_b = grad + P.lnb[Q.n_layers - 1]; a.ln_act = d->activation;
+    a.part_delta = w.dwpart - grad; a.part_stride = w.ptotal;
     if ((rc = launch_value_head(1, a, st))) return rc;
     if ((rc = trunk_backward(d, P, Q, params, prepared, grad, n, w, st))) return rc;
   }
-  if (gemm_impl() != 0 && (rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
+  if ((rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
   return launch_featnorm_fold(d, params, grad, st);
 }
 }

@@ -139,6 +139,12 @@ __device__ __forceinline__ float act_bwd_rt(int act, float z) {
   }
 }
 
+// gradient-sum output: plain RMW into this CTA's split-buffer slot (slot != 0) or a global atomic
+__device__ __forceinline__ void acc_out(float* p, float v, int64_t slot) {
+  if (slot != 0) p[slot] += v;
+  else atomicAdd(p, v);
+}
+
 // Philox4x32-10 (Salmon et al. 2011), counter-based: one call -> 4 x 32 random bits.
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -42,6 +42,9 @@ struct HeadArgs {
   // fused LayerNorm + activation backward of the last trunk block (grad mode, when ln_z != nullptr):
   // dfeat then receives dZ_L instead of d/d features, and the LN affine gradients are accumulated here
   const float* ln_z; const float* ln_stats; const float* ln_w; float* g_ln_w; float* g_ln_b; int ln_act;
+  // parameter-gradient sums go to slot blockIdx.x of a split buffer (g_ptr + part_delta + blockIdx.x * part_stride, plain
+  // read-modify-write, summed once per call by dw_reduce) instead of same-address global atomics; 0 = atomics
+  int64_t part_delta, part_stride;
 };
 
 struct ValueArgs {
@@ -55,6 +58,7 @@ struct ValueArgs {
   int use_huber, use_clipped;
   float* dfeat; float* g_hw; float* g_hbias; double* scalars;  // scalars += (loss_sum, rows)
   const float* ln_z; const float* ln_stats; const float* ln_w; float* g_ln_w; float* g_ln_b; int ln_act;  // as in HeadArgs
+  int64_t part_delta, part_stride;
 };
 
 // launchers (gemm_simt.cu, rowwise.cu, optim.cu)
@@ -76,7 +80,7 @@ int launch_tc_linear_ln_fwd(int passes, int act, const float* X, int ldx, const 
 
 int launch_tc_dx_ln_bwd(int passes, int act, const float* dZ, int N, const float* tiles, int nchunks, const float* Zp,
                         const float* stats_p, const float* lnw_p, float* dZp, float* g_lnw_p, float* g_lnb_p, int64_t M,
-                        int Np, cudaStream_t st);
+                        int Np, int64_t part_delta, int64_t part_stride, cudaStream_t st);
 int launch_tc_dw_accum(int passes, const float* dZ, int N, const float* X, int ldx, int K, float* dW, float* db,
                        int64_t M, int64_t part_stride, cudaStream_t st);
 int tc_dw_splits();

@@ -44,7 +44,7 @@ int tc_nt_of(int n);
 int launch_pack_umma_tiles(const float* W, int ldn, int ldk, const float* scale, int N, int K, int NT, int nchunks,
                            float* dst, cudaStream_t st);
 
-static std::atomic<int> g_gemm_impl{0};
+static std::atomic<int> g_gemm_impl{1};  // default: tcgen05 with the fp32-accurate 3xTF32 split
 int gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 
 int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_layout* out) {

@@ -14,6 +14,14 @@ constexpr int ROW_THREADS = 256;
 constexpr int ROW_WARPS = ROW_THREADS / 32;
 #define HB_LOG_2PI_F 1.8378770664093453f
 
+int tc_dw_splits();
+// grid of a gradient kernel that owns one split-buffer slot per CTA
+static int slot_grid(int64_t rows) {
+  int64_t g = ceil_div64(rows, ROW_WARPS);
+  int64_t cap = tc_dw_splits();
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
 static int row_grid(int64_t rows) {
   int64_t g = ceil_div64(rows, ROW_WARPS);
   int64_t cap = 148 * 8;
@@ -208,7 +216,7 @@ __device__ __forceinline__ float dmin_dratio(float ratio, float adv, float clip,
 // LayerNorm + activation backward of one row held lane-strided by a warp (fused tail of the head kernels).
 // df: d loss / d (LN output) for columns lane + 32 q.  Writes dZ to out_row; accumulates dgamma / dbeta partials.
 template <int HPL>
-__device__ __forceinline__ void ln_act_bwd_row(const float (&df)[HPL], const float* __restrict__ zrow, float mu, float rstd,
+__device__ __forceinline__ void ln_act_bwd_row(const float (&df)[HPL], const float (&zrow)[HPL], float mu, float rstd,
                                                const float* __restrict__ lnw, int h, int act, int lane,
                                                float* __restrict__ out_row, float (&cg)[HPL], float (&cb)[HPL]) {
   float g[HPL], xh[HPL], da[HPL];
@@ -218,7 +226,7 @@ __device__ __forceinline__ void ln_act_bwd_row(const float (&df)[HPL], const flo
     const int n = lane + 32 * q;
     g[q] = xh[q] = da[q] = 0.f;
     if (n < h) {
-      const float z = zrow[n];
+      const float z = zrow[q];
       const float x = (act_fwd_rt(act, z) - mu) * rstd;
       cg[q] = fmaf(df[q], x, cg[q]);
       cb[q] += df[q];
@@ -241,14 +249,15 @@ __device__ __forceinline__ void ln_act_bwd_row(const float (&df)[HPL], const flo
 // block-level reduction of the per-lane LN-affine partial sums (all warps) into global memory
 template <int HPL>
 __device__ __forceinline__ void ln_affine_flush(const float (&cg)[HPL], const float (&cb)[HPL], int h, int lane,
-                                                float* sacc /* [2][256] shared, zeroed */, float* g_ln_w, float* g_ln_b) {
+                                                float* sacc /* [2][256] shared, zeroed */, float* g_ln_w, float* g_ln_b,
+                                                int64_t slot) {
 #pragma unroll
   for (int q = 0; q < HPL; ++q) {
     const int n = lane + 32 * q;
     if (n < h) { atomicAdd(&sacc[n], cg[q]); atomicAdd(&sacc[256 + n], cb[q]); }
   }
   __syncthreads();
-  for (int n = threadIdx.x; n < h; n += ROW_THREADS) { atomicAdd(g_ln_w + n, sacc[n]); atomicAdd(g_ln_b + n, sacc[256 + n]); }
+  for (int n = threadIdx.x; n < h; n += ROW_THREADS) { acc_out(g_ln_w + n, sacc[n], slot); acc_out(g_ln_b + n, sacc[256 + n], slot); }
 }
 
 // ---- Categorical (distributions.py:7-21,37-55; act.py:44-80,143-155)
@@ -285,10 +294,22 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
     const int64_t src = a.index ? (int64_t)a.index[r] : r;
     float f[HPL];
     load_feat<HPL>(a.feat + r * h, h, lane, f);
-    float logit = head_linear<HPL>(f, shw, h, na, sb, lane);
     const bool valid = lane < na;
     bool masked = false;
     if (valid && a.avail != nullptr) masked = a.avail[src * na + lane] == 0.f;
+    // issue every load of this row up front (one memory round trip per row instead of one per use)
+    float zr[HPL], ln_mu = 0.f, ln_rs = 0.f, sc_act = 0.f, sc_w = 1.f, sc_fac = 1.f, sc_adv = 0.f, sc_old = 0.f;
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) zr[q] = 0.f;
+    if constexpr (MODE == MODE_GRAD) {
+      if (a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, zr); ln_mu = a.ln_stats[r * 2]; ln_rs = a.ln_stats[r * 2 + 1]; }
+      sc_act = a.actions[src];
+      sc_w = a.use_active ? a.active[src] : 1.f;
+      sc_fac = a.factor ? a.factor[src] : 1.f;
+      sc_adv = a.adv[src];
+      sc_old = a.old_logp[src];
+    }
+    float logit = head_linear<HPL>(f, shw, h, na, sb, lane);
     if (masked) logit = -1e10f;
     const float mx = warp_max(valid ? logit : -INFINITY);
     const float ex = valid ? expf(logit - mx) : 0.f;
@@ -327,13 +348,11 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
       }
     } else {
     // ---- MODE_GRAD: happo.py:66-91
-    const int act = (int)a.actions[src];
+    const int act = (int)sc_act;
     const float lpa = __shfl_sync(0xffffffffu, lp, act);
     const float ent = -warp_sum(valid ? fmaxf(lp, -3.4028234663852886e38f) * p : 0.f);
-    const float w = a.use_active ? a.active[src] : 1.f;
-    const float fac = a.factor ? a.factor[src] : 1.f;
-    const float adv = a.adv[src];
-    const float ratio = expf(lpa - a.old_logp[src]);
+    const float w = sc_w, fac = sc_fac, adv = sc_adv;
+    const float ratio = expf(lpa - sc_old);
     float m;
     const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
     const float c_lp = -fac * w * inv_norm * dm * ratio;       // d obj / d logp(action)
@@ -359,8 +378,7 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
 #pragma unroll
     for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h && a.ln_z == nullptr) a.dfeat[r * h + n] = df[q]; }
     if (a.ln_z != nullptr)
-      ln_act_bwd_row<HPL>(df, a.ln_z + r * h, a.ln_stats[r * 2], a.ln_stats[r * 2 + 1], a.ln_w, h, a.ln_act, lane,
-                          a.dfeat + r * h, lcg, lcb);
+      ln_act_bwd_row<HPL>(df, zr, ln_mu, ln_rs, a.ln_w, h, a.ln_act, lane, a.dfeat + r * h, lcg, lcb);
     }
   }
   if constexpr (MODE == MODE_GRAD) {
@@ -372,10 +390,11 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
       }
     if (lane < na) atomicAdd(&sgb[lane], gb);
     __syncthreads();
-    for (int i = threadIdx.x; i < na * h; i += ROW_THREADS) atomicAdd(a.g_hw + i, sg[i]);
-    if (threadIdx.x < na) atomicAdd(a.g_hbias + threadIdx.x, sgb[threadIdx.x]);
+    const int64_t slot = a.part_stride ? a.part_delta + (int64_t)blockIdx.x * a.part_stride : 0;
+    for (int i = threadIdx.x; i < na * h; i += ROW_THREADS) acc_out(a.g_hw + i, sg[i], slot);
+    if (threadIdx.x < na) acc_out(a.g_hbias + threadIdx.x, sgb[threadIdx.x], slot);
     block_add_scalars(s_loss, s_ent, s_ratio, s_rows, a.scalars, sred);
-    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b);
+    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b, slot);
   }
 }
 
@@ -420,6 +439,12 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
     const int64_t src = a.index ? (int64_t)a.index[r] : r;
     float f[HPL];
     load_feat<HPL>(a.feat + r * h, h, lane, f);
+    float zr[HPL], ln_mu = 0.f, ln_rs = 0.f;
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) zr[q] = 0.f;
+    if constexpr (MODE == MODE_GRAD) {
+      if (a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, zr); ln_mu = a.ln_stats[r * 2]; ln_rs = a.ln_stats[r * 2 + 1]; }
+    }
     const float mean = head_linear<HPL>(f, shw, h, ad, sb, lane);
     if constexpr (MODE == MODE_ACT) {
       float act = mean;
@@ -496,8 +521,7 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
 #pragma unroll
     for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h && a.ln_z == nullptr) a.dfeat[r * h + n] = df[q]; }
     if (a.ln_z != nullptr)
-      ln_act_bwd_row<HPL>(df, a.ln_z + r * h, a.ln_stats[r * 2], a.ln_stats[r * 2 + 1], a.ln_w, h, a.ln_act, lane,
-                          a.dfeat + r * h, lcg, lcb);
+      ln_act_bwd_row<HPL>(df, zr, ln_mu, ln_rs, a.ln_w, h, a.ln_act, lane, a.dfeat + r * h, lcg, lcb);
     }
     }
   }
@@ -510,10 +534,11 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
       }
     if (valid) { atomicAdd(&sgb[lane], gb); atomicAdd(&sgb[32 + lane], gs); }
     __syncthreads();
-    for (int i = threadIdx.x; i < ad * h; i += ROW_THREADS) atomicAdd(a.g_hw + i, sg[i]);
-    if (threadIdx.x < ad) { atomicAdd(a.g_hbias + threadIdx.x, sgb[threadIdx.x]); atomicAdd(a.g_log_std + threadIdx.x, sgb[32 + threadIdx.x]); }
+    const int64_t slot = a.part_stride ? a.part_delta + (int64_t)blockIdx.x * a.part_stride : 0;
+    for (int i = threadIdx.x; i < ad * h; i += ROW_THREADS) acc_out(a.g_hw + i, sg[i], slot);
+    if (threadIdx.x < ad) { acc_out(a.g_hbias + threadIdx.x, sgb[threadIdx.x], slot); acc_out(a.g_log_std + threadIdx.x, sgb[32 + threadIdx.x], slot); }
     block_add_scalars(s_loss, s_ent, s_ratio, s_rows, a.scalars, sred);
-    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b);
+    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b, slot);
   }
 }
 
@@ -521,7 +546,7 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
   do {                                                                                                        \
     auto kern = KERN<HPLV, MAXJV, MODEV>;                                                                     \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    kern<<<row_grid(a.rows), ROW_THREADS, smem, st>>>(a);                                                     \
+    kern<<<(MODEV == MODE_GRAD && a.part_stride) ? slot_grid(a.rows) : row_grid(a.rows), ROW_THREADS, smem, st>>>(a);                                                     \
   } while (0)
 
 template <int MODE>
@@ -603,6 +628,10 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
   for (int64_t r = w0; r < a.rows; r += nw) {
     float f[HPL];
     load_feat<HPL>(a.feat + r * h, h, lane, f);
+    float zr[HPL], ln_mu = 0.f, ln_rs = 0.f;
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) zr[q] = 0.f;
+    if (GRAD && a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, zr); ln_mu = a.ln_stats[r * 2]; ln_rs = a.ln_stats[r * 2 + 1]; }
     float p = 0.f;
 #pragma unroll
     for (int q = 0; q < HPL; ++q) p = fmaf(f[q], wv[q], p);
@@ -636,25 +665,25 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
       if (n < h) { df[q] = g * wv[q]; gw[q] = fmaf(g, f[q], gw[q]); if (a.ln_z == nullptr) a.dfeat[r * h + n] = df[q]; }
     }
     if (a.ln_z != nullptr)
-      ln_act_bwd_row<HPL>(df, a.ln_z + r * h, a.ln_stats[r * 2], a.ln_stats[r * 2 + 1], a.ln_w, h, a.ln_act, lane,
-                          a.dfeat + r * h, lcg, lcb);
+      ln_act_bwd_row<HPL>(df, zr, ln_mu, ln_rs, a.ln_w, h, a.ln_act, lane, a.dfeat + r * h, lcg, lcb);
   }
   if (GRAD) {
 #pragma unroll
     for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h) atomicAdd(&sgw[n], gw[q]); }
     if (lane == 0) atomicAdd(&sgb, gbias);
     __syncthreads();
-    for (int n = threadIdx.x; n < h; n += ROW_THREADS) atomicAdd(a.g_hw + n, sgw[n]);
-    if (threadIdx.x == 0) atomicAdd(a.g_hbias, sgb);
+    const int64_t slot = a.part_stride ? a.part_delta + (int64_t)blockIdx.x * a.part_stride : 0;
+    for (int n = threadIdx.x; n < h; n += ROW_THREADS) acc_out(a.g_hw + n, sgw[n], slot);
+    if (threadIdx.x == 0) acc_out(a.g_hbias, sgb, slot);
     block_add_scalars(s_loss, s_rows, 0.0, 0.0, a.scalars, sred);
-    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b);
+    if (a.ln_z != nullptr) ln_affine_flush<HPL>(lcg, lcb, h, lane, s_ln, a.g_ln_w, a.g_ln_b, slot);
   }
 }
 
 int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st) {
   if (a.rows <= 0) return HB_OK;
   const int hpl = a.h <= 32 ? 1 : a.h <= 64 ? 2 : a.h <= 128 ? 4 : 8;
-  const int g = row_grid(a.rows);
+  const int g = (grad && a.part_stride) ? slot_grid(a.rows) : row_grid(a.rows);
 #define HB_V(H)                                                                 \
   case H:                                                                       \
     if (grad) value_head_kernel<H, 1><<<g, ROW_THREADS, 0, st>>>(a);            \

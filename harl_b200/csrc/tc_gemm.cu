@@ -333,6 +333,8 @@ int launch_tc_linear_ln_fwd(int passes, int act, const float* X, int ldx, const 
 // =====================================================================================================
 namespace hb {
 
+__host__ __device__ constexpr int tc_dw_splits_c() { return 296; }
+
 // Column sums over the 32 lanes of a warp for 32 per-lane values: lane l ends with sum_lanes v[l].
 // Reduce-scatter butterfly: 31 shuffles instead of 32 full reductions.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
                                                               const float* __restrict__ Zp, const float* __restrict__ stats_p,
                                                               const float* __restrict__ lnw_p, float* __restrict__ dZp,
                                                               float* __restrict__ g_lnw_p, float* __restrict__ g_lnb_p,
-                                                              int64_t M, int Np) {
+                                                              int64_t M, int Np, int64_t part_delta, int64_t part_stride) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem<NT>& s = *reinterpret_cast<TcSmem<NT>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -510,7 +512,10 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
     }
   }
   __syncthreads();
-  for (int n = tid; n < Np; n += 128) { atomicAdd(g_lnw_p + n, colsum[n]); atomicAdd(g_lnb_p + n, colsum[NT + n]); }
+  {
+    const int64_t slot = (part_stride && blockIdx.x < (unsigned)tc_dw_splits_c()) ? part_delta + (int64_t)blockIdx.x * part_stride : 0;
+    for (int n = tid; n < Np; n += 128) { acc_out(g_lnw_p + n, colsum[n], slot); acc_out(g_lnb_p + n, colsum[NT + n], slot); }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NT) : "memory");
@@ -519,14 +524,14 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
 template <int NT, int PASSES>
 static int launch_tc_dx_nt(int act, const float* dZ, int N, const float* tiles, int nchunks, const float* Zp,
                            const float* stats_p, const float* lnw_p, float* dZp, float* g_lnw_p, float* g_lnb_p,
-                           int64_t M, int Np, cudaStream_t st) {
+                           int64_t M, int Np, int64_t part_delta, int64_t part_stride, cudaStream_t st) {
   const size_t smem = sizeof(TcSmem<NT>) + 1024;
   dim3 grid((unsigned)ceil_div64(M, TC_BM));
 #define HB_TC_CASE(A)                                                                                       \
   case A: {                                                                                                 \
     auto kern = tc_dx_ln_bwd_kernel<NT, A, PASSES>;                                                         \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
-    kern<<<grid, 128, smem, st>>>(dZ, N, tiles, nchunks, Zp, stats_p, lnw_p, dZp, g_lnw_p, g_lnb_p, M, Np); \
+    kern<<<grid, 128, smem, st>>>(dZ, N, tiles, nchunks, Zp, stats_p, lnw_p, dZp, g_lnw_p, g_lnb_p, M, Np, part_delta, part_stride); \
   } break;
   switch (act) {
     HB_TC_CASE(HB_ACT_RELU) HB_TC_CASE(HB_ACT_TANH) HB_TC_CASE(HB_ACT_SIGMOID) HB_TC_CASE(HB_ACT_LEAKY_RELU)
@@ -540,12 +545,12 @@ static int launch_tc_dx_nt(int act, const float* dZ, int N, const float* tiles, 
 
 int launch_tc_dx_ln_bwd(int passes, int act, const float* dZ, int N, const float* tiles, int nchunks, const float* Zp,
                         const float* stats_p, const float* lnw_p, float* dZp, float* g_lnw_p, float* g_lnb_p, int64_t M,
-                        int Np, cudaStream_t st) {
+                        int Np, int64_t part_delta, int64_t part_stride, cudaStream_t st) {
   if (M <= 0) return HB_OK;
 #define HB_TC_NT(NTV)                                                                                                   \
   case NTV:                                                                                                             \
-    return passes == 3 ? launch_tc_dx_nt<NTV, 3>(act, dZ, N, tiles, nchunks, Zp, stats_p, lnw_p, dZp, g_lnw_p, g_lnb_p, M, Np, st) \
-                       : launch_tc_dx_nt<NTV, 1>(act, dZ, N, tiles, nchunks, Zp, stats_p, lnw_p, dZp, g_lnw_p, g_lnb_p, M, Np, st);
+    return passes == 3 ? launch_tc_dx_nt<NTV, 3>(act, dZ, N, tiles, nchunks, Zp, stats_p, lnw_p, dZp, g_lnw_p, g_lnb_p, M, Np, part_delta, part_stride, st) \
+                       : launch_tc_dx_nt<NTV, 1>(act, dZ, N, tiles, nchunks, Zp, stats_p, lnw_p, dZp, g_lnw_p, g_lnb_p, M, Np, part_delta, part_stride, st);
   switch (tc_nt_of(Np)) { HB_TC_NT(32) HB_TC_NT(64) HB_TC_NT(128) HB_TC_NT(256) }
 #undef HB_TC_NT
   return HB_ERR_UNSUPPORTED;
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NTK) : "memory");
 }
 
-constexpr int TC_DW_SPLITS = 296;  // slots of the dW split buffer: two CTAs per SM
+constexpr int TC_DW_SPLITS = tc_dw_splits_c();  // slots of the split buffer: two CTAs per SM
 
 __global__ void dw_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int splits, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -99,8 +99,8 @@ uint64_t hb_kernel_launch_count(void);
 int hb_profile_begin(void* stream);
 int hb_profile_end(char* out, int out_size);
 
-/* GEMM implementation of the MLP blocks: 0 = FP32 SIMT (default), 1 = tcgen05 tensor cores with the
- * error-compensated 3xTF32 split (fp32-level accuracy), 2 = tcgen05 plain TF32.  Call hb_net_prepare after
+/* GEMM implementation of the MLP blocks: 0 = FP32 SIMT, 1 = tcgen05 tensor cores with the error-compensated
+ * 3xTF32 split (fp32-level accuracy; default), 2 = tcgen05 plain TF32.  Call hb_net_prepare after
  * changing it (the tensor-core path reads pre-packed operand images from the prepared buffer). */
 int hb_set_gemm_impl(int impl);
 int hb_get_gemm_impl(void);
