@@ -21,6 +21,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -152,7 +153,9 @@ def kernel_profile(runner, torch):
     runner.compute()
     torch.cuda.synchronize()
     L.call("hb_profile_begin", L.stream_ptr())
+    overlap, runner.overlap_critic_update = getattr(runner, "overlap_critic_update", True), False  # one stream: clean gaps
     runner.train()
+    runner.overlap_critic_update = overlap
     buf = C.create_string_buffer(1 << 16)
     n = L.lib.hb_profile_end(buf, len(buf))
     runner.after_update()
@@ -163,30 +166,66 @@ def kernel_profile(runner, torch):
     return rows
 
 
-def roofline_of(rows, peaks):
-    """Roofline entry for the kernel label with the largest share of the step.
+GEMM_LABEL = re.compile(r"^(tc_)?(linear_ln_fwd|dx_ln_bwd|dw_accum)")
 
-    GEMM kernels (the MLP layers -- tensor-pipe work by BASELINE.json's own classification) are rated
-    in FLOP/s against the measured dense bf16 peak; everything else in algorithmic bytes against HBM."""
-    import re
+
+def _algorithmic(label):
+    """(kind, amount per launch) of a profiled kernel label ``name[M..,N..,K..]``."""
+    m = re.match(r"([\w]+)\[M(\d+),N(\d+),K(\d+)\]", label)
+    if not m:
+        return None, None
+    name, M, N, K = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4))
+    if GEMM_LABEL.match(name):
+        return "flops", 2.0 * M * N * K  # algorithmic: one fp32-accurate product (3xTF32 issues 3 MMAs for it)
+    if name.startswith("policy_head_grad"):  # features + pre-LN z + dZ out (K floats each) + stats + 5 row scalars + avail
+        return "bytes", M * (12.0 * K + 8 + 20 + 4 * N)
+    if name.startswith("value_head_grad"):
+        return "bytes", M * (12.0 * K + 8 + 8)
+    if name.startswith("policy_head") or name.startswith("value_head"):
+        return "bytes", M * (4.0 * K + 8 + 4 * N)
+    if name.startswith("feat_norm"):  # N = padded output width, K = input width
+        return "bytes", M * 4.0 * (K + N)
+    return None, None
+
+
+def _rate(row, peaks):
+    label, cnt, ms = row
+    kind, amount = _algorithmic(label)
+    sec = 1e-3 * ms / cnt
+    tf_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+    hbm_peak = peaks.get("hbm_gbs_sustained") or peaks.get("hbm_gbs")
+    if kind == "flops":
+        ach = amount / sec / 1e12
+        return dict(bound="tensor", achieved=ach, peak=tf_peak, unit="TFLOP/s", frac=ach / tf_peak, flops_per_launch=amount)
+    if kind == "bytes":
+        ach = amount / sec / 1e9
+        return dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, bytes_per_launch=amount)
+    return dict(bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None)
+
+
+def roofline_of(rows, peaks):
+    """Roofline entry for the kernel label with the largest share of the update phase.
+
+    GEMM kernels (the MLP layers -- tensor-pipe work by BASELINE.json's own classification) are rated in algorithmic
+    FLOP/s (2MNK) against the measured dense bf16 peak; row-wise kernels in algorithmic bytes against measured HBM
+    bandwidth.  ``top_gemm`` rates the largest GEMM label the same way when the top label is not a GEMM."""
+    from harl_b200 import _lib as L
 
     total = sum(r[2] for r in rows) or 1.0
     label, cnt, ms = rows[0]
     out = {"kernel": label, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share_of_update_phase": ms / total,
            "scope": "update phase (runner.train) of one iteration; phases in config.phases_ms",
-           "top5": [{"kernel": r[0], "launches": r[1], "share": round(r[2] / total, 4)} for r in rows[:5]]}
-    m = re.match(r"(\w+)\[M(\d+),N(\d+),K(\d+)\]", label)
-    tf_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
-    if m:
-        M, N, K = int(m.group(2)), int(m.group(3)), int(m.group(4))
-        flops = 2.0 * M * N * K
-        ach = flops / (1e-3 * ms / cnt) / 1e12
-        out.update(bound="tensor", achieved=ach, peak=tf_peak, unit="TFLOP/s", frac=ach / tf_peak,
-                   flops_per_launch=flops, peak_source=peaks["_source"] + " (bf16 dense, sustained)",
-                   note="fp32 SIMT FFMA kernel; rated against the tensor-pipe peak the MLP GEMMs are bound by")
-    else:
-        out.update(bound="hbm", achieved=None, peak=peaks.get("hbm_gbs"), unit="GB/s", frac=None,
-                   peak_source=peaks["_source"])
+           "gemm_impl": {0: "fp32 SIMT", 1: "tcgen05 3xTF32", 2: "tcgen05 TF32"}[L.lib.hb_get_gemm_impl()],
+           "peak_source": peaks["_source"],
+           "top5": [{"kernel": r[0], "launches": r[1], "avg_us": round(1e3 * r[2] / r[1], 2), "share": round(r[2] / total, 4)}
+                    for r in rows[:5]]}
+    out.update(_rate(rows[0], peaks))
+    gem = [r for r in rows if GEMM_LABEL.match(r[0])]
+    if gem:
+        g = dict(kernel=gem[0][0], launches=gem[0][1], avg_us=1e3 * gem[0][2] / gem[0][1], share=gem[0][2] / total)
+        g.update(_rate(gem[0], peaks))
+        out["top_gemm"] = g
+        out["gemm_share_of_update_phase"] = sum(r[2] for r in gem) / total
     tr = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     out["traffic"] = None
     if os.path.exists(tr):
@@ -331,6 +370,9 @@ def main():
         na = r2.actor[0].actor.out_dim if r2.actor_buffer[0].available_actions is not None else 0
         h2d = T * N * (A * od * 4 + sd * 4 + 4 + A + A + A * na * 4)  # obs, state, reward, dones, bad flags, avail
         d2h = T * N * A * aw * 4 + (4 * A + 2) * 8
+        if getattr(r2.envs, "h2d_bytes", 0):  # the staged host env counts what it actually copies
+            h2d = r2.envs.h2d_bytes // (k2 + 1)
+            d2h = r2.envs.d2h_bytes // (k2 + 1) + (4 * A + 2) * 8
         line["e2e"] = {"value": T * n_global * k2 / (ms2 / 1e3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / k2,
                        "what": "runner.run_iteration with the env on the host: pinned H2D of obs/state/reward/done/avail and "

@@ -89,8 +89,10 @@ class VCritic:
         s = scal.cpu().numpy()
         return s[0] / s[1], self.critic.grad_norm.item()
 
-    def train(self, critic_buffer, value_normalizer=None):
-        """Reference v_critic.py:159-200."""
+    def train(self, critic_buffer, value_normalizer=None, defer=False):
+        """Reference v_critic.py:159-200.  ``defer=True`` enqueues the whole update without a host read and returns
+        a closure producing the train-info (the HA runner runs the critic update on a side stream, overlapped with
+        the sequential actor updates, and reads the scalars after joining the streams)."""
         self._no_rnn()
         d = self.device
         buf = critic_buffer
@@ -117,8 +119,12 @@ class VCritic:
                 gnorm[u] = self.critic.grad_norm[0]
                 u += 1
         dist.all_reduce_sum_(scal)
-        s = scal.cpu().numpy()
-        return dict(value_loss=float((s[:, 0] / s[:, 1]).mean()), critic_grad_norm=float(gnorm.mean().item()))
+
+        def finish():
+            s = scal.cpu().numpy()
+            return dict(value_loss=float((s[:, 0] / s[:, 1]).mean()), critic_grad_norm=float(gnorm.mean().item()))
+
+        return finish if defer else finish()
 
     def prep_training(self):
         pass

@@ -172,17 +172,32 @@ __device__ __forceinline__ void load_feat(const float* __restrict__ f, int h, in
   for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; v[q] = n < h ? f[n] : 0.f; }
 }
 
-// out[j] for j < nout lands in lane j's return value
-template <int HPL>
+// out[j] for j < nout lands in lane j's return value.  The MAXJ dot products are unrolled so that their warp
+// reductions interleave (independent shuffle chains) instead of running back to back.
+template <int HPL, int MAXJ>
 __device__ __forceinline__ float head_linear(const float (&f)[HPL], const float* __restrict__ shw, int h, int nout,
                                              const float* __restrict__ sb, int lane) {
   float mine = 0.f;
-  for (int j = 0; j < nout; ++j) {
-    float p = 0.f;
 #pragma unroll
-    for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h) p = fmaf(f[q], shw[j * h + n], p); }
-    p = warp_sum(p);
-    if (lane == j) mine = p + sb[j];
+  for (int j0 = 0; j0 < 32; j0 += MAXJ) {
+    if (j0 < nout) {
+      float p[MAXJ];
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        p[j] = 0.f;
+        if (j0 + j < nout) {
+#pragma unroll
+          for (int q = 0; q < HPL; ++q) { int n = lane + 32 * q; if (n < h) p[j] = fmaf(f[q], shw[(j0 + j) * h + n], p[j]); }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) if (j0 + j < nout) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
+      }
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) if (lane == j0 + j && j0 + j < nout) mine = p[j] + sb[j0 + j];
+    }
   }
   return mine;
 }
@@ -290,26 +305,48 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
       for (int q = 0; q < HPL; ++q) gacc[j][q] = 0.f;
   }
   const float inv_norm = MODE == MODE_GRAD ? (float)(1.0 / a.norm3[2]) : 0.f;
-  for (int64_t r = w0; r < a.rows; r += nw) {
-    const int64_t src = a.index ? (int64_t)a.index[r] : r;
-    float f[HPL];
-    load_feat<HPL>(a.feat + r * h, h, lane, f);
-    const bool valid = lane < na;
-    bool masked = false;
-    if (valid && a.avail != nullptr) masked = a.avail[src * na + lane] == 0.f;
-    // issue every load of this row up front (one memory round trip per row instead of one per use)
-    float zr[HPL], ln_mu = 0.f, ln_rs = 0.f, sc_act = 0.f, sc_w = 1.f, sc_fac = 1.f, sc_adv = 0.f, sc_old = 0.f;
+  // Software pipeline: the loads of row r + nw (and the gather index of row r + 2 nw) are in flight while row r is
+  // computed, so a warp pays the two dependent memory round trips (index -> row scalars) once, not once per row.
+  struct RowIn { float f[HPL], zr[HPL]; float mu, rs, act, w, fac, adv, old, av, ref; };
+  auto fetch = [&](int64_t r, int64_t src, RowIn& d) {
+    load_feat<HPL>(a.feat + r * h, h, lane, d.f);
+    d.av = 1.f;
+    if (lane < na && a.avail != nullptr) d.av = a.avail[src * na + lane];
 #pragma unroll
-    for (int q = 0; q < HPL; ++q) zr[q] = 0.f;
+    for (int q = 0; q < HPL; ++q) d.zr[q] = 0.f;
+    d.mu = d.rs = d.act = d.adv = d.old = d.ref = 0.f;
+    d.w = d.fac = 1.f;
     if constexpr (MODE == MODE_GRAD) {
-      if (a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, zr); ln_mu = a.ln_stats[r * 2]; ln_rs = a.ln_stats[r * 2 + 1]; }
-      sc_act = a.actions[src];
-      sc_w = a.use_active ? a.active[src] : 1.f;
-      sc_fac = a.factor ? a.factor[src] : 1.f;
-      sc_adv = a.adv[src];
-      sc_old = a.old_logp[src];
+      if (a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, d.zr); d.mu = a.ln_stats[r * 2]; d.rs = a.ln_stats[r * 2 + 1]; }
+      d.act = a.actions[src];
+      if (a.use_active) d.w = a.active[src];
+      if (a.factor) d.fac = a.factor[src];
+      d.adv = a.adv[src];
+      d.old = a.old_logp[src];
     }
-    float logit = head_linear<HPL>(f, shw, h, na, sb, lane);
+    if constexpr (MODE == MODE_EVAL) {
+      d.act = a.actions[src];
+      if (a.factor_inout) { d.ref = a.logp_ref[src]; d.fac = a.factor_inout[src]; }
+    }
+  };
+  RowIn cur, nxt;
+  int64_t src_cur = 0, src_nxt = 0;
+  if (w0 < a.rows) { src_cur = a.index ? (int64_t)a.index[w0] : w0; fetch(w0, src_cur, cur); }
+  if (w0 + nw < a.rows) src_nxt = a.index ? (int64_t)a.index[w0 + nw] : w0 + nw;
+  for (int64_t r = w0; r < a.rows; r += nw) {
+    const int64_t src = src_cur;
+    int64_t src_nn = 0;
+    if (r + 2 * nw < a.rows) src_nn = a.index ? (int64_t)a.index[r + 2 * nw] : r + 2 * nw;
+    if (r + nw < a.rows) fetch(r + nw, src_nxt, nxt);
+    float f[HPL], zr[HPL];
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) { f[q] = cur.f[q]; zr[q] = cur.zr[q]; }
+    const float ln_mu = cur.mu, ln_rs = cur.rs, sc_act = cur.act, sc_w = cur.w, sc_fac = cur.fac, sc_adv = cur.adv, sc_old = cur.old;
+    const float sc_ref = cur.ref;
+    const bool valid = lane < na;
+    const bool masked = valid && cur.av == 0.f;
+    (void)zr; (void)ln_mu; (void)ln_rs; (void)sc_w; (void)sc_adv; (void)sc_old; (void)sc_ref; (void)src;
+    float logit = head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(f, shw, h, na, sb, lane);
     if (masked) logit = -1e10f;
     const float mx = warp_max(valid ? logit : -INFINITY);
     const float ex = valid ? expf(logit - mx) : 0.f;
@@ -340,11 +377,11 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
       float lpa = __shfl_sync(0xffffffffu, lp, act);
       if (lane == 0) { a.actions_out[r] = (float)act; a.logp_out[r] = lpa; }
     } else if constexpr (MODE == MODE_EVAL) {
-      const int act = (int)a.actions[src];
+      const int act = (int)sc_act;
       const float lpa = __shfl_sync(0xffffffffu, lp, act);
       if (lane == 0) {
         if (a.logp_out) a.logp_out[r] = lpa;
-        if (a.factor_inout) a.factor_inout[src] = a.factor_inout[src] * expf(lpa - a.logp_ref[src]);
+        if (a.factor_inout) a.factor_inout[src] = sc_fac * expf(lpa - sc_ref);
       }
     } else {
     // ---- MODE_GRAD: happo.py:66-91
@@ -380,6 +417,7 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
     if (a.ln_z != nullptr)
       ln_act_bwd_row<HPL>(df, zr, ln_mu, ln_rs, a.ln_w, h, a.ln_act, lane, a.dfeat + r * h, lcg, lcb);
     }
+    cur = nxt; src_cur = src_nxt; src_nxt = src_nn;
   }
   if constexpr (MODE == MODE_GRAD) {
 #pragma unroll
@@ -435,17 +473,41 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
       for (int q = 0; q < HPL; ++q) gacc[j][q] = 0.f;
   }
   const float inv_norm = MODE == MODE_GRAD ? (float)(1.0 / a.norm3[2]) : 0.f;
-  for (int64_t r = w0; r < a.rows; r += nw) {
-    const int64_t src = a.index ? (int64_t)a.index[r] : r;
-    float f[HPL];
-    load_feat<HPL>(a.feat + r * h, h, lane, f);
-    float zr[HPL], ln_mu = 0.f, ln_rs = 0.f;
+  // software pipeline as in discrete_head_kernel
+  struct RowIn { float f[HPL], zr[HPL]; float mu, rs, act, old, w, fac, adv, ref; };
+  auto fetch = [&](int64_t r, int64_t src, RowIn& d) {
+    load_feat<HPL>(a.feat + r * h, h, lane, d.f);
 #pragma unroll
-    for (int q = 0; q < HPL; ++q) zr[q] = 0.f;
-    if constexpr (MODE == MODE_GRAD) {
-      if (a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, zr); ln_mu = a.ln_stats[r * 2]; ln_rs = a.ln_stats[r * 2 + 1]; }
+    for (int q = 0; q < HPL; ++q) d.zr[q] = 0.f;
+    d.mu = d.rs = d.act = d.old = d.adv = d.ref = 0.f;
+    d.w = d.fac = 1.f;
+    if constexpr (MODE != MODE_ACT) { if (valid) d.act = a.actions[src * ad + lane]; }
+    if constexpr (MODE == MODE_EVAL) {
+      if (a.factor_inout) { if (valid) d.ref = a.logp_ref[src * ad + lane]; d.fac = a.factor_inout[src]; }
     }
-    const float mean = head_linear<HPL>(f, shw, h, ad, sb, lane);
+    if constexpr (MODE == MODE_GRAD) {
+      if (a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, d.zr); d.mu = a.ln_stats[r * 2]; d.rs = a.ln_stats[r * 2 + 1]; }
+      if (valid) d.old = a.old_logp[src * ad + lane];
+      if (a.use_active) d.w = a.active[src];
+      if (a.factor) d.fac = a.factor[src];
+      d.adv = a.adv[src];
+    }
+  };
+  RowIn cur, nxt;
+  int64_t src_cur = 0, src_nxt = 0;
+  if (w0 < a.rows) { src_cur = a.index ? (int64_t)a.index[w0] : w0; fetch(w0, src_cur, cur); }
+  if (w0 + nw < a.rows) src_nxt = a.index ? (int64_t)a.index[w0 + nw] : w0 + nw;
+  for (int64_t r = w0; r < a.rows; r += nw) {
+    const int64_t src = src_cur;
+    int64_t src_nn = 0;
+    if (r + 2 * nw < a.rows) src_nn = a.index ? (int64_t)a.index[r + 2 * nw] : r + 2 * nw;
+    if (r + nw < a.rows) fetch(r + nw, src_nxt, nxt);
+    float f[HPL], zr[HPL];
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) { f[q] = cur.f[q]; zr[q] = cur.zr[q]; }
+    const float ln_mu = cur.mu, ln_rs = cur.rs;
+    (void)zr; (void)ln_mu; (void)ln_rs; (void)src;
+    const float mean = head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(f, shw, h, ad, sb, lane);
     if constexpr (MODE == MODE_ACT) {
       float act = mean;
       if (!a.deterministic) {
@@ -461,14 +523,14 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
         a.logp_out[r * ad + lane] = -(dlt * dlt) / (2.f * std * std) - log_std_v - 0.5f * HB_LOG_2PI_F;
       }
     } else {
-    const float act = valid ? a.actions[src * ad + lane] : 0.f;
+    const float act = cur.act;
     const float dlt = act - mean;
     const float var = std * std;
     const float lp = -(dlt * dlt) / (2.f * var) - log_std_v - 0.5f * HB_LOG_2PI_F;
     if constexpr (MODE == MODE_EVAL) {
       if (valid && a.logp_out) a.logp_out[r * ad + lane] = lp;
       if (a.factor_inout) {
-        float e = valid ? expf(lp - a.logp_ref[src * ad + lane]) : (a.agg_prod ? 1.f : 0.f);
+        float e = valid ? expf(lp - cur.ref) : (a.agg_prod ? 1.f : 0.f);
         float agg;
         if (a.agg_prod) {
           agg = e;
@@ -477,11 +539,11 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
         } else {
           agg = warp_sum(e) / (float)ad;
         }
-        if (lane == 0) a.factor_inout[src] = a.factor_inout[src] * agg;
+        if (lane == 0) a.factor_inout[src] = cur.fac * agg;
       }
     } else {
     // ---- MODE_GRAD
-    const float e = valid ? expf(lp - a.old_logp[src * ad + lane]) : (a.agg_prod ? 1.f : 0.f);
+    const float e = valid ? expf(lp - cur.old) : (a.agg_prod ? 1.f : 0.f);
     float ratio;
     if (a.agg_prod) {
       ratio = e;
@@ -490,9 +552,7 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
     } else {
       ratio = warp_sum(e) / (float)ad;
     }
-    const float w = a.use_active ? a.active[src] : 1.f;
-    const float fac = a.factor ? a.factor[src] : 1.f;
-    const float adv = a.adv[src];
+    const float w = cur.w, fac = cur.fac, adv = cur.adv;
     float m;
     const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
     const float c_r = -fac * w * inv_norm * dm;   // d obj / d ratio
@@ -524,6 +584,7 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
       ln_act_bwd_row<HPL>(df, zr, ln_mu, ln_rs, a.ln_w, h, a.ln_act, lane, a.dfeat + r * h, lcg, lcb);
     }
     }
+    cur = nxt; src_cur = src_nxt; src_nxt = src_nn;
   }
   if constexpr (MODE == MODE_GRAD) {
 #pragma unroll
@@ -625,21 +686,37 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
   if (GRAD) { for (int i = threadIdx.x; i < 512; i += ROW_THREADS) s_ln[i] = 0.f; }
   double s_loss = 0.0, s_rows = 0.0;
   const int64_t w0 = (int64_t)blockIdx.x * ROW_WARPS + warp, nw = (int64_t)gridDim.x * ROW_WARPS;
-  for (int64_t r = w0; r < a.rows; r += nw) {
-    float f[HPL];
-    load_feat<HPL>(a.feat + r * h, h, lane, f);
-    float zr[HPL], ln_mu = 0.f, ln_rs = 0.f;
+  // software pipeline as in the policy heads: row r + nw's loads fly while row r is computed
+  struct RowIn { float f[HPL], zr[HPL]; float mu, rs, vp, ret; };
+  auto fetch = [&](int64_t r, int64_t src, RowIn& d) {
+    load_feat<HPL>(a.feat + r * h, h, lane, d.f);
 #pragma unroll
-    for (int q = 0; q < HPL; ++q) zr[q] = 0.f;
-    if (GRAD && a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, zr); ln_mu = a.ln_stats[r * 2]; ln_rs = a.ln_stats[r * 2 + 1]; }
+    for (int q = 0; q < HPL; ++q) d.zr[q] = 0.f;
+    d.mu = d.rs = d.vp = d.ret = 0.f;
+    if (GRAD) {
+      if (a.ln_z != nullptr) { load_feat<HPL>(a.ln_z + r * h, h, lane, d.zr); d.mu = a.ln_stats[r * 2]; d.rs = a.ln_stats[r * 2 + 1]; }
+      d.vp = a.value_preds[src];
+      d.ret = a.returns[src];
+    }
+  };
+  RowIn cur, nxt;
+  int64_t src_cur = 0, src_nxt = 0;
+  if (w0 < a.rows) { src_cur = (GRAD && a.index) ? (int64_t)a.index[w0] : w0; fetch(w0, src_cur, cur); }
+  if (w0 + nw < a.rows) src_nxt = (GRAD && a.index) ? (int64_t)a.index[w0 + nw] : w0 + nw;
+  for (int64_t r = w0; r < a.rows; r += nw) {
+    int64_t src_nn = 0;
+    if (r + 2 * nw < a.rows) src_nn = (GRAD && a.index) ? (int64_t)a.index[r + 2 * nw] : r + 2 * nw;
+    if (r + nw < a.rows) fetch(r + nw, src_nxt, nxt);
+    float f[HPL], zr[HPL];
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) { f[q] = cur.f[q]; zr[q] = cur.zr[q]; }
+    const float ln_mu = cur.mu, ln_rs = cur.rs, vp = cur.vp;
+    float ret = cur.ret;
     float p = 0.f;
 #pragma unroll
     for (int q = 0; q < HPL; ++q) p = fmaf(f[q], wv[q], p);
     const float v = warp_sum(p) + bias;
-    if (!GRAD) { if (lane == 0) a.values_out[r] = v; continue; }
-    const int64_t src = a.index ? (int64_t)a.index[r] : r;
-    const float vp = a.value_preds[src];
-    float ret = a.returns[src];
+    if (!GRAD) { if (lane == 0) a.values_out[r] = v; cur = nxt; src_cur = src_nxt; src_nxt = src_nn; continue; }
     if (a.vn_state != nullptr) ret = (ret - vmean) / vstd;
     const float dv = v - vp;
     const float dc = fminf(fmaxf(dv, -a.clip), a.clip);
@@ -666,6 +743,7 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
     }
     if (a.ln_z != nullptr)
       ln_act_bwd_row<HPL>(df, zr, ln_mu, ln_rs, a.ln_w, h, a.ln_act, lane, a.dfeat + r * h, lcg, lcb);
+    cur = nxt; src_cur = src_nxt; src_nxt = src_nn;
   }
   if (GRAD) {
 #pragma unroll

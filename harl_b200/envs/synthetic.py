@@ -87,12 +87,12 @@ class SyntheticBatchedEnv:
         self._avail = None
         if self.discrete:
             if self.avail_prob >= 1.0:
-                self._avail = torch.ones(1, N, A, ad, device=self.device)
+                self._avail = pin(torch.ones(1, N, A, ad)).to(self.device)
             else:
                 av = (torch.rand(K, N, A, ad, generator=g) < self.avail_prob).float()
                 av[..., 0] = 0.0  # SMAC rule: no-op unavailable while alive, "stop" always available
                 av[..., 1] = 1.0
-                self._avail = av.to(self.device)
+                self._avail = pin(av).to(self.device)
         self._t = 0
         self._ep_step = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._dead = torch.zeros(N, A, dtype=torch.bool, device=self.device)
@@ -102,6 +102,15 @@ class SyntheticBatchedEnv:
         self._false = torch.zeros(N, A, dtype=torch.bool, device=self.device)
         self.last_bad_transition = self._false
         self.steps_served = 0
+        # host mode + step_into: outputs are staged in pinned host memory and copied H2D asynchronously
+        self.host_staged = self.host and torch.cuda.is_available()
+        self.h2d_bytes = self.d2h_bytes = 0
+        self._act_host = None
+        if self.host_staged:
+            self._dones_h = torch.zeros(N, A, dtype=torch.uint8).pin_memory()
+            self._bad_h = torch.zeros(N, A, dtype=torch.uint8).pin_memory()
+            self._rew_na_h = torch.zeros(N, A).pin_memory()
+            self._avail_h = torch.zeros(N, A, ad).pin_memory() if self.discrete else None
 
     def _views(self, k):
         obs = self._obs[k].permute(1, 0, 2)  # [N, A, od] view; obs[:, a] contiguous
@@ -167,6 +176,8 @@ class SyntheticBatchedEnv:
 
         ``dst``: obs (list per agent, [N, od]), share_obs, rewards (critic slot), avail (list or None entries),
         actions (list per agent -- ignored by the synthetic dynamics), dones / bad ([N, A] uint8)."""
+        if self.host:
+            return self._step_into_from_host(dst)
         self._t += 1
         self.steps_served += 1
         k = self._t % self.pool
@@ -207,6 +218,66 @@ class SyntheticBatchedEnv:
                 for a in range(A):
                     dst["avail"][a].copy_(av[:, a])
             self.last_bad_transition = dst["bad"].bool()
+
+    def _step_into_from_host(self, dst):
+        """``step_into`` for the host-resident env: the actions come D2H (the simulator consumes them before it
+        steps), every output goes H2D from pinned memory straight into the buffer slots.  One stream
+        synchronisation per step -- the true data dependency of a CPU simulator."""
+        A = self.n_agents
+        if self._act_host is None:
+            self._act_host = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in dst["actions"]]
+        for a in range(A):
+            self._act_host[a].copy_(dst["actions"][a], non_blocking=True)
+            self.d2h_bytes += self._act_host[a].numel() * 4
+        torch.cuda.current_stream().synchronize()  # also: last step's H2D copies have drained the staging buffers
+        self.last_actions = self._act_host
+        self._t += 1
+        self.steps_served += 1
+        k = self._t % self.pool
+
+        def h2d(dst_t, src):
+            dst_t.copy_(src, non_blocking=True)
+            self.h2d_bytes += dst_t.numel() * dst_t.element_size()
+
+        for a in range(A):
+            h2d(dst["obs"][a], self._obs[k, a])
+        h2d(dst["share_obs"], self._state[k])
+        rew = self._rew[k, :, 0]
+        if self.state_type == "EP":
+            h2d(dst["rewards"], rew)
+        else:
+            self._rew_na_h.copy_(rew.expand(-1, A))
+            h2d(dst["rewards"], self._rew_na_h.unsqueeze(-1))
+        if dst.get("rewards_na") is not None:
+            self._rew_na_h.copy_(rew.expand(-1, A))
+            h2d(dst["rewards_na"], self._rew_na_h)
+        if self._simple:
+            self._ep_step_host += 1
+            done = self._ep_step_host >= self.episode_limit
+            if done:
+                self._ep_step_host = 0
+            self._dones_h.fill_(1 if done else 0)
+            self._bad_h.fill_(1 if done else 0)
+            av = self._avail_view(k)
+        else:
+            r = self._rand[k]
+            self._ep_step += 1
+            trunc = self._ep_step >= self.episode_limit
+            self._dead |= r[:, :A] < self.death_prob
+            env_done = trunc | self._dead.all(1) | (r[:, A] < self.terminate_prob)
+            dones = self._dead | env_done[:, None]
+            self._dones_h.copy_(dones)
+            self._bad_h.copy_((trunc & env_done)[:, None].expand(-1, A))
+            self._ep_step = torch.where(env_done, torch.zeros_like(self._ep_step), self._ep_step)
+            self._dead = self._dead & ~env_done[:, None]
+            av = self._avail_view(k, dones & ~env_done[:, None])
+            self.last_bad_transition = self._bad_h.bool()
+        h2d(dst["dones"], self._dones_h)
+        h2d(dst["bad"], self._bad_h)
+        if av is not None:
+            self._avail_h.copy_(av)
+            for a in range(A):
+                h2d(dst["avail"][a], self._avail_h[:, a])
 
     def seed(self, seed):
         pass

@@ -18,8 +18,8 @@ _WORKSPACES = {}
 
 
 def workspace(device, nbytes):
-    """One grow-only scratch tensor per device, shared by every net (calls are stream-ordered)."""
-    key = str(device)
+    """One grow-only scratch tensor per (device, stream), shared by every net (calls are stream-ordered)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)

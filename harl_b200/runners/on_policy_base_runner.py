@@ -171,11 +171,13 @@ class OnPolicyBaseRunner:
 
     # ------------------------------------------------------------------ zero-copy rollout (device-resident envs)
     def _fast_rollout_ready(self):
-        """The lean rollout loop applies when the env lives on the training device and can write its outputs
-        straight into the buffer slots (``step_into``); otherwise the generic collect/step/insert loop runs."""
+        """The lean rollout loop applies when the env can write its outputs straight into the buffer slots
+        (``step_into``: a device-resident env, or a host env staging through pinned memory); otherwise the generic
+        collect/step/insert loop runs."""
         if getattr(self, "_fast", None) is None:
             ok = (self.device.type == "cuda" and hasattr(self.envs, "step_into")
-                  and getattr(self.envs, "device", None) == self.device and not self.actor_buffer[0].recurrent
+                  and (getattr(self.envs, "device", None) == self.device or getattr(self.envs, "host_staged", False))
+                  and not self.actor_buffer[0].recurrent
                   and not self.critic_buffer.recurrent and not getattr(self, "disable_fast_rollout", False))
             self._fast = self._build_fast_path() if ok else False
         return bool(self._fast)

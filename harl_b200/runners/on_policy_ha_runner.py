@@ -38,6 +38,16 @@ class OnPolicyHARunner(OnPolicyBaseRunner):
         self.last_agent_order = agent_order
         infos = []
         agg_prod = self.action_aggregation == "prod"
+        # The critic update (reference :128) shares no state with the actor updates: enqueue it first on a side
+        # stream so that its (latency-bound, under-filling) kernels overlap the sequential actor updates.
+        critic_pending = None
+        if getattr(self, "overlap_critic_update", True):
+            side = getattr(self, "_side_stream", None)
+            if side is None:
+                side = self._side_stream = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                critic_pending = self.critic.train(cb, self.value_normalizer, defer=True)
         for agent_id in agent_order:
             buf, actor = self.actor_buffer[agent_id], self.actor[agent_id]
             buf.update_factor(factor)
@@ -49,7 +59,11 @@ class OnPolicyHARunner(OnPolicyBaseRunner):
             adv_a = advantages if self.state_type == "EP" else advantages[:, :, agent_id].contiguous()
             infos.append(actor.train(buf, adv_a, self.state_type))               # :86-93
             actor.actor.evaluate(sweep, logp_ref=old_logp, factor_inout=factor.reshape(rows), agg_prod=agg_prod)  # :96-124
-        critic_info = self.critic.train(cb, self.value_normalizer)               # :128
+        if critic_pending is not None:
+            torch.cuda.current_stream(dev).wait_stream(self._side_stream)
+            critic_info = critic_pending()
+        else:
+            critic_info = self.critic.train(cb, self.value_normalizer)           # :128
         # per-agent infos are reported in agent-id order
         ordered = [None] * self.num_agents
         for pos, agent_id in enumerate(agent_order):

@@ -197,3 +197,44 @@ def test_zero_copy_rollout_equals_generic_rollout(action_type, state_type, simpl
     np.testing.assert_allclose(fs, gs, rtol=1e-5)
     for r in runners:
         r.close()
+
+
+@pytest.mark.parametrize("action_type,state_type,simple", [("Discrete", "EP", True), ("Box", "FP", False), ("Discrete", "EP", False)])
+def test_host_staged_rollout_equals_device_rollout(action_type, state_type, simple):
+    """A host-resident env (pinned staging, H2D of every output, D2H of the actions) must fill the buffers
+    bit-identically to the device-resident env, and the env must have seen the sampled actions on the host."""
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    snaps, runners = [], []
+    for host in (True, False):
+        args, algo_args, env_args = small_config(action_type=action_type, state_type=state_type)
+        env_args["host"] = host
+        if simple:
+            env_args.update(death_prob=0.0, terminate_prob=0.0, avail_prob=1.0)
+        algo_args["algo"]["fixed_order"] = True
+        r = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+        r.warmup()
+        r.logger.init(2)
+        r.run_iteration(1, 2)
+        torch.cuda.synchronize()
+        assert r._fast, "the staged host env must take the lean rollout loop"
+        snap = {}
+        for a in range(r.num_agents):
+            b = r.actor_buffer[a]
+            for k in ("obs", "actions", "action_log_probs", "masks", "active_masks", "available_actions"):
+                if getattr(b, k) is not None:
+                    snap[f"a{a}.{k}"] = getattr(b, k).clone()
+        for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks"):
+            snap["c." + k] = getattr(r.critic_buffer, k).clone()
+        snaps.append(snap)
+        runners.append(r)
+    h, d = snaps
+    for k in h:
+        assert torch.equal(h[k], d[k]), k
+    env = runners[0].envs
+    T = runners[0].algo_args["train"]["episode_length"]
+    assert env.h2d_bytes > 0 and env.d2h_bytes == T * sum(x.numel() * 4 for x in env.last_actions)
+    last = runners[0].actor_buffer[0].actions[T - 1].cpu()
+    assert torch.equal(env.last_actions[0], last)
+    for r in runners:
+        r.close()
