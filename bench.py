@@ -295,6 +295,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default="", help="write the per-kernel event profile of one iteration here")
     a = ap.parse_args()
+    # the contract is ONE JSON line on stdout: everything the runner / env print (the reference prints its spaces
+    # and progress lines) goes to stderr
+    real_stdout, sys.stdout = sys.stdout, sys.stderr
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     wl = WORKLOADS[a.workload]
@@ -315,7 +318,7 @@ def main():
                     e2e={"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         line["config"]["reference_note"] = ("PKU-MARL/HARL is pure Python and /root/reference is not on the GPU box; this arm "
                                             "times the oracle CPU port of the same path (kind=port)")
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
         return
 
     import torch
@@ -382,7 +385,7 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_run(a.workload, 1, 1, min(a.cpu_sample, wl["n"]))
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if dist_on:
         torch.distributed.destroy_process_group()
 

@@ -88,6 +88,9 @@ int launch_dw_reduce(float* grad, const float* part, int total, cudaStream_t st)
 
 int launch_policy_head(int head, int mode, const HeadArgs& a, cudaStream_t st);
 int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st);
+// row-group variants for the common widths (heads_fast.cu); *handled = false -> fall back to the generic kernels
+int launch_policy_head_rows(int head, int mode, const HeadArgs& a, cudaStream_t st, bool* handled);
+int launch_value_head_rows(int grad, const ValueArgs& a, cudaStream_t st, bool* handled);
 
 
 }  // namespace hb

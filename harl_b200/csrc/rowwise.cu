@@ -645,6 +645,9 @@ static int launch_head_mode(int head, const HeadArgs& a, cudaStream_t st) {
 }
 
 int launch_policy_head(int head, int mode, const HeadArgs& a, cudaStream_t st) {
+  bool handled = false;
+  const int rc = launch_policy_head_rows(head, mode, a, st, &handled);
+  if (handled || rc != HB_OK) return rc;
   if (mode == MODE_ACT) return launch_head_mode<MODE_ACT>(head, a, st);
   if (mode == MODE_EVAL) return launch_head_mode<MODE_EVAL>(head, a, st);
   return launch_head_mode<MODE_GRAD>(head, a, st);
@@ -760,6 +763,9 @@ __global__ void __launch_bounds__(ROW_THREADS) value_head_kernel(ValueArgs a) {
 
 int launch_value_head(int grad, const ValueArgs& a, cudaStream_t st) {
   if (a.rows <= 0) return HB_OK;
+  bool handled = false;
+  const int rc = launch_value_head_rows(grad, a, st, &handled);
+  if (handled || rc != HB_OK) return rc;
   const int hpl = a.h <= 32 ? 1 : a.h <= 64 ? 2 : a.h <= 128 ? 4 : 8;
   const int g = (grad && a.part_stride) ? slot_grid(a.rows) : row_grid(a.rows);
 #define HB_V(H)                                                                 \

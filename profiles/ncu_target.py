@@ -34,3 +34,13 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     net.adam_step(5e-4, 1e-5, 0.0, 10.0, True)
 torch.cuda.synchronize()
 print("done", scal.cpu().numpy())
+# forward-only sweep (policy_head_eval) and one critic gradient pass (value_head_grad)
+lp = torch.empty(R, 1, device=dev)
+net.evaluate(DeviceNet.actor_batch(obs, acts, avail=avail), logp_out=lp)
+cnet = DeviceNet(cfg, 54, L.HEAD_VALUE, 1, dev)
+sobs = torch.randn(R, 54, generator=g).to(dev)
+vp, rt = torch.randn(R, generator=g).to(dev), torch.randn(R, generator=g).to(dev)
+cscal = torch.zeros(4, dtype=torch.float64, device=dev)
+cnet.value_grad(DeviceNet.critic_batch(sobs, vp, rt, None, R), L.ValueHyper(0.2, 10.0, 1.0, 1, 1), None, 1.0 / R, cscal)
+torch.cuda.synchronize()
+print("done2", lp.mean().item(), cscal.cpu().numpy())
