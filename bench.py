@@ -152,8 +152,10 @@ def kernel_profile(runner, torch):
         runner.insert((obs, share_obs, rewards, dones, infos, avail, values, actions, logp, rnn, rnn_c))
     runner.compute()
     torch.cuda.synchronize()
-    L.call("hb_profile_begin", L.stream_ptr())
     overlap, runner.overlap_critic_update = getattr(runner, "overlap_critic_update", True), False  # one stream: clean gaps
+    runner.train()  # unprofiled pass: the critic's workspace on this stream is allocated here, not inside a gap
+    torch.cuda.synchronize()
+    L.call("hb_profile_begin", L.stream_ptr())
     runner.train()
     runner.overlap_critic_update = overlap
     buf = C.create_string_buffer(1 << 16)

@@ -1,14 +1,24 @@
 // C-ABI entry points that sequence the kernels for one network over row chunks.
 //
-// Chunking is the B200-specific part of the host logic: activations of a chunk
-// (<= 32768 rows x <= 256 floats x a handful of tensors) stay resident in the 126 MB L2
-// between the layer kernels, so only the rollout-buffer rows themselves stream from HBM.
+// Rows are processed in chunks of up to 2^20 (the workspace is sized for one chunk: ~3 KB per row at hidden 128,
+// i.e. ~3 GB -- nothing against 180 GB of HBM3e).  Measured on B200 (profiles/chunk_sweep_r01.txt): L2-sized
+// chunks of 32768 rows leave the GPU with 256 CTAs per launch -- 1.7 per SM, latency-bound at every kernel --
+// and cost 94 ms per C2 update phase; whole-batch launches (819200 rows, 6400 CTAs) take 55 ms although the
+// activations then stream through HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace hb {
 
-constexpr int64_t CHUNK_ROWS = 32768;
+// Rows per kernel launch.  HB_CHUNK_ROWS overrides it for tuning runs (read once).
+static int64_t chunk_rows_init() {
+  const char* e = getenv("HB_CHUNK_ROWS");
+  long long v = e ? atoll(e) : 0;
+  return v >= 1024 ? (int64_t)v : (int64_t)1 << 20;
+}
+static const int64_t CHUNK_ROWS = chunk_rows_init();
 
 struct Work {
   float* x0;

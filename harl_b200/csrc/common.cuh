@@ -139,11 +139,9 @@ __device__ __forceinline__ float act_bwd_rt(int act, float z) {
   }
 }
 
-// gradient-sum output: plain RMW into this CTA's split-buffer slot (slot != 0) or a global atomic
-__device__ __forceinline__ void acc_out(float* p, float v, int64_t slot) {
-  if (slot != 0) p[slot] += v;
-  else atomicAdd(p, v);
-}
+// gradient-sum output: a fire-and-forget reduction into this CTA's split-buffer slot (slot != 0: a handful of CTAs
+// share a slot at most, so no same-address serialisation) or into the gradient itself (slot == 0)
+__device__ __forceinline__ void acc_out(float* p, float v, int64_t slot) { atomicAdd(p + slot, v); }
 
 // Philox4x32-10 (Salmon et al. 2011), counter-based: one call -> 4 x 32 random bits.
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {

@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
   }
   __syncthreads();
   {
-    const int64_t slot = (part_stride && blockIdx.x < (unsigned)tc_dw_splits_c()) ? part_delta + (int64_t)blockIdx.x * part_stride : 0;
+    const int64_t slot = part_stride ? part_delta + (int64_t)(blockIdx.x % (unsigned)tc_dw_splits_c()) * part_stride : 0;
     for (int n = tid; n < Np; n += 128) { acc_out(g_lnw_p + n, colsum[n], slot); acc_out(g_lnb_p + n, colsum[NT + n], slot); }
   }
   tc_fence_before();

@@ -182,13 +182,18 @@ class SyntheticBatchedEnv:
         self.steps_served += 1
         k = self._t % self.pool
         A = self.n_agents
-        for a in range(A):
-            dst["obs"][a].copy_(self._obs[k, a])
-        dst["share_obs"].copy_(self._state[k])
+        # one multi-tensor copy (a single launch) instead of A + 2 separate copy kernels
+        dsts = list(dst["obs"]) + [dst["share_obs"]]
+        srcs = [self._obs[k, a] for a in range(A)] + [self._state[k]]
         rew = self._rew[k, :, 0]
-        dst["rewards"].copy_(rew if self.state_type == "EP" else rew.unsqueeze(1).expand(-1, A, -1))
+        if self.state_type == "EP":
+            dsts.append(dst["rewards"])
+            srcs.append(rew)
+        else:
+            dst["rewards"].copy_(rew.unsqueeze(1).expand(-1, A, -1))
         if dst.get("rewards_na") is not None:
             dst["rewards_na"].copy_(rew.expand(-1, A))
+        torch._foreach_copy_(dsts, srcs)
         if self._simple:
             self._ep_step_host += 1
             done = self._ep_step_host >= self.episode_limit

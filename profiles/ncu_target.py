@@ -16,7 +16,7 @@ cfg = {**algo_args["model"], **algo_args["algo"]}
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = DeviceNet(cfg, 18, L.HEAD_DISCRETE, 5, dev)
-R = 65536
+R = int(os.environ.get("NCU_ROWS", "65536"))
 g = torch.Generator().manual_seed(1)
 obs = torch.randn(R, 18, generator=g).to(dev)
 acts = torch.randint(0, 5, (R, 1), generator=g).float().to(dev)
