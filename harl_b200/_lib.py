@@ -56,7 +56,7 @@ class CollectArgs(C.Structure):
         ("actions", C.c_void_p * HB_MAX_AGENTS), ("logp", C.c_void_p * HB_MAX_AGENTS),
         ("seed", C.c_uint64 * HB_MAX_AGENTS),
         ("critic_desc", C.POINTER(NetDesc)), ("critic_prepared", C.c_void_p), ("share_obs", C.c_void_p),
-        ("critic_rows", C.c_int64), ("values", C.c_void_p),
+        ("critic_rows", C.c_int64), ("values", C.c_void_p), ("offset_base", C.c_void_p),
     ]
 
 
@@ -103,6 +103,7 @@ SIGNATURES = {
     "hb_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64, C.c_int]),
     "hb_rollout_insert_masks": (C.c_int, [C.POINTER(InsertArgs), P]),
     "hb_rollout_collect": (C.c_int, [C.POINTER(CollectArgs), P, C.c_size_t, P]),
+    "hb_counter_add": (C.c_int, [P, C.c_uint64, P]),
     "hb_policy_act": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, C.c_int, C.c_uint64, C.c_uint64, P, P, P,
                                 C.c_size_t, P]),
     "hb_value_forward": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, C.c_size_t, P]),

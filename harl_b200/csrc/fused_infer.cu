@@ -32,6 +32,7 @@ struct InferArgs {
   int n_nets, n_layers, act, feature_norm, deterministic;
   int hidden[HB_MAX_LAYERS];
   unsigned long long offset;
+  const unsigned long long* offset_base;   // device counter added to offset (nullable)
   InferNet net[HB_MAX_AGENTS + 1];
 };
 
@@ -239,8 +240,9 @@ __global__ void __launch_bounds__(256) fused_infer_kernel(const __grid_constant_
         const float pm = warp_max(p);
         act = __ffs(__ballot_sync(0xffffffffu, valid && p == pm)) - 1;
       } else {
-        const uint4 rnd = philox4x32(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32), 0u, (uint32_t)A.offset),
-                                     make_uint2((uint32_t)net.seed, (uint32_t)(net.seed >> 32) ^ (uint32_t)(A.offset >> 32)));
+        const unsigned long long off = A.offset + (A.offset_base ? *A.offset_base : 0ull);
+        const uint4 rnd = philox4x32(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32), 0u, (uint32_t)off),
+                                     make_uint2((uint32_t)net.seed, (uint32_t)(net.seed >> 32) ^ (uint32_t)(off >> 32)));
         const float u = u01(rnd.x);
         float c = p;
 #pragma unroll
@@ -260,8 +262,9 @@ __global__ void __launch_bounds__(256) fused_infer_kernel(const __grid_constant_
       const float log_std_v = logf(std);
       float act = mine;
       if (!A.deterministic) {
-        const uint4 rnd = philox4x32(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32), (uint32_t)lane, (uint32_t)A.offset),
-                                     make_uint2((uint32_t)net.seed, (uint32_t)(net.seed >> 32) ^ (uint32_t)(A.offset >> 32)));
+        const unsigned long long off = A.offset + (A.offset_base ? *A.offset_base : 0ull);
+        const uint4 rnd = philox4x32(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32), (uint32_t)lane, (uint32_t)off),
+                                     make_uint2((uint32_t)net.seed, (uint32_t)(net.seed >> 32) ^ (uint32_t)(off >> 32)));
         const float u1 = u01(rnd.x), u2 = u01(rnd.y);
         act = mine + std * (sqrtf(-2.f * logf(u1)) * cospif(2.f * u2));
       }
@@ -280,6 +283,19 @@ static size_t fused_infer_smem(int nt, int kp0_max) {
 
 }  // namespace hb
 
+namespace hb {
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+}  // namespace hb
+
+extern "C" int hb_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(counter != nullptr, "NULL counter");
+  cudaStream_t st = (cudaStream_t)stream;
+  counter_add_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(counter), (unsigned long long)inc);
+  HB_LAUNCH_DONE(st, "hb_counter_add");
+  return HB_OK;
+}
+
 extern "C" int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_bytes, void* stream) {
   using namespace hb;
   (void)ws; (void)ws_bytes;
@@ -294,6 +310,7 @@ extern "C" int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_
   A.feature_norm = d0->feature_norm;
   A.deterministic = a->deterministic;
   A.offset = a->offset;
+  A.offset_base = reinterpret_cast<const unsigned long long*>(a->offset_base);
   int hmax = 0, kp0 = 0;
   long long max_rows = a->rows;
   for (int l = 0; l < d0->n_layers; ++l) { A.hidden[l] = d0->hidden[l]; hmax = d0->hidden[l] > hmax ? d0->hidden[l] : hmax; }

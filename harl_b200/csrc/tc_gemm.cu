@@ -176,19 +176,24 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
       mbar_expect_tx(&s.full_b[st], B_BYTES);
       tma_bulk_g2s(s.b[st], tiles + (int64_t)c * (2 * NT * TC_KC), B_BYTES, &s.full_b[st]);
     }
-    // A: thread t stages row t of the tile (zeros beyond M / Kred), hi and lo images
+    // A: a warp stages 32 rows of the tile, 4 rows x 8 16-byte k-chunks per instruction -- every global request
+    // covers four full 128-byte lines (a thread-per-row walk would touch 32 lines per request and serialise in the
+    // LSU).  Zeros beyond M / Kred; hi and lo images in the canonical layout [(row/8)][kc][row%8][4].
     {
       float* ahi = s.a[st][0];
       float* alo = s.a[st][1];
-      const int base = ((tid >> 3) * 8) * 32 + (tid & 7) * 4;  // floats: [(row/8)][kc][row%8][4]
-      const float* xr = X + row * ldx + c * TC_KC;
+      const int kc = tid & 7, r4 = (tid & 31) >> 3;
+      const bool kin = c * TC_KC + kc * 4 < Kred;
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int i = 0; i < 8; ++i) {
+        const int rl = warp * 32 + i * 4 + r4;
+        const int64_t grow = row0 + rl;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M && c * TC_KC + kc * 4 < Kred) v = *reinterpret_cast<const float4*>(xr + kc * 4);
+        if (kin && grow < M) v = *reinterpret_cast<const float4*>(X + grow * ldx + c * TC_KC + kc * 4);
+        const int base = ((rl >> 3) * 8 + kc) * 32 + (rl & 7) * 4;
         float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        *reinterpret_cast<float4*>(ahi + base + kc * 32) = h;
-        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        *reinterpret_cast<float4*>(ahi + base) = h;
+        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
     }
     fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -387,18 +392,21 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
       mbar_expect_tx(&s.full_b[st], B_BYTES);
       tma_bulk_g2s(s.b[st], tiles + (int64_t)c * (2 * NT * TC_KC), B_BYTES, &s.full_b[st]);
     }
-    {
+    {  // coalesced staging of the dZ rows (4 rows x 8 k-chunks per warp instruction), as in the forward kernel
       float* ahi = s.a[st][0];
       float* alo = s.a[st][1];
-      const int base = ((tid >> 3) * 8) * 32 + (tid & 7) * 4;
-      const float* xr = dZ + row * N + c * TC_KC;
+      const int kc = tid & 7, r4 = (tid & 31) >> 3;
+      const bool kin = c * TC_KC + kc * 4 < N;
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int i = 0; i < 8; ++i) {
+        const int rl = warp * 32 + i * 4 + r4;
+        const int64_t grow = row0 + rl;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M && c * TC_KC + kc * 4 < N) v = *reinterpret_cast<const float4*>(xr + kc * 4);
+        if (kin && grow < M) v = *reinterpret_cast<const float4*>(dZ + grow * N + c * TC_KC + kc * 4);
+        const int base = ((rl >> 3) * 8 + kc) * 32 + (rl & 7) * 4;
         float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        *reinterpret_cast<float4*>(ahi + base + kc * 32) = h;
-        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        *reinterpret_cast<float4*>(ahi + base) = h;
+        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
     }
     fence_async_smem();

@@ -58,7 +58,7 @@ class LazyInfos:
 
 
 class SyntheticBatchedEnv:
-    def __init__(self, env_name, seed, n_threads, env_args, device=None, pool=16):
+    def __init__(self, env_name, seed, n_threads, env_args, device=None, pool=None):
         c = resolve_shapes(env_name, env_args)
         self.cfg = c
         # host=True: behave like a CPU simulator -- outputs live in pinned host memory and the actions
@@ -75,7 +75,7 @@ class SyntheticBatchedEnv:
         self.action_space = [Discrete(ad) if self.discrete else Box(shape=(ad,)) for _ in range(A)]
         self.episode_limit = int(c["episode_limit"])
         self.death_prob, self.terminate_prob, self.avail_prob = (float(c[k]) for k in ("death_prob", "terminate_prob", "avail_prob"))
-        self.pool = K = int(pool)
+        self.pool = K = int(pool if pool is not None else env_args.get("pool", 8))
         g = torch.Generator(device="cpu").manual_seed(int(seed) * 7919 + 1234)
         pin = (lambda t: t.pin_memory()) if self.host and torch.cuda.is_available() else (lambda t: t)
         rn = lambda *s: pin(torch.randn(*s, generator=g)).to(self.device)
@@ -216,8 +216,8 @@ class SyntheticBatchedEnv:
             dones = self._dead | env_done[:, None]
             dst["dones"].copy_(dones)
             dst["bad"].copy_((trunc & env_done)[:, None].expand(-1, A))
-            self._ep_step = torch.where(env_done, torch.zeros_like(self._ep_step), self._ep_step)
-            self._dead = self._dead & ~env_done[:, None]
+            self._ep_step.masked_fill_(env_done, 0)          # in place: the state must carry across CUDA-graph replays
+            self._dead &= ~env_done[:, None]
             av = self._avail_view(k, dones & ~env_done[:, None])
             if av is not None:
                 for a in range(A):
@@ -283,6 +283,25 @@ class SyntheticBatchedEnv:
             self._avail_h.copy_(av)
             for a in range(A):
                 h2d(dst["avail"][a], self._avail_h[:, a])
+
+    def graph_period(self):
+        """Number of steps after which the HOST side of ``step_into`` repeats itself (pool index, and in the simple
+        mode the host episode counter) -- a rollout of a multiple of this many steps can be captured into a CUDA
+        graph and replayed.  None: not capturable (host-resident env)."""
+        if self.host:
+            return None
+        if self._simple:
+            import math
+
+            return self.pool * self.episode_limit // math.gcd(self.pool, self.episode_limit)
+        return self.pool
+
+    def graph_advance(self, steps):
+        """Bookkeeping for a replayed graph of ``steps`` steps (the device state advanced inside the graph)."""
+        self._t += steps
+        self.steps_served += steps
+        if self._simple:
+            self._ep_step_host = (self._ep_step_host + steps) % self.episode_limit
 
     def seed(self, seed):
         pass

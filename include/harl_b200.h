@@ -163,8 +163,13 @@ typedef struct hb_collect_args {
   const float* share_obs;                        /* [critic_rows, sd] */
   int64_t critic_rows;                           /* rows (EP) or rows * n_agents (FP) */
   float* values;                                 /* [critic_rows, 1] */
+  const uint64_t* offset_base;                   /* device counter added to `offset` inside the kernel, or NULL:
+                                                    lets a CUDA graph of T rollout steps be replayed with fresh
+                                                    random streams (see hb_counter_add) */
 } hb_collect_args;
 int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_bytes, void* stream);
+/* *counter += inc on the device (one thread).  Stream-ordered; capturable into a CUDA graph. */
+int hb_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 
 /* VNet.forward (VCritic.get_values), v_net.py:48-67. values [rows,1]. */
 int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs,

@@ -238,3 +238,52 @@ def test_host_staged_rollout_equals_device_rollout(action_type, state_type, simp
     assert torch.equal(env.last_actions[0], last)
     for r in runners:
         r.close()
+
+
+@pytest.mark.parametrize("action_type,state_type,simple", [("Discrete", "EP", True), ("Box", "FP", False), ("Discrete", "EP", False)])
+def test_cuda_graph_rollout_equals_eager_rollout(action_type, state_type, simple):
+    """The T-step rollout replayed from a CUDA graph (iterations >= 2) must fill the buffers bit-identically to the
+    eager loop: same kernels, the Philox offsets advanced through the device counter.  Learning rates are zero so
+    that the two runs see identical weights in every iteration."""
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    snaps = []
+    for graph in (True, False):
+        args, algo_args, env_args = small_config(action_type=action_type, state_type=state_type, T=8)
+        env_args["pool"] = 4
+        if simple:
+            env_args.update(death_prob=0.0, terminate_prob=0.0, avail_prob=1.0)
+        algo_args["model"]["lr"] = 0.0
+        algo_args["model"]["critic_lr"] = 0.0
+        algo_args["train"]["use_linear_lr_decay"] = False
+        algo_args["train"]["log_interval"] = 10**9
+        algo_args["algo"]["fixed_order"] = True
+        r = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+        r.use_cuda_graph_rollout = graph
+        r.warmup()
+        r.logger.init(4)
+        per_iter = []
+        for it in range(1, 5):
+            r.run_iteration(it, 4)
+            torch.cuda.synchronize()
+            snap = {}
+            for a in range(r.num_agents):
+                b = r.actor_buffer[a]
+                for k in ("obs", "actions", "action_log_probs", "masks", "active_masks", "available_actions"):
+                    if getattr(b, k) is not None:
+                        snap[f"a{a}.{k}"] = getattr(b, k).clone()
+            for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks"):
+                snap["c." + k] = getattr(r.critic_buffer, k).clone()
+            per_iter.append(snap)
+        assert (r._fast.get("graph") is not None) == graph
+        snaps.append(per_iter)
+        done_sum = r.logger.done_sum.cpu().numpy()
+        snaps.append(done_sum)
+        r.close()
+    g_iters, g_done, e_iters, e_done = snaps
+    for it, (g, e) in enumerate(zip(g_iters, e_iters)):
+        for k in g:
+            assert torch.equal(g[k], e[k]), (it, k)
+    # consecutive iterations must not repeat the same samples (the offset counter advances inside the graph)
+    assert not torch.equal(g_iters[2]["a0.actions"], g_iters[3]["a0.actions"])
+    np.testing.assert_allclose(g_done, e_done, rtol=1e-6)
