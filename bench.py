@@ -238,6 +238,49 @@ def roofline_of(rows, peaks):
     return out
 
 
+def gae_microbench(torch, T, C, peaks, sets=8, reps=5):
+    """hb_gae_returns alone at the workload's [T, C]: CUDA events around sets x reps launches that rotate over
+    `sets` independent buffer sets (8 x 19.7 MB at C2 > the 126 MB L2, so every launch streams from HBM).
+    Algorithmic bytes = 24 B per (t, column): rewards, value_preds, masks, bad_masks read; returns, advantages
+    written."""
+    from harl_b200 import _lib as L
+
+    dev = torch.device("cuda:0" if "LOCAL_RANK" not in os.environ else f"cuda:{os.environ['LOCAL_RANK']}")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    bufs = []
+    for _ in range(sets):
+        rew = torch.randn(T, C, generator=g).to(dev)
+        vp = torch.randn(T + 1, C, generator=g).to(dev)
+        masks = (torch.rand(T + 1, C, generator=g) > 0.04).float().to(dev)
+        bad = (torch.rand(T + 1, C, generator=g) > 0.02).float().to(dev)
+        bufs.append((rew, vp, masks, bad, torch.randn(C, generator=g).to(dev), torch.empty(T + 1, C, device=dev),
+                     torch.empty(T, C, device=dev)))
+    vn = torch.tensor([0.1, 1.3, 1.0], device=dev)
+    st = L.stream_ptr()
+
+    def launch(b):
+        L.call("hb_gae_returns", L.ptr(b[0]), L.ptr(b[1]), L.ptr(b[2]), L.ptr(b[3]), L.ptr(b[4]), L.ptr(b[5]), L.ptr(b[6]),
+               T, C, 0.99, 0.99 * 0.95, 1, 1, L.ptr(vn), st)
+
+    for b in bufs:
+        launch(b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for b in bufs:
+            launch(b)
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / (sets * reps)
+    nbytes = 24.0 * T * C
+    hbm = peaks.get("hbm_gbs_sustained") or peaks.get("hbm_gbs")
+    ach = nbytes / (us * 1e-6) / 1e9
+    return {"kernel": f"hb_gae_returns[T{T},C{C}]", "avg_us": us, "bytes_per_launch": nbytes, "bound": "hbm", "achieved": ach,
+            "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "how": f"{sets} rotating buffer sets x {reps} reps, CUDA events on the launching stream (includes launch gaps)"}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -347,6 +390,12 @@ def main():
     rows = kernel_profile(runner, torch)
     if rank == 0 and rows:
         line["roofline"] = roofline_of(rows, load_peaks())
+        # the two kernels BASELINE.json's north_star names: the GAE scan and the PPO-update (clip-loss) kernel
+        named = {"gae": gae_microbench(torch, T, runner.critic_buffer.value_preds[0].numel(), load_peaks())}
+        ppo = [r for r in rows if r[0].startswith("policy_head_grad")]
+        if ppo:
+            named["ppo_update"] = dict(kernel=ppo[0][0], launches=ppo[0][1], avg_us=1e3 * ppo[0][2] / ppo[0][1], **_rate(ppo[0], load_peaks()))
+        line["roofline"]["named_kernels"] = named
         line["config"]["phases_ms"] = {k: round(v, 3) for k, v in getattr(runner, "phase_ms", {}).items()}
         if a.profile_out:
             tot = sum(r[2] for r in rows)

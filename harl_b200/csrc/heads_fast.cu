@@ -109,18 +109,42 @@ __device__ __forceinline__ void ln_bwd_cols(float (&df)[CPL], const float (&z)[C
   for (int i = 0; i < CPL; ++i) df[i] = rstd * (g[i] - m1 - xh[i] * m2) * actb<ACT>(act_rt, z[i]);
 }
 
+// ------------------------------------------------------------------ per-warp cp.async row ring
+// Rows are streamed through a D-stage shared-memory ring per warp: every lane copies the 16-byte column chunks it
+// will consume (feat, and the pre-LN z in gradient mode) with cp.async.cg, and lanes 0..15 of a row group copy that
+// row's 4-byte scalars (action, masks, advantage, old log-prob, LN statistics, availability).  D-1 stages (~2 KB
+// each per warp) are in flight while one is consumed -- the memory-level parallelism a register prefetch cannot
+// afford at ~200 live registers per thread.
+constexpr int RING_D = 4;
+constexpr int SC_FLOATS = 24;   // per-row scalar block: [0..7] scalars, [8..15] availability, [16..17] int64 source row
+enum { SC_ACT = 0, SC_W = 1, SC_FAC = 2, SC_ADV = 3, SC_OLD = 4, SC_REF = 5, SC_MU = 6, SC_RS = 7, SC_AVAIL = 8, SC_SRC = 16 };
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------ Categorical head: evaluate / gradient
 template <int CPL, int LPR, int MAXJ, int MODE, int ACT>
 __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discrete_rows_kernel(HeadArgs a) {
   constexpr int RT = MODE == MODE_GRAD ? RT_GRAD : RT_EVAL, RWARPS = RT / 32;
   constexpr int RPW = 32 / LPR, NC = CPL / 4, H = CPL * LPR;
+  constexpr bool GRAD = MODE == MODE_GRAD;
+  constexpr int ROW_FLOATS = H * (GRAD ? 2 : 1) + SC_FLOATS;      // feat [+ z] + scalars of one row
+  constexpr int STAGE_FLOATS = RPW * ROW_FLOATS;
   extern __shared__ __align__(16) float sm[];
   float* shw = sm;                    // [MAXJ][H]  rows >= na zero
   float* sb = shw + MAXJ * H;         // [8]
   float* sg = sb + 8;                 // [MAXJ][H]  head-weight gradient sums of this CTA
   float* sgb = sg + MAXJ * H;         // [8]
   float* sln = sgb + 8;               // [2][H]     LN affine gradient sums
-  double* sred = reinterpret_cast<double*>(sln + 2 * H);
+  double* sred = reinterpret_cast<double*>(sln + 2 * H);          // [RWARPS * 4]
+  float* ring = reinterpret_cast<float*>(sred + RWARPS * 4);      // [RWARPS][RING_D][STAGE_FLOATS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = lane % LPR, rw = lane / LPR;
   const int na = a.out;
@@ -129,19 +153,20 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
   if (threadIdx.x < 8) { sb[threadIdx.x] = threadIdx.x < na ? a.hbias[threadIdx.x] : 0.f; sgb[threadIdx.x] = 0.f; }
   __syncthreads();
 
-  float gacc[MODE == MODE_GRAD ? MAXJ : 1][CPL];
-  float gb[MODE == MODE_GRAD ? MAXJ : 1];
+  float gacc[GRAD ? MAXJ : 1][CPL];
+  float gb[GRAD ? MAXJ : 1];
   float lcg[CPL], lcb[CPL], lnw[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) { lcg[i] = lcb[i] = 0.f; lnw[i] = 1.f; }
-  if (MODE == MODE_GRAD) {
+  const bool has_ln = GRAD && a.ln_z != nullptr;
+  if (GRAD) {
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       gb[j] = 0.f;
 #pragma unroll
       for (int i = 0; i < CPL; ++i) gacc[j][i] = 0.f;
     }
-    if (a.ln_z != nullptr) {
+    if (has_ln) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         float4 v = ld4(a.ln_w + c * 4 * LPR + 4 * s);
@@ -149,57 +174,69 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
       }
     }
   }
-  const float inv_norm = MODE == MODE_GRAD ? (float)(1.0 / a.norm3[2]) : 0.f;
+  const float inv_norm = GRAD ? (float)(1.0 / a.norm3[2]) : 0.f;
   float s_loss = 0.f, s_ent = 0.f, s_ratio = 0.f, s_rows = 0.f;  // per-lane partials over <= ~16 rows; summed in fp64
 
-  struct RowIn { float4 f[NC]; float act, w, fac, adv, old, ref, av; };
-  auto fetch = [&](int64_t r, bool ok, int64_t src, RowIn& d) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) d.f[c] = ok ? ld4(a.feat + r * H + c * 4 * LPR + 4 * s) : make_float4(0.f, 0.f, 0.f, 0.f);
-    d.act = d.adv = d.old = d.ref = 0.f;
-    d.w = d.fac = d.av = 1.f;
-    if (ok) {
-      if (a.avail != nullptr && s < na) d.av = a.avail[src * na + s];
-      d.act = a.actions[src];
-      if constexpr (MODE == MODE_GRAD) {
-        if (a.use_active) d.w = a.active[src];
-        if (a.factor) d.fac = a.factor[src];
-        d.adv = a.adv[src];
-        d.old = a.old_logp[src];
-      } else {
-        if (a.factor_inout) { d.ref = a.logp_ref[src]; d.fac = a.factor_inout[src]; }
-      }
-    }
-  };
+  // which scalar this lane fetches for its row group: pointer, index multiplier (0: indexed by the batch row r with
+  // stride 2 -- the LN statistics; else by the buffer row src) and the slot it lands in
+  const float* sc_ptr = nullptr;
+  int sc_mul = 1, sc_off = 0, sc_slot = s;
+  bool sc_by_r = false;
+  if (s == SC_ACT) sc_ptr = a.actions;
+  else if (s == SC_W) { if (GRAD && a.use_active) sc_ptr = a.active; }
+  else if (s == SC_FAC) sc_ptr = GRAD ? a.factor : a.factor_inout;
+  else if (s == SC_ADV) { if (GRAD) sc_ptr = a.adv; }
+  else if (s == SC_OLD) { if (GRAD) sc_ptr = a.old_logp; }
+  else if (s == SC_REF) { if (!GRAD && a.factor_inout) sc_ptr = a.logp_ref; }
+  else if (s == SC_MU || s == SC_RS) { if (has_ln) { sc_ptr = a.ln_stats + (s - SC_MU); sc_by_r = true; sc_mul = 2; } }
+  else if (s >= SC_AVAIL && s - SC_AVAIL < na && a.avail != nullptr) { sc_ptr = a.avail; sc_mul = na; sc_off = s - SC_AVAIL; }
+
+  float* wring = ring + (size_t)warp * RING_D * STAGE_FLOATS;
   const int64_t stride = (int64_t)gridDim.x * RWARPS * RPW;
-  int64_t r0 = ((int64_t)blockIdx.x * RWARPS + warp) * RPW;  // first row of this warp's group of RPW rows
+  const int64_t rbase = ((int64_t)blockIdx.x * RWARPS + warp) * RPW + rw;   // this lane's row in iteration 0
   auto src_of = [&](int64_t r) -> int64_t { return (r < a.rows && a.index) ? (int64_t)a.index[r] : r; };
-  RowIn cur, nxt;
-  int64_t src_cur = src_of(r0 + rw), src_nxt = src_of(r0 + stride + rw);
-  fetch(r0 + rw, r0 + rw < a.rows, src_cur, cur);
-  for (; r0 < a.rows; r0 += stride) {
+  auto issue = [&](int it, int64_t src) {
+    const int64_t r = rbase + (int64_t)it * stride;
+    if (r < a.rows) {
+      float* row = wring + (it % RING_D) * STAGE_FLOATS + rw * ROW_FLOATS;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) cp_async16(row + c * 4 * LPR + 4 * s, a.feat + r * H + c * 4 * LPR + 4 * s);
+      if (has_ln) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cp_async16(row + H + c * 4 * LPR + 4 * s, a.ln_z + r * H + c * 4 * LPR + 4 * s);
+      }
+      float* sc = row + H * (GRAD ? 2 : 1);
+      if (sc_ptr != nullptr) cp_async4(sc + sc_slot, sc_ptr + (sc_by_r ? r : src) * sc_mul + sc_off);
+      if (s == 0) *reinterpret_cast<long long*>(sc + SC_SRC) = (long long)src;
+    }
+    cp_async_commit();
+  };
+  // prologue: stages 0 .. D-2
+  int64_t q0 = src_of(rbase);
+#pragma unroll
+  for (int d = 0; d < RING_D - 1; ++d) {
+    const int64_t qn = src_of(rbase + (int64_t)(d + 1) * stride);
+    issue(d, q0);
+    q0 = qn;
+  }
+  int64_t q1 = src_of(rbase + (int64_t)RING_D * stride);
+  int it = 0;
+  for (int64_t r0 = rbase - rw; r0 < a.rows; r0 += stride, ++it) {
     const int64_t r = r0 + rw;
     const bool ok = r < a.rows;
-    const int64_t src = src_cur;
-    const int64_t src_nn = src_of(r + 2 * stride);
-    fetch(r + stride, r + stride < a.rows, src_nxt, nxt);
-    // this row's pre-LN activations (consumed last: their latency hides behind the head algebra)
-    float z[CPL];
-    float ln_mu = 0.f, ln_rs = 0.f;
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) z[i] = 0.f;
-    if (MODE == MODE_GRAD && a.ln_z != nullptr && ok) {
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        float4 v = ld4(a.ln_z + r * H + c * 4 * LPR + 4 * s);
-        z[c * 4 + 0] = v.x; z[c * 4 + 1] = v.y; z[c * 4 + 2] = v.z; z[c * 4 + 3] = v.w;
-      }
-      ln_mu = a.ln_stats[r * 2];
-      ln_rs = a.ln_stats[r * 2 + 1];
-    }
+    issue(it + RING_D - 1, q0);
+    q0 = q1;
+    q1 = src_of(r + (int64_t)(RING_D + 1) * stride);
+    cp_async_wait<RING_D - 1>();
+    __syncwarp();
+    const float* row = wring + (it % RING_D) * STAGE_FLOATS + rw * ROW_FLOATS;
+    const float* sc = row + H * (GRAD ? 2 : 1);
     float f[CPL];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { f[c * 4 + 0] = cur.f[c].x; f[c * 4 + 1] = cur.f[c].y; f[c * 4 + 2] = cur.f[c].z; f[c * 4 + 3] = cur.f[c].w; }
+    for (int c = 0; c < NC; ++c) {
+      float4 v = ok ? ld4(row + c * 4 * LPR + 4 * s) : make_float4(0.f, 0.f, 0.f, 0.f);
+      f[c * 4 + 0] = v.x; f[c * 4 + 1] = v.y; f[c * 4 + 2] = v.z; f[c * 4 + 3] = v.w;
+    }
     // ---- logits: every lane of the group ends up with all of them
     float lg[MAXJ];
 #pragma unroll
@@ -218,38 +255,54 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
 #pragma unroll
       for (int j = 0; j < MAXJ; ++j) lg[j] += __shfl_xor_sync(FULL, lg[j], o);
     }
-    const unsigned avm = __ballot_sync(FULL, cur.av != 0.f) >> (rw * LPR);
+    unsigned avm = 0xffu;
+    if (a.avail != nullptr && ok) {
+      avm = 0u;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) if (j < na && sc[SC_AVAIL + j] != 0.f) avm |= 1u << j;
+    }
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       lg[j] = j < na ? (((avm >> j) & 1u) ? lg[j] + sb[j] : -1e10f) : -INFINITY;
       mx = fmaxf(mx, lg[j]);
     }
+    float ex[MAXJ];
     float se = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) se += expf(lg[j] - mx);
+    for (int j = 0; j < MAXJ; ++j) { ex[j] = expf(lg[j] - mx); se += ex[j]; }
     const float lse = mx + logf(se);
+    const float inv_se = 1.f / se;
     float lp[MAXJ], pj[MAXJ];
     float ent = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       lp[j] = lg[j] - lse;                       // normalised logit (torch Categorical(logits=)); -inf for j >= na
-      pj[j] = j < na ? expf(lp[j]) : 0.f;
+      pj[j] = ex[j] * inv_se;                    // softmax probability (0 for j >= na and for masked actions)
       ent = fmaf(-fmaxf(lp[j], -3.4028234663852886e38f), pj[j], ent);
     }
-    const int act = (int)cur.act;
+    const int act = ok ? (int)sc[SC_ACT] : 0;
     float lpa = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) lpa = j == act ? lp[j] : lpa;
-    if constexpr (MODE == MODE_EVAL) {
+    if constexpr (!GRAD) {
       if (ok && s == 0) {
         if (a.logp_out) a.logp_out[r] = lpa;
-        if (a.factor_inout) a.factor_inout[src] = cur.fac * expf(lpa - cur.ref);
+        if (a.factor_inout) {
+          const long long src = *reinterpret_cast<const long long*>(sc + SC_SRC);
+          a.factor_inout[src] = sc[SC_FAC] * expf(lpa - sc[SC_REF]);
+        }
       }
     } else {
       // ---- happo.py:66-91
-      const float w = cur.w, fac = cur.fac, adv = cur.adv;
-      const float ratio = expf(lpa - cur.old);
+      float w = 1.f, fac = 1.f, adv = 0.f, old = 0.f;
+      if (ok) {
+        if (a.use_active) w = sc[SC_W];
+        if (a.factor) fac = sc[SC_FAC];
+        adv = sc[SC_ADV];
+        old = sc[SC_OLD];
+      }
+      const float ratio = expf(lpa - old);
       float m;
       const float dm = dmin_dr(ratio, adv, a.clip, a.use_clip, &m);
       const float okf = ok ? 1.f : 0.f;
@@ -277,16 +330,26 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
 #pragma unroll
         for (int i = 0; i < CPL; ++i) gacc[j][i] = fmaf(dl[j], f[i], gacc[j][i]);
       }
-      if (a.ln_z != nullptr) ln_bwd_cols<CPL, LPR, ACT>(df, z, ln_mu, ln_rs, lnw, a.ln_act, lcg, lcb);
+      if (has_ln) {
+        float z[CPL];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float4 v = ok ? ld4(row + H + c * 4 * LPR + 4 * s) : make_float4(0.f, 0.f, 0.f, 0.f);
+          z[c * 4 + 0] = v.x; z[c * 4 + 1] = v.y; z[c * 4 + 2] = v.z; z[c * 4 + 3] = v.w;
+        }
+        const float ln_mu = ok ? sc[SC_MU] : 0.f, ln_rs = ok ? sc[SC_RS] : 0.f;
+        ln_bwd_cols<CPL, LPR, ACT>(df, z, ln_mu, ln_rs, lnw, a.ln_act, lcg, lcb);
+      }
       if (ok) {
 #pragma unroll
         for (int c = 0; c < NC; ++c)
           st4(a.dfeat + r * H + c * 4 * LPR + 4 * s, make_float4(df[c * 4 + 0], df[c * 4 + 1], df[c * 4 + 2], df[c * 4 + 3]));
       }
     }
-    cur = nxt; src_cur = src_nxt; src_nxt = src_nn;
+    __syncwarp();   // every lane is done with this stage before a later issue overwrites it
   }
-  if constexpr (MODE == MODE_GRAD) {
+  cp_async_wait<0>();
+  if constexpr (GRAD) {
     // fold the row groups of the warp, then the warps of the CTA (shared atomics), then one slot write per CTA
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
@@ -305,7 +368,7 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
           if (s == 0) atomicAdd(&sgb[j], gb[j]);
         }
       }
-      if (a.ln_z != nullptr) {
+      if (has_ln) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const int col = (i / 4) * 4 * LPR + 4 * s + (i % 4);
@@ -318,7 +381,7 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
     const int64_t slot = a.part_stride ? a.part_delta + (int64_t)blockIdx.x * a.part_stride : 0;
     for (int i = threadIdx.x; i < na * H; i += RT) acc_out(a.g_hw + i, sg[i], slot);
     if (threadIdx.x < na) acc_out(a.g_hbias + threadIdx.x, sgb[threadIdx.x], slot);
-    if (a.ln_z != nullptr)
+    if (has_ln)
       for (int n = threadIdx.x; n < H; n += RT) { acc_out(a.g_ln_w + n, sln[n], slot); acc_out(a.g_ln_b + n, sln[H + n], slot); }
     block_scalars<RWARPS>((double)s_loss, (double)s_ent, (double)s_ratio, (double)s_rows, a.scalars, sred);
   }
@@ -457,7 +520,10 @@ template <int CPL, int LPR, int MAXJ, int MODE, int ACT>
 int launch_discrete(const HeadArgs& a, cudaStream_t st) {
   constexpr int H = CPL * LPR;
   constexpr int RT = MODE == MODE_GRAD ? RT_GRAD : RT_EVAL;
-  const size_t smem = (size_t)(2 * MAXJ * H + 16 + 2 * H) * sizeof(float) + (RT / 32) * 4 * sizeof(double);
+  constexpr int ROW_FLOATS = H * (MODE == MODE_GRAD ? 2 : 1) + SC_FLOATS;
+  const size_t smem = (size_t)(2 * MAXJ * H + 16 + 2 * H) * sizeof(float) + (RT / 32) * 4 * sizeof(double) +
+                      (size_t)(RT / 32) * RING_D * (32 / LPR) * ROW_FLOATS * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(discrete_rows_kernel<CPL, LPR, MAXJ, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   auto kern = discrete_rows_kernel<CPL, LPR, MAXJ, MODE, ACT>;
   const int g = grid_for(a.rows, (RT / 32) * (32 / LPR), MODE == MODE_GRAD && a.part_stride != 0);
   kern<<<g, RT, smem, st>>>(a);
@@ -468,6 +534,7 @@ int launch_discrete(const HeadArgs& a, cudaStream_t st) {
 template <int CPL, int LPR, int MODE, int ACT>
 int launch_discrete_j(const HeadArgs& a, cudaStream_t st) {
   if (a.out <= 4) return launch_discrete<CPL, LPR, 4, MODE, ACT>(a, st);
+  if (a.out == 5) return launch_discrete<CPL, LPR, 5, MODE, ACT>(a, st);
   if (a.out <= 6) return launch_discrete<CPL, LPR, 6, MODE, ACT>(a, st);
   return launch_discrete<CPL, LPR, 8, MODE, ACT>(a, st);
 }

@@ -130,7 +130,9 @@ struct TcSmem {
   uint64_t empty[TC_STAGES];               // MMAs that read the stage retired
   uint64_t done;                   // all MMAs retired
   uint32_t tmem_base;
-  float pbias[NT], plnw[NT], plnb[NT];   // epilogue parameters
+  alignas(16) float pbias[NT];           // epilogue parameters (16-byte aligned: read as broadcast float4)
+  alignas(16) float plnw[NT];
+  alignas(16) float plnb[NT];
 };
 
 template <int NT, int ACT, int PASSES>
@@ -176,24 +178,19 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
       mbar_expect_tx(&s.full_b[st], B_BYTES);
       tma_bulk_g2s(s.b[st], tiles + (int64_t)c * (2 * NT * TC_KC), B_BYTES, &s.full_b[st]);
     }
-    // A: a warp stages 32 rows of the tile, 4 rows x 8 16-byte k-chunks per instruction -- every global request
-    // covers four full 128-byte lines (a thread-per-row walk would touch 32 lines per request and serialise in the
-    // LSU).  Zeros beyond M / Kred; hi and lo images in the canonical layout [(row/8)][kc][row%8][4].
+    // A: thread t stages row t of the tile (zeros beyond M / Kred), hi and lo images
     {
       float* ahi = s.a[st][0];
       float* alo = s.a[st][1];
-      const int kc = tid & 7, r4 = (tid & 31) >> 3;
-      const bool kin = c * TC_KC + kc * 4 < Kred;
+      const int base = ((tid >> 3) * 8) * 32 + (tid & 7) * 4;  // floats: [(row/8)][kc][row%8][4]
+      const float* xr = X + row * ldx + c * TC_KC;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rl = warp * 32 + i * 4 + r4;
-        const int64_t grow = row0 + rl;
+      for (int kc = 0; kc < 8; ++kc) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kin && grow < M) v = *reinterpret_cast<const float4*>(X + grow * ldx + c * TC_KC + kc * 4);
-        const int base = ((rl >> 3) * 8 + kc) * 32 + (rl & 7) * 4;
+        if (row < M && c * TC_KC + kc * 4 < Kred) v = *reinterpret_cast<const float4*>(xr + kc * 4);
         float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        *reinterpret_cast<float4*>(ahi + base) = h;
-        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        *reinterpret_cast<float4*>(ahi + base + kc * 32) = h;
+        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
     }
     fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -223,65 +220,76 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
   tc_fence_after();
 
   // ---- epilogue: thread = row.  z = acc + b, a = act(z), LayerNorm over the N valid columns.
-  // Parameters come from shared memory; output tiles are transposed through the (now idle) operand stage with an
-  // XOR swizzle on 16-byte chunks so that both the row-per-thread writes and the row-per-warp reads are conflict
-  // free, and the global stores are full 512-byte rows.
+  // Two passes over the accumulator row in TMEM.  Pass A: shifted one-pass statistics (shift = the row's first
+  // activation, so E[d^2] - E[d]^2 has no large-mean cancellation).  Pass B: Z and Y of a 64-column half tile are
+  // formed together and transposed through the (now idle) operand stages -- two XOR-swizzled half tiles, conflict
+  // free for the row-per-thread writes and the row-per-warp reads -- into full-row coalesced global stores.
+  // Parameters are read from shared memory as broadcast float4 (one LDS per 4 columns: the LSU / shared pipe, not
+  // the tensor pipe, is what this kernel saturates -- profiles/ncu_bigm_r01_summary.txt).
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const float inv_n = 1.f / (float)N;
-  float sum = 0.f;
+  float s1 = 0.f, s2 = 0.f, shift = 0.f;
   for (int c0 = 0; c0 < N; c0 += 32) {
     float v[32];
     tmem_ld32(trow + c0, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c0 + j < N) sum += act_fwd<ACT>(v[j] + s.pbias[c0 + j]);
-  }
-  const float mean = sum * inv_n;
-  float sq = 0.f;
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float v[32];
-    tmem_ld32(trow + c0, v);
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+      if (c0 + j4 < N) {  // N is a multiple of 4
+        const float4 b4 = *reinterpret_cast<const float4*>(&s.pbias[c0 + j4]);
+        const float av[4] = {act_fwd<ACT>(v[j4] + b4.x), act_fwd<ACT>(v[j4 + 1] + b4.y), act_fwd<ACT>(v[j4 + 2] + b4.z),
+                             act_fwd<ACT>(v[j4 + 3] + b4.w)};
+        if (c0 == 0 && j4 == 0) shift = av[0];
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c0 + j < N) { float d = act_fwd<ACT>(v[j] + s.pbias[c0 + j]) - mean; sq = fmaf(d, d, sq); }
+        for (int q = 0; q < 4; ++q) { const float d = av[q] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+      }
+    }
   }
-  const float rstd = rsqrtf(sq * inv_n + 1e-5f);
-  constexpr int CPR = NT / 4;                       // 16-byte chunks per tile row
-  constexpr bool kViaSmem = (size_t)TC_BM * NT * 4 <= sizeof(s.a) + sizeof(s.b);
-  float4* tile = reinterpret_cast<float4*>(&s.a[0][0][0]);
+  const float dm = s1 * inv_n;
+  const float mean = shift + dm;
+  const float rstd = rsqrtf(fmaxf(s2 * inv_n - dm * dm, 0.f) + 1e-5f);
+  constexpr int NH = NT >= 64 ? 2 : 1;              // column halves
+  constexpr int HC = NT / NH;                       // columns per half
+  constexpr int CPRH = HC / 4;                      // 16-byte chunks per half-tile row
+  constexpr bool kViaSmem = (size_t)2 * TC_BM * HC * 4 <= sizeof(s.a) + sizeof(s.b);
+  float4* zt = reinterpret_cast<float4*>(&s.a[0][0][0]);
+  float4* yt = zt + TC_BM * CPRH;
   const int nvalid = (int)(M - row0 < TC_BM ? M - row0 : TC_BM);
+  const int sw = tid & (CPRH - 1);
 #pragma unroll 1
-  for (int pass = (Z != nullptr ? 0 : 1); pass < 2; ++pass) {
-    float* __restrict__ out = pass == 0 ? Z : Y;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+  for (int h = 0; h < NH; ++h) {
+    for (int c0 = h * HC; c0 < (h + 1) * HC && c0 < N; c0 += 32) {
       float v[32];
       tmem_ld32(trow + c0, v);
 #pragma unroll
       for (int j4 = 0; j4 < 32; j4 += 4) {
-        if (c0 + j4 < N) {  // N is a multiple of 4
-          float o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = c0 + j4 + q;
-            const float z = v[j4 + q] + s.pbias[n];
-            o[q] = pass == 0 ? z : (act_fwd<ACT>(z) - mean) * rstd * s.plnw[n] + s.plnb[n];
-          }
-          const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+        if (c0 + j4 < N && c0 + j4 < (h + 1) * HC) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s.pbias[c0 + j4]);
+          const float4 g4 = *reinterpret_cast<const float4*>(&s.plnw[c0 + j4]);
+          const float4 e4 = *reinterpret_cast<const float4*>(&s.plnb[c0 + j4]);
+          const float4 z4 = make_float4(v[j4] + b4.x, v[j4 + 1] + b4.y, v[j4 + 2] + b4.z, v[j4 + 3] + b4.w);
+          const float4 y4 = make_float4((act_fwd<ACT>(z4.x) - mean) * rstd * g4.x + e4.x, (act_fwd<ACT>(z4.y) - mean) * rstd * g4.y + e4.y,
+                                        (act_fwd<ACT>(z4.z) - mean) * rstd * g4.z + e4.z, (act_fwd<ACT>(z4.w) - mean) * rstd * g4.w + e4.w);
           if (kViaSmem) {
-            const int ch = (c0 + j4) >> 2;
-            tile[tid * CPR + (ch ^ (tid & (CPR - 1) & 31))] = o4;
+            const int ch = (c0 - h * HC + j4) >> 2;
+            if (Z != nullptr) zt[tid * CPRH + (ch ^ sw)] = z4;
+            yt[tid * CPRH + (ch ^ sw)] = y4;
           } else if (row < M) {
-            *reinterpret_cast<float4*>(out + row * N + c0 + j4) = o4;
+            if (Z != nullptr) *reinterpret_cast<float4*>(Z + row * N + c0 + j4) = z4;
+            *reinterpret_cast<float4*>(Y + row * N + c0 + j4) = y4;
           }
         }
       }
     }
     if (kViaSmem) {
       __syncthreads();
-      for (int i = tid; i < TC_BM * CPR; i += 128) {
-        const int r = i / CPR, lc = i % CPR;
-        if (r < nvalid && lc * 4 < N)
-          *reinterpret_cast<float4*>(out + (row0 + r) * N + lc * 4) = tile[r * CPR + (lc ^ (r & (CPR - 1) & 31))];
+      for (int i = tid; i < TC_BM * CPRH; i += 128) {
+        const int r = i / CPRH, lc = i % CPRH;
+        const int col = h * HC + lc * 4;
+        if (r < nvalid && col < N) {
+          const int slot = r * CPRH + (lc ^ (r & (CPRH - 1)));
+          if (Z != nullptr) *reinterpret_cast<float4*>(Z + (row0 + r) * N + col) = zt[slot];
+          *reinterpret_cast<float4*>(Y + (row0 + r) * N + col) = yt[slot];
+        }
       }
       __syncthreads();
     }
@@ -392,21 +400,18 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
       mbar_expect_tx(&s.full_b[st], B_BYTES);
       tma_bulk_g2s(s.b[st], tiles + (int64_t)c * (2 * NT * TC_KC), B_BYTES, &s.full_b[st]);
     }
-    {  // coalesced staging of the dZ rows (4 rows x 8 k-chunks per warp instruction), as in the forward kernel
+    {
       float* ahi = s.a[st][0];
       float* alo = s.a[st][1];
-      const int kc = tid & 7, r4 = (tid & 31) >> 3;
-      const bool kin = c * TC_KC + kc * 4 < N;
+      const int base = ((tid >> 3) * 8) * 32 + (tid & 7) * 4;
+      const float* xr = dZ + row * N + c * TC_KC;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rl = warp * 32 + i * 4 + r4;
-        const int64_t grow = row0 + rl;
+      for (int kc = 0; kc < 8; ++kc) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kin && grow < M) v = *reinterpret_cast<const float4*>(dZ + grow * N + c * TC_KC + kc * 4);
-        const int base = ((rl >> 3) * 8 + kc) * 32 + (rl & 7) * 4;
+        if (row < M && c * TC_KC + kc * 4 < N) v = *reinterpret_cast<const float4*>(xr + kc * 4);
         float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        *reinterpret_cast<float4*>(ahi + base) = h;
-        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        *reinterpret_cast<float4*>(ahi + base + kc * 32) = h;
+        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
     }
     fence_async_smem();
@@ -470,12 +475,13 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
       if (kViaSmem) { if (c0 + j4 < NT) z = tile[tid * CPR + ((((c0 + j4) >> 2)) ^ sw)]; }
       else if (ok) z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
       const float zz[4] = {z.x, z.y, z.z, z.w};
+      const float4 w4 = *reinterpret_cast<const float4*>(&s.plnb[c0 + j4 < NT ? c0 + j4 : 0]);
+      const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int n = c0 + j4 + q;
         const float dy = ok ? v[j4 + q] : 0.f;
         const float x = ok ? (act_fwd<ACT>(zz[q]) - mu) * rstd : 0.f;
-        const float g = ok ? dy * s.plnb[n] : 0.f;
+        const float g = ok ? dy * ww[q] : 0.f;
         cg[j4 + q] = dy * x;
         cb[j4 + q] = dy;
         s1 += g;
@@ -497,12 +503,13 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
         if (kViaSmem) z = tile[slot];
         else if (rok) z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
         const float zz[4] = {z.x, z.y, z.z, z.w};
+        const float4 w4 = *reinterpret_cast<const float4*>(&s.plnb[c0 + j4]);
+        const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
         float o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int n = c0 + j4 + q;
           const float x = (act_fwd<ACT>(zz[q]) - mu) * rstd;
-          const float g = v[j4 + q] * s.plnb[n];
+          const float g = v[j4 + q] * ww[q];
           o[q] = rstd * (g - m1 - x * m2) * act_bwd<ACT>(zz[q]);
         }
         const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
@@ -610,42 +617,55 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
   float bsum = 0.f;
   const int fa = n0 + tid;                                   // this thread's dZ feature
   const int slot = ((tid >> 3) * 8) * 32 + (tid & 7) * 4;    // floats; + kc*32 per 4-row group
+  // Register double buffering: the global loads of chunk c + 1 are issued right after chunk c went to shared memory,
+  // so their latency overlaps the fence / barrier / MMAs of chunk c instead of adding to every chunk's critic path
+  // (the single operand stage keeps three CTAs per SM).
+  constexpr int NB = (NTK + 127) / 128;    // X features per thread
+  float va[TC_KC], vb[NB][TC_KC];
+  auto load_chunk = [&](int c) {
+    const int64_t r0 = m0 + (int64_t)c * TC_KC;
+#pragma unroll
+    for (int q = 0; q < TC_KC; ++q) {
+      const int64_t r = r0 + q;
+      va[q] = (r < m1 && fa < N) ? dZ[r * N + fa] : 0.f;
+    }
+#pragma unroll
+    for (int fb = 0; fb < NB; ++fb) {
+      const int f = fb * 128 + tid;
+#pragma unroll
+      for (int q = 0; q < TC_KC; ++q) {
+        const int64_t r = r0 + q;
+        vb[fb][q] = (f < NTK && r < m1 && k0 + f < ldx) ? X[r * ldx + k0 + f] : 0.f;
+      }
+    }
+  };
+  if (nchunks > 0) load_chunk(0);
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % TC_STAGES;
     if (c >= TC_STAGES) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }
-    const int64_t r0 = m0 + (int64_t)c * TC_KC;
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) {
-      float v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t r = r0 + kc * 4 + q;
-        v[q] = (r < m1 && fa < N) ? dZ[r * N + fa] : 0.f;
-        bsum += v[q];
-      }
+      const float* v = va + kc * 4;
+      bsum += (v[0] + v[1]) + (v[2] + v[3]);
       const float4 h = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
       *reinterpret_cast<float4*>(&s.a[st][0][slot + kc * 32]) = h;
       if (PASSES == 3) *reinterpret_cast<float4*>(&s.a[st][1][slot + kc * 32]) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
     }
 #pragma unroll
-    for (int fb = 0; fb < NTK; fb += 128) {
-      const int f = fb + tid;
+    for (int fb = 0; fb < NB; ++fb) {
+      const int f = fb * 128 + tid;
       if (f < NTK) {
         const int bslot = ((f >> 3) * 8) * 32 + (f & 7) * 4;
 #pragma unroll
         for (int kc = 0; kc < 8; ++kc) {
-          float v[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int64_t r = r0 + kc * 4 + q;
-            v[q] = (r < m1 && k0 + f < ldx) ? X[r * ldx + k0 + f] : 0.f;
-          }
+          const float* v = vb[fb] + kc * 4;
           const float4 h = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
           *reinterpret_cast<float4*>(&s.b[st][0][bslot + kc * 32]) = h;
           if (PASSES == 3) *reinterpret_cast<float4*>(&s.b[st][1][bslot + kc * 32]) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
         }
       }
     }
+    if (c + 1 < nchunks) load_chunk(c + 1);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
