@@ -259,26 +259,53 @@ def gae_microbench(torch, T, C, peaks, sets=8, reps=5):
     st = L.stream_ptr()
 
     def launch(b):
+        nonlocal st
         L.call("hb_gae_returns", L.ptr(b[0]), L.ptr(b[1]), L.ptr(b[2]), L.ptr(b[3]), L.ptr(b[4]), L.ptr(b[5]), L.ptr(b[6]),
                T, C, 0.99, 0.99 * 0.95, 1, 1, L.ptr(vn), st)
 
     for b in bufs:
         launch(b)
     torch.cuda.synchronize()
+    # the launches go through a CUDA graph: issued eagerly from Python they would be host-bound (~10 us per call)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        st = L.stream_ptr()
+        for b in bufs:
+            launch(b)
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for b in bufs:
-            launch(b)
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
+    # the same traffic as plain device copies (12 B read + 12 B written per element), same rotation, same graph trick
+    srcs = [torch.empty(3 * T * C, device=dev) for _ in range(sets)]
+    dsts = [torch.empty(3 * T * C, device=dev) for _ in range(sets)]
+    cgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cgraph):
+        for a_, b_ in zip(dsts, srcs):
+            a_.copy_(b_)
+    cgraph.replay()
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(reps):
+        cgraph.replay()
+    c1.record()
+    torch.cuda.synchronize()
+    copy_us = 1e3 * c0.elapsed_time(c1) / (sets * reps)
     us = 1e3 * e0.elapsed_time(e1) / (sets * reps)
     nbytes = 24.0 * T * C
     hbm = peaks.get("hbm_gbs_sustained") or peaks.get("hbm_gbs")
     ach = nbytes / (us * 1e-6) / 1e9
     return {"kernel": f"hb_gae_returns[T{T},C{C}]", "avg_us": us, "bytes_per_launch": nbytes, "bound": "hbm", "achieved": ach,
             "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-            "how": f"{sets} rotating buffer sets x {reps} reps, CUDA events on the launching stream (includes launch gaps)"}
+            "same_bytes_copy_us": copy_us, "frac_of_same_size_copy": copy_us / us,
+            "how": f"{sets} rotating buffer sets (> L2) x {reps} replays of a CUDA graph of the launches; same_bytes_copy_us = "
+                   "torch copy_ kernels moving the same 24 B per element at this size, timed the same way (what a 19.7 MB "
+                   "launch can reach at all: launch + fill latency are not amortised at n_rollout_threads=4096)"}
 
 
 def load_peaks():

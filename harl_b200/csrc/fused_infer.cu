@@ -2,7 +2,7 @@
 //   feature LayerNorm -> [Linear -> act -> LayerNorm] x L -> head (sample / mode + log-prob, or value)
 // for all rollout threads (OnPolicyBaseRunner.collect, harl/runners/on_policy_base_runner.py:285-340, which issues
 // (A+1) x ~10 framework kernels per step).  Rollout batches are small (N rows per net), so the step is launch- and
-// latency-bound: grid = (row tiles of 32) x (A+1 nets); activations never leave shared memory; weights (<= 340 KB per
+// latency-bound: grid = (row tiles of 64) x (A+1 nets); activations never leave shared memory; weights (<= 340 KB per
 // net, L2-resident) stream through a double-buffered shared tile.  FP32 FFMA with the same summation order as
 // linear_ln_fwd_kernel / the row-wise head kernels, so results are bit-identical to the unfused path.
 #include <math.h>
@@ -12,7 +12,8 @@
 
 namespace hb {
 
-constexpr int FI_ROWS = 32;
+constexpr int FI_ROWS = 64;             // rows per CTA: 4 per thread -> 6.4 FMAs per shared-memory wavefront (FFMA-bound)
+constexpr int FI_RPT = FI_ROWS / 16;   // rows per thread
 constexpr int FI_KC = 16;
 #define FI_LOG_2PI_F 1.8378770664093453f
 
@@ -102,9 +103,9 @@ __global__ void __launch_bounds__(256) fused_infer_kernel(const __grid_constant_
     const float* lnw = bias + N;
     const float* lnb = lnw + N;
     off += K * N + 3 * N;
-    float acc[2][NT / 16];
+    float acc[FI_RPT][NT / 16];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < FI_RPT; ++i)
 #pragma unroll
       for (int j = 0; j < NT / 16; ++j) acc[i][j] = 0.f;
     const int nk = (K + FI_KC - 1) / FI_KC;
@@ -136,17 +137,17 @@ __global__ void __launch_bounds__(256) fused_infer_kernel(const __grid_constant_
 #pragma unroll
       for (int k4 = 0; k4 < FI_KC; k4 += 4) {
         const int kg = kt * FI_KC + k4;
-        float4 av[2];
+        float4 av[FI_RPT];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-          av[i] = kg < K ? *reinterpret_cast<const float4*>(&cur[(ty * 2 + i) * pc + kg]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < FI_RPT; ++i)
+          av[i] = kg < K ? *reinterpret_cast<const float4*>(&cur[(ty * FI_RPT + i) * pc + kg]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           float4 bv[NCH];
 #pragma unroll
           for (int c = 0; c < NCH; ++c) bv[c] = *reinterpret_cast<const float4*>(&wbuf[(buf * FI_KC + k4 + kk) * NT + c * 64 + tx * 4]);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < FI_RPT; ++i) {
             const float a = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(256) fused_infer_kernel(const __grid_constant_
     // epilogue: bias, activation, LayerNorm (row statistics inside a half-warp), write to the other tile
     const float inv_n = 1.f / (float)N;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = ty * 2 + i;
+    for (int i = 0; i < FI_RPT; ++i) {
+      const int r = ty * FI_RPT + i;
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {

@@ -3,7 +3,7 @@
 //   tc_linear_ln_fwd : Y = LN(act(X W'^T + b'))     (same contract as the SIMT linear_ln_fwd_kernel)
 //
 // Numerics: kind::tf32 MMAs with fp32 accumulation in TMEM.  PASSES = 3 runs the error-compensated
-// split  x = hi + lo  (hi = x with the low 13 mantissa bits cleared, lo = x - hi, both exactly
+// split  x = hi + lo  (hi = x rounded to TF32, lo = the residual rounded to TF32, both exactly
 // representable in TF32 up to 2^-22):  D += A_hi B_hi + A_lo B_hi + A_hi B_lo, which restores fp32-level
 // accuracy (relative error ~3e-7 per product) at 3 MMAs per tile; PASSES = 1 is plain TF32.
 //
@@ -92,7 +92,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// Round-to-nearest TF32 (cvt.rna): |x - hi| <= 2^-11 |x| and, for the residual, |r - lo| <= 2^-11 |r|, so
+// x = hi + lo up to 2^-22 |x| -- four times tighter than clearing the low 13 mantissa bits, at the same MMA count.
+// (two integer ops: add half a TF32 ulp to the magnitude bits, clear the low 13; a mantissa carry into the exponent
+// is the correct round-up; inf / nan inputs are not preserved -- they are garbage in the reference as well.)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_hi(x - hi); }
 
 // ------------------------------------------------------------------ weight tile packing (part of hb_net_prepare)
 // dst: for each k-chunk c (32 wide): hi image [NT][32] then lo image, canonical K-major UMMA layout.
@@ -109,7 +114,7 @@ __global__ void pack_umma_tiles_kernel(const float* __restrict__ W, int ldn, int
     if (n < N && k < K) { v = W[(int64_t)n * ldn + (int64_t)k * ldk]; if (scale) v *= scale[k]; }
     const float hi = tf32_hi(v);
     dst[(int64_t)c * per_chunk + e] = hi;
-    dst[(int64_t)c * per_chunk + NT * TC_KC + e] = v - hi;
+    dst[(int64_t)c * per_chunk + NT * TC_KC + e] = tf32_lo(v, hi);
   }
 }
 
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
         if (row < M && c * TC_KC + kc * 4 < Kred) v = *reinterpret_cast<const float4*>(xr + kc * 4);
         float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
         *reinterpret_cast<float4*>(ahi + base + kc * 32) = h;
-        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
       }
     }
     fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -220,15 +225,15 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
   tc_fence_after();
 
   // ---- epilogue: thread = row.  z = acc + b, a = act(z), LayerNorm over the N valid columns.
-  // Two passes over the accumulator row in TMEM.  Pass A: shifted one-pass statistics (shift = the row's first
-  // activation, so E[d^2] - E[d]^2 has no large-mean cancellation).  Pass B: Z and Y of a 64-column half tile are
+  // Three passes over the accumulator row in TMEM: sum, centred sum of squares (the exact two-pass LayerNorm
+  // statistics, in the same summation order as the FP32 SIMT kernel), then Z and Y of a 64-column half tile are
   // formed together and transposed through the (now idle) operand stages -- two XOR-swizzled half tiles, conflict
   // free for the row-per-thread writes and the row-per-warp reads -- into full-row coalesced global stores.
   // Parameters are read from shared memory as broadcast float4 (one LDS per 4 columns: the LSU / shared pipe, not
   // the tensor pipe, is what this kernel saturates -- profiles/ncu_bigm_r01_summary.txt).
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const float inv_n = 1.f / (float)N;
-  float s1 = 0.f, s2 = 0.f, shift = 0.f;
+  float sum = 0.f;
   for (int c0 = 0; c0 < N; c0 += 32) {
     float v[32];
     tmem_ld32(trow + c0, v);
@@ -236,17 +241,31 @@ __global__ void __launch_bounds__(128, 1) tc_linear_ln_fwd_kernel(const float* _
     for (int j4 = 0; j4 < 32; j4 += 4) {
       if (c0 + j4 < N) {  // N is a multiple of 4
         const float4 b4 = *reinterpret_cast<const float4*>(&s.pbias[c0 + j4]);
-        const float av[4] = {act_fwd<ACT>(v[j4] + b4.x), act_fwd<ACT>(v[j4 + 1] + b4.y), act_fwd<ACT>(v[j4 + 2] + b4.z),
-                             act_fwd<ACT>(v[j4 + 3] + b4.w)};
-        if (c0 == 0 && j4 == 0) shift = av[0];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float d = av[q] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+        sum += act_fwd<ACT>(v[j4] + b4.x);
+        sum += act_fwd<ACT>(v[j4 + 1] + b4.y);
+        sum += act_fwd<ACT>(v[j4 + 2] + b4.z);
+        sum += act_fwd<ACT>(v[j4 + 3] + b4.w);
       }
     }
   }
-  const float dm = s1 * inv_n;
-  const float mean = shift + dm;
-  const float rstd = rsqrtf(fmaxf(s2 * inv_n - dm * dm, 0.f) + 1e-5f);
+  const float mean = sum * inv_n;
+  float sq = 0.f;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(trow + c0, v);
+#pragma unroll
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+      if (c0 + j4 < N) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&s.pbias[c0 + j4]);
+        float d;
+        d = act_fwd<ACT>(v[j4] + b4.x) - mean; sq = fmaf(d, d, sq);
+        d = act_fwd<ACT>(v[j4 + 1] + b4.y) - mean; sq = fmaf(d, d, sq);
+        d = act_fwd<ACT>(v[j4 + 2] + b4.z) - mean; sq = fmaf(d, d, sq);
+        d = act_fwd<ACT>(v[j4 + 3] + b4.w) - mean; sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  const float rstd = rsqrtf(sq * inv_n + 1e-5f);
   constexpr int NH = NT >= 64 ? 2 : 1;              // column halves
   constexpr int HC = NT / NH;                       // columns per half
   constexpr int CPRH = HC / 4;                      // 16-byte chunks per half-tile row
@@ -411,7 +430,7 @@ __global__ void __launch_bounds__(128, 1) tc_dx_ln_bwd_kernel(const float* __res
         if (row < M && c * TC_KC + kc * 4 < N) v = *reinterpret_cast<const float4*>(xr + kc * 4);
         float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
         *reinterpret_cast<float4*>(ahi + base + kc * 32) = h;
-        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
       }
     }
     fence_async_smem();
@@ -649,7 +668,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
       bsum += (v[0] + v[1]) + (v[2] + v[3]);
       const float4 h = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
       *reinterpret_cast<float4*>(&s.a[st][0][slot + kc * 32]) = h;
-      if (PASSES == 3) *reinterpret_cast<float4*>(&s.a[st][1][slot + kc * 32]) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+      if (PASSES == 3) *reinterpret_cast<float4*>(&s.a[st][1][slot + kc * 32]) = make_float4(tf32_lo(v[0], h.x), tf32_lo(v[1], h.y), tf32_lo(v[2], h.z), tf32_lo(v[3], h.w));
     }
 #pragma unroll
     for (int fb = 0; fb < NB; ++fb) {
@@ -661,7 +680,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
           const float* v = vb[fb] + kc * 4;
           const float4 h = make_float4(tf32_hi(v[0]), tf32_hi(v[1]), tf32_hi(v[2]), tf32_hi(v[3]));
           *reinterpret_cast<float4*>(&s.b[st][0][bslot + kc * 32]) = h;
-          if (PASSES == 3) *reinterpret_cast<float4*>(&s.b[st][1][bslot + kc * 32]) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+          if (PASSES == 3) *reinterpret_cast<float4*>(&s.b[st][1][bslot + kc * 32]) = make_float4(tf32_lo(v[0], h.x), tf32_lo(v[1], h.y), tf32_lo(v[2], h.z), tf32_lo(v[3], h.w));
         }
       }
     }

@@ -385,9 +385,10 @@ def test_actor_grad_vs_oracle_baseline_shapes(shape):
     np.testing.assert_allclose([s[0] / norm3[2].item(), s[1] / norm3[2].item(), s[2] / s[3]],
                                [pl.item(), ent.item(), imp.mean().item()], rtol=5e-5, atol=5e-6)
     for k, v in net.views(net.grad).items():
-        # feature-norm affine grads are sums with heavy cancellation over up to 70k rows: 2e-3 of the tensor max
-        # (observed: <= 1e-3 on the FP32 SIMT path, <= 1.3e-3 on the 3xTF32 tensor-core path)
-        _tol_grad(v.cpu().numpy(), ref[k].numpy(), rel=2e-3 if "feature_norm" in k else 5e-4)
+        # Tolerances are relative to the tensor max; these gradients are sums over up to 70k rows that cancel to ~1e-3
+        # of sum|terms|: 5e-4, and 1e-3 for the feature-norm affine grads (which cancel hardest) -- on BOTH GEMM paths
+        # (the 3xTF32 tensor-core path with round-to-nearest splits agrees with the FP32 SIMT path to ~1e-6 here).
+        _tol_grad(v.cpu().numpy(), ref[k].numpy(), rel=1e-3 if "feature_norm" in k else 5e-4)
     # log-prob sweep on the same rows + factor update (identity batch)
     lp_dev = torch.zeros(Rbuf, ad, device=_dev())
     fac = _cu(factor.copy())
