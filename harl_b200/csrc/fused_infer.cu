@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "head_rows.cuh"
 #include "kernels.cuh"
 
 namespace hb {
@@ -36,6 +37,40 @@ struct InferArgs {
   const unsigned long long* offset_base;   // device counter added to offset (nullable)
   InferNet net[HB_MAX_AGENTS + 1];
 };
+
+// Categorical head on a row group (16 lanes per row, 2 rows per warp): the same arithmetic as discrete_rows_kernel's
+// act mode (head_rows.cuh), fed from the activation tile in shared memory.
+template <int CPL>
+__device__ __forceinline__ void fused_discrete_rows(const InferArgs& A, const InferNet& net, const float* __restrict__ cur,
+                                                    int pc, const float* __restrict__ shw, const float* __restrict__ sb,
+                                                    int nrows, long long r0, int od) {
+  constexpr int LPR = 16, MAXJ = 8, NC = CPL / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = lane % LPR, rw = lane / LPR;
+  const unsigned long long off = A.offset + (A.offset_base ? *A.offset_base : 0ull);
+  for (int rr = warp * 2; rr < FI_ROWS; rr += 16) {
+    const int r = rr + rw;
+    const bool ok = r < nrows;
+    const long long row = r0 + r;
+    float f[CPL];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 v = rows::ld4(cur + r * pc + c * 4 * LPR + 4 * s);
+      f[c * 4 + 0] = v.x; f[c * 4 + 1] = v.y; f[c * 4 + 2] = v.z; f[c * 4 + 3] = v.w;
+    }
+    float lg[MAXJ];
+    rows::group_dots<CPL, LPR, MAXJ>(f, shw, s, lg);
+    float av = 1.f;
+    if (ok && net.avail != nullptr && s < od) av = net.avail[row * od + s];
+    const unsigned avm = net.avail != nullptr ? ((__ballot_sync(rows::FULL, av != 0.f) >> (rw * LPR)) & 0xffu) : 0xffu;
+    float lp[MAXJ], pj[MAXJ];
+    rows::categorical<MAXJ>(lg, sb, od, avm, lp, pj);
+    const int pick = rows::categorical_pick<MAXJ>(pj, od, A.deterministic != 0,
+                                                  A.deterministic ? 0.f : rows::row_uniform(row, net.seed, off));
+    const float lpp = rows::select<MAXJ>(lp, pick);
+    if (ok && s == 0) { net.out0[row] = (float)pick; net.out1[row] = lpp; }
+  }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(256) fused_infer_kernel(const __grid_constant__ InferArgs A) {
@@ -215,6 +250,16 @@ __global__ void __launch_bounds__(256) fused_infer_kernel(const __grid_constant_
   const float* hw = net.prep + off;
   const float* hbias = hw + ((od * h + 3) & ~3);
   const float* log_std = hbias + ((od + 3) & ~3);
+  if (net.head == HB_HEAD_DISCRETE && od <= 8 && (h == 128 || h == 64) && h <= NT) {
+    float* shw = wbuf;             // [8][h] zero padded (the weight ring is idle now), then the 8 biases
+    float* sb = wbuf + 8 * h;
+    for (int i = tid; i < 8 * h; i += 256) shw[i] = i < od * h ? hw[i] : 0.f;
+    if (tid < 8) sb[tid] = tid < od ? hbias[tid] : 0.f;
+    __syncthreads();
+    if (h == 128) fused_discrete_rows<8>(A, net, cur, pc, shw, sb, nrows, r0, od);
+    else fused_discrete_rows<4>(A, net, cur, pc, shw, sb, nrows, r0, od);
+    return;
+  }
   for (int r = warp; r < nrows; r += 8) {
     const long long row = r0 + r;
     const float* f = cur + r * pc;

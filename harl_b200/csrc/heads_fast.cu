@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "head_rows.cuh"
 #include "kernels.cuh"
 
 namespace hb {
@@ -23,7 +24,7 @@ namespace {
 // threads per CTA: the gradient kernels hold ~240 registers per thread (per-lane head-weight gradient
 // accumulators), so a 128-thread CTA lets two of them share an SM and the 296 split-buffer slots stay one wave
 constexpr int RT_EVAL = 256, RT_GRAD = 128;
-constexpr unsigned FULL = 0xffffffffu;
+using namespace rows;
 
 template <int ACT>
 __device__ __forceinline__ float actf(int rt, float z) {
@@ -36,8 +37,6 @@ __device__ __forceinline__ float actb(int rt, float z) {
   return act_bwd_rt(rt, z);
 }
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // d(min(s1,s2))/d(ratio) with torch.min / clamp tie semantics (happo.py:71-75)
 __device__ __forceinline__ float dmin_dr(float ratio, float adv, float clip, int use_clip, float* m_out) {
@@ -182,12 +181,12 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
   const float* sc_ptr = nullptr;
   int sc_mul = 1, sc_off = 0, sc_slot = s;
   bool sc_by_r = false;
-  if (s == SC_ACT) sc_ptr = a.actions;
+  if (s == SC_ACT) { if (MODE != MODE_ACT) sc_ptr = a.actions; }
   else if (s == SC_W) { if (GRAD && a.use_active) sc_ptr = a.active; }
-  else if (s == SC_FAC) sc_ptr = GRAD ? a.factor : a.factor_inout;
+  else if (s == SC_FAC) { if (MODE != MODE_ACT) sc_ptr = GRAD ? a.factor : a.factor_inout; }
   else if (s == SC_ADV) { if (GRAD) sc_ptr = a.adv; }
   else if (s == SC_OLD) { if (GRAD) sc_ptr = a.old_logp; }
-  else if (s == SC_REF) { if (!GRAD && a.factor_inout) sc_ptr = a.logp_ref; }
+  else if (s == SC_REF) { if (MODE == MODE_EVAL && a.factor_inout) sc_ptr = a.logp_ref; }
   else if (s == SC_MU || s == SC_RS) { if (has_ln) { sc_ptr = a.ln_stats + (s - SC_MU); sc_by_r = true; sc_mul = 2; } }
   else if (s >= SC_AVAIL && s - SC_AVAIL < na && a.avail != nullptr) { sc_ptr = a.avail; sc_mul = na; sc_off = s - SC_AVAIL; }
 
@@ -237,55 +236,27 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
       float4 v = ok ? ld4(row + c * 4 * LPR + 4 * s) : make_float4(0.f, 0.f, 0.f, 0.f);
       f[c * 4 + 0] = v.x; f[c * 4 + 1] = v.y; f[c * 4 + 2] = v.z; f[c * 4 + 3] = v.w;
     }
-    // ---- logits: every lane of the group ends up with all of them
+    // ---- logits: every lane of the group ends up with all of them (head_rows.cuh)
     float lg[MAXJ];
-#pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      float p = 0.f;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const float4 w4 = ld4(shw + j * H + c * 4 * LPR + 4 * s);
-        p = fmaf(f[c * 4 + 0], w4.x, p); p = fmaf(f[c * 4 + 1], w4.y, p);
-        p = fmaf(f[c * 4 + 2], w4.z, p); p = fmaf(f[c * 4 + 3], w4.w, p);
-      }
-      lg[j] = p;
-    }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-#pragma unroll
-      for (int j = 0; j < MAXJ; ++j) lg[j] += __shfl_xor_sync(FULL, lg[j], o);
-    }
+    group_dots<CPL, LPR, MAXJ>(f, shw, s, lg);
     unsigned avm = 0xffu;
     if (a.avail != nullptr && ok) {
       avm = 0u;
 #pragma unroll
       for (int j = 0; j < MAXJ; ++j) if (j < na && sc[SC_AVAIL + j] != 0.f) avm |= 1u << j;
     }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      lg[j] = j < na ? (((avm >> j) & 1u) ? lg[j] + sb[j] : -1e10f) : -INFINITY;
-      mx = fmaxf(mx, lg[j]);
-    }
-    float ex[MAXJ];
-    float se = 0.f;
-#pragma unroll
-    for (int j = 0; j < MAXJ; ++j) { ex[j] = expf(lg[j] - mx); se += ex[j]; }
-    const float lse = mx + logf(se);
-    const float inv_se = 1.f / se;
     float lp[MAXJ], pj[MAXJ];
-    float ent = 0.f;
-#pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      lp[j] = lg[j] - lse;                       // normalised logit (torch Categorical(logits=)); -inf for j >= na
-      pj[j] = ex[j] * inv_se;                    // softmax probability (0 for j >= na and for masked actions)
-      ent = fmaf(-fmaxf(lp[j], -3.4028234663852886e38f), pj[j], ent);
+    const float ent = categorical<MAXJ>(lg, sb, na, avm, lp, pj);
+    if constexpr (MODE == MODE_ACT) {
+      const int pick = categorical_pick<MAXJ>(pj, na, a.deterministic != 0, a.deterministic ? 0.f : row_uniform(r, a.seed, a.offset));
+      const float lpp = select<MAXJ>(lp, pick);
+      if (ok && s == 0) { a.actions_out[r] = (float)pick; a.logp_out[r] = lpp; }
+      __syncwarp();
+      continue;
     }
     const int act = ok ? (int)sc[SC_ACT] : 0;
-    float lpa = 0.f;
-#pragma unroll
-    for (int j = 0; j < MAXJ; ++j) lpa = j == act ? lp[j] : lpa;
-    if constexpr (!GRAD) {
+    const float lpa = select<MAXJ>(lp, act);
+    if constexpr (MODE == MODE_EVAL) {
       if (ok && s == 0) {
         if (a.logp_out) a.logp_out[r] = lpa;
         if (a.factor_inout) {
@@ -293,7 +264,7 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discret
           a.factor_inout[src] = sc[SC_FAC] * expf(lpa - sc[SC_REF]);
         }
       }
-    } else {
+    } else if constexpr (GRAD) {
       // ---- happo.py:66-91
       float w = 1.f, fac = 1.f, adv = 0.f, old = 0.f;
       if (ok) {
@@ -527,7 +498,7 @@ int launch_discrete(const HeadArgs& a, cudaStream_t st) {
   auto kern = discrete_rows_kernel<CPL, LPR, MAXJ, MODE, ACT>;
   const int g = grid_for(a.rows, (RT / 32) * (32 / LPR), MODE == MODE_GRAD && a.part_stride != 0);
   kern<<<g, RT, smem, st>>>(a);
-  HB_LAUNCH_DONE(st, shape_label(MODE == MODE_GRAD ? "policy_head_grad" : "policy_head_eval", a.rows, a.out, a.h));
+  HB_LAUNCH_DONE(st, shape_label(MODE == MODE_GRAD ? "policy_head_grad" : MODE == MODE_EVAL ? "policy_head_eval" : "policy_head_act", a.rows, a.out, a.h));
   return HB_OK;
 }
 
@@ -551,11 +522,14 @@ int launch_discrete_act(const HeadArgs& a, cudaStream_t st) {
 // Returns HB_OK and sets *handled when the shape has a row-group kernel; otherwise leaves *handled = false.
 int launch_policy_head_rows(int head, int mode, const HeadArgs& a, cudaStream_t st, bool* handled) {
   *handled = false;
-  if (head != HB_HEAD_DISCRETE || mode == MODE_ACT || a.out > 8 || a.rows <= 0) return HB_OK;
+  if (head != HB_HEAD_DISCRETE || a.out > 8 || a.rows <= 0) return HB_OK;
   if (a.h != 64 && a.h != 128) return HB_OK;
   *handled = true;
-  if (a.h == 64) return mode == MODE_GRAD ? launch_discrete_act<4, 16, MODE_GRAD>(a, st) : launch_discrete_act<4, 16, MODE_EVAL>(a, st);
-  return mode == MODE_GRAD ? launch_discrete_act<8, 16, MODE_GRAD>(a, st) : launch_discrete_act<8, 16, MODE_EVAL>(a, st);
+  if (a.h == 64)
+    return mode == MODE_GRAD ? launch_discrete_act<4, 16, MODE_GRAD>(a, st)
+           : mode == MODE_EVAL ? launch_discrete_act<4, 16, MODE_EVAL>(a, st) : launch_discrete_act<4, 16, MODE_ACT>(a, st);
+  return mode == MODE_GRAD ? launch_discrete_act<8, 16, MODE_GRAD>(a, st)
+         : mode == MODE_EVAL ? launch_discrete_act<8, 16, MODE_EVAL>(a, st) : launch_discrete_act<8, 16, MODE_ACT>(a, st);
 }
 
 int launch_value_head_rows(int grad, const ValueArgs& a, cudaStream_t st, bool* handled) {
