@@ -115,6 +115,7 @@ def timed_iterations(runner, steps, warmup, torch, dist_on, sample_clocks=False)
     from harl_b200 import _lib as L
 
     l0 = L.lib.hb_kernel_launch_count()
+    g0 = getattr(runner, "graph_replayed_launches", 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
@@ -122,7 +123,8 @@ def timed_iterations(runner, steps, warmup, torch, dist_on, sample_clocks=False)
         runner.run_iteration(ep, 10**9)
     ev1.record()
     torch.cuda.synchronize()
-    launches = L.lib.hb_kernel_launch_count() - l0
+    # library kernels launched directly + those replayed from the captured rollout graph
+    launches = L.lib.hb_kernel_launch_count() - l0 + getattr(runner, "graph_replayed_launches", 0) - g0
     if dist_on:
         torch.distributed.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
@@ -369,7 +371,11 @@ def main():
     a = ap.parse_args()
     # the contract is ONE JSON line on stdout: everything the runner / env print (the reference prints its spaces
     # and progress lines) goes to stderr
-    real_stdout, sys.stdout = sys.stdout, sys.stderr
+    # -- at the file-descriptor level, so that C libraries (NCCL prints its version banner to fd 1) are covered too
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     wl = WORKLOADS[a.workload]

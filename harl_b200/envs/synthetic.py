@@ -239,6 +239,8 @@ class SyntheticBatchedEnv:
         self._t += 1
         self.steps_served += 1
         k = self._t % self.pool
+        if self._simple:
+            return self._step_into_packed(dst, k)
 
         def h2d(dst_t, src):
             dst_t.copy_(src, non_blocking=True)
@@ -283,6 +285,55 @@ class SyntheticBatchedEnv:
             self._avail_h.copy_(av)
             for a in range(A):
                 h2d(dst["avail"][a], self._avail_h[:, a])
+
+    def _step_into_packed(self, dst, k):
+        """Simple dynamics, host-resident: the simulator's outputs of one step sit packed in ONE pinned block
+        (agent-major obs | state | reward | avail), so a step costs one large H2D copy into a device staging block,
+        two small ones (dones / bad-transition flags) and one multi-tensor device copy into the buffer slots --
+        instead of 3A + 4 separate DMA set-ups."""
+        A, N = self.n_agents, self.n_threads
+        if getattr(self, "_pack", None) is None:
+            od = self._obs.shape[-1]
+            st = self._state[0].numel()
+            ad = self._avail.shape[-1] if self._avail is not None else 0
+            P = A * N * od + st + N + A * N * ad
+            pack = torch.empty(self.pool, P).pin_memory()
+            o0, o1, o2 = A * N * od, A * N * od + st, A * N * od + st + N
+            for kk in range(self.pool):
+                pack[kk, :o0] = self._obs[kk].reshape(-1)
+                pack[kk, o0:o1] = self._state[kk].reshape(-1)
+                pack[kk, o1:o2] = self._rew[kk].reshape(-1)
+                if ad:
+                    pack[kk, o2:] = self._avail[kk % self._avail.shape[0]].permute(1, 0, 2).reshape(-1)  # agent-major
+            dev = dst["share_obs"].device
+            self._pack, self._pack_d = pack, torch.empty(P, device=dev)
+            d = self._pack_d
+            self._pack_views = ([d[a * N * od:(a + 1) * N * od].view(N, od) for a in range(A)], d[o0:o1].view(self._state[0].shape),
+                                d[o1:o2].view(N, 1), [d[o2 + a * N * ad:o2 + (a + 1) * N * ad].view(N, ad) for a in range(A)] if ad else None)
+        self._pack_d.copy_(self._pack[k], non_blocking=True)
+        self.h2d_bytes += self._pack_d.numel() * 4
+        self._ep_step_host += 1
+        done = self._ep_step_host >= self.episode_limit
+        if done:
+            self._ep_step_host = 0
+        self._dones_h.fill_(1 if done else 0)
+        self._bad_h.fill_(1 if done else 0)
+        dst["dones"].copy_(self._dones_h, non_blocking=True)
+        dst["bad"].copy_(self._bad_h, non_blocking=True)
+        self.h2d_bytes += 2 * self._dones_h.numel()
+        obs_v, state_v, rew_v, avail_v = self._pack_views
+        dsts, srcs = list(dst["obs"]) + [dst["share_obs"]], list(obs_v) + [state_v]
+        if self.state_type == "EP":
+            dsts.append(dst["rewards"])
+            srcs.append(rew_v)
+        else:
+            dst["rewards"].copy_(rew_v.unsqueeze(1).expand(-1, A, -1))
+        if dst.get("rewards_na") is not None:
+            dst["rewards_na"].copy_(rew_v.expand(-1, A))
+        if avail_v is not None:
+            dsts += list(dst["avail"])
+            srcs += list(avail_v)
+        torch._foreach_copy_(dsts, srcs)
 
     def graph_period(self):
         """Number of steps after which the HOST side of ``step_into`` repeats itself (pool index, and in the simple

@@ -257,6 +257,7 @@ class OnPolicyBaseRunner:
             f["graph"].replay()
             self._draws += T
             self.envs.graph_advance(T)
+            self.graph_replayed_launches = getattr(self, "graph_replayed_launches", 0) + f["graph_kernels"]
         elif use_graph and f.get("eager_runs", 0) >= 1:
             # capture (the first iteration ran eagerly: every lazy initialisation is done)
             self._draw_ctr.fill_(self._draws)
@@ -265,10 +266,12 @@ class OnPolicyBaseRunner:
                 f["collect"][s].offset_base = L.ptr(self._draw_ctr)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = L.lib.hb_kernel_launch_count()
             with torch.cuda.graph(g):
                 self._rollout_steps(f, L.stream_ptr(), bump=False)
                 L.call("hb_counter_add", L.ptr(self._draw_ctr), T, L.stream_ptr())
             f["graph"] = g
+            f["graph_kernels"] = int(L.lib.hb_kernel_launch_count() - n0)  # library kernels per replay (env copies not counted)
             g.replay()
             self._draws += T
         else:
