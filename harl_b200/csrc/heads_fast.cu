@@ -130,7 +130,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ------------------------------------------------------------------ Categorical head: evaluate / gradient
 template <int CPL, int LPR, int MAXJ, int MODE, int ACT>
-__global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL) discrete_rows_kernel(HeadArgs a) {
+__global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL, MODE == MODE_GRAD ? (MAXJ <= 6 ? 3 : 2) : 1) discrete_rows_kernel(HeadArgs a) {
   constexpr int RT = MODE == MODE_GRAD ? RT_GRAD : RT_EVAL, RWARPS = RT / 32;
   constexpr int RPW = 32 / LPR, NC = CPL / 4, H = CPL * LPR;
   constexpr bool GRAD = MODE == MODE_GRAD;
@@ -481,9 +481,9 @@ __global__ void __launch_bounds__(RT_EVAL) value_rows_grad_kernel(ValueArgs a) {
   block_scalars<RWARPS>((double)s_loss, (double)s_rows, 0.0, 0.0, a.scalars, sred);
 }
 
-int grid_for(int64_t rows, int rows_per_cta, bool slots) {
+int grid_for(int64_t rows, int rows_per_cta, bool slots, int slot_cap = 296) {
   int64_t g = ceil_div64(rows, (int64_t)rows_per_cta);
-  int64_t cap = slots ? tc_dw_splits() : 148 * 8;
+  int64_t cap = slots ? (tc_dw_splits() < slot_cap ? tc_dw_splits() : slot_cap) : 148 * 8;   // gradient kernels: 2-3 CTAs per SM (registers)
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
@@ -496,7 +496,7 @@ int launch_discrete(const HeadArgs& a, cudaStream_t st) {
                       (size_t)(RT / 32) * RING_D * (32 / LPR) * ROW_FLOATS * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(discrete_rows_kernel<CPL, LPR, MAXJ, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   auto kern = discrete_rows_kernel<CPL, LPR, MAXJ, MODE, ACT>;
-  const int g = grid_for(a.rows, (RT / 32) * (32 / LPR), MODE == MODE_GRAD && a.part_stride != 0);
+  const int g = grid_for(a.rows, (RT / 32) * (32 / LPR), MODE == MODE_GRAD && a.part_stride != 0, MAXJ <= 6 ? 444 : 296);
   kern<<<g, RT, smem, st>>>(a);
   HB_LAUNCH_DONE(st, shape_label(MODE == MODE_GRAD ? "policy_head_grad" : MODE == MODE_EVAL ? "policy_head_eval" : "policy_head_act", a.rows, a.out, a.h));
   return HB_OK;

@@ -18,7 +18,7 @@ int tc_dw_splits();
 // grid of a gradient kernel that owns one split-buffer slot per CTA
 static int slot_grid(int64_t rows) {
   int64_t g = ceil_div64(rows, ROW_WARPS);
-  int64_t cap = tc_dw_splits();
+  int64_t cap = tc_dw_splits() < 296 ? tc_dw_splits() : 296;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 

@@ -365,7 +365,8 @@ int launch_tc_linear_ln_fwd(int passes, int act, const float* X, int ldx, const 
 // =====================================================================================================
 namespace hb {
 
-__host__ __device__ constexpr int tc_dw_splits_c() { return 296; }
+// slots of the split gradient buffer = CTAs of the dW kernel: three per SM (its 64 KB operand stage allows three)
+__host__ __device__ constexpr int tc_dw_splits_c() { return 444; }
 
 // Column sums over the 32 lanes of a warp for 32 per-lane values: lane l ends with sum_lanes v[l].
 // Reduce-scatter butterfly: 31 shuffles instead of 32 full reductions.
@@ -745,7 +746,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_accum_kernel(const float* __rest
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NTK) : "memory");
 }
 
-constexpr int TC_DW_SPLITS = tc_dw_splits_c();  // slots of the split buffer: two CTAs per SM
+constexpr int TC_DW_SPLITS = tc_dw_splits_c();
 
 __global__ void dw_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int splits, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
