@@ -424,7 +424,9 @@ def main():
     if rank == 0 and rows:
         line["roofline"] = roofline_of(rows, load_peaks())
         # the two kernels BASELINE.json's north_star names: the GAE scan and the PPO-update (clip-loss) kernel
-        named = {"gae": gae_microbench(torch, T, runner.critic_buffer.value_preds[0].numel(), load_peaks())}
+        named = {"gae": gae_microbench(torch, T, runner.critic_buffer.value_preds[0].numel(), load_peaks()),
+                 # the same kernel where launch + fill latency and the T-step serial recurrence are amortised
+                 "gae_16x_columns": gae_microbench(torch, T, 16 * runner.critic_buffer.value_preds[0].numel(), load_peaks(), sets=2, reps=3)}
         ppo = [r for r in rows if r[0].startswith("policy_head_grad")]
         if ppo:
             named["ppo_update"] = dict(kernel=ppo[0][0], launches=ppo[0][1], avg_us=1e3 * ppo[0][2] / ppo[0][1], **_rate(ppo[0], load_peaks()))

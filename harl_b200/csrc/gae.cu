@@ -10,6 +10,8 @@
 // four input arrays into shared memory with 16-byte cp.async (all loads in flight at once),
 // all threads form V^ = denorm(v) and delta_t in parallel, CW threads run the serial
 // recurrence out of shared memory, then all threads write returns/advantages coalesced.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hb {
@@ -56,58 +58,100 @@ __global__ void __launch_bounds__(256) gae_tiled_kernel(const float* __restrict_
   const int64_t c0 = (int64_t)blockIdx.x * CW;
   const int tid = threadIdx.x;
   const VNConst vc = vn_load(vn);
-  // ---- stage: (T+1) rows x CW/4 float4 per array (C % 4 == 0 guaranteed by the launcher)
+  // ---- stage: (T+1) rows x CW/4 float4 per array (C % 4 == 0 guaranteed by the launcher), in GAE_CH time chunks
+  // issued LAST CHUNK FIRST, one cp.async group each: the backward recurrence starts on the last chunk while the
+  // earlier ones are still in flight, and each chunk's results stream out while the next one is being consumed.
   constexpr int V4 = CW / 4;
-  for (int f = tid; f < (T + 1) * V4; f += 256) {
-    int t = f / V4, q = (f % V4) * 4;
-    if (c0 + q < C) {
-      int64_t g = (int64_t)t * C + c0 + q;
-      if (t < T) {
-        cp_async16(&s_v[t * CW + q], value_preds + g);
-        cp_async16(&s_w[t * CW + q], rewards + g);
-      } else {
-        cp_async16(&s_v[t * CW + q], use_gae ? next_value + c0 + q : value_preds + g);
-      }
-      cp_async16(&s_m[t * CW + q], masks + g);
-      cp_async16(&s_b[t * CW + q], bad_masks + g);
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  // ---- value_preds[-1] = next_value (GAE branches), denormalise, delta
-  if (use_gae) {
-    for (int f = tid; f < CW; f += 256)
-      if (c0 + f < C) value_preds[(int64_t)T * C + c0 + f] = s_v[T * CW + f];
-  }
-  for (int f = tid; f < (T + 1) * CW; f += 256) s_v[f] = denorm(vc, s_v[f]);
-  __syncthreads();
-  if (use_gae) {
-    for (int f = tid; f < T * CW; f += 256) {
-      float vn1 = s_v[f + CW], m1 = s_m[f + CW];
-      // delta = r + gamma * V^[t+1] * m[t+1] - V^[t]
-      s_w[f] = __fsub_rn(__fadd_rn(s_w[f], __fmul_rn(__fmul_rn(gamma, vn1), m1)), s_v[f]);
-    }
-    __syncthreads();
-    if (tid < CW && c0 + tid < C) {
-      float g = 0.f;
-#pragma unroll 4
-      for (int t = T - 1; t >= 0; --t) {
-        float m1 = s_m[(t + 1) * CW + tid];
-        g = __fadd_rn(s_w[t * CW + tid], __fmul_rn(__fmul_rn(gl, m1), g));
-        if (ptl) g = __fmul_rn(s_b[(t + 1) * CW + tid], g);
-        s_w[t * CW + tid] = g;
+  constexpr int GAE_CH = 4;
+  const int rows_per = (T + GAE_CH - 1) / GAE_CH;
+#pragma unroll
+  for (int k = GAE_CH - 1; k >= 0; --k) {
+    const int t0 = k * rows_per < T ? k * rows_per : T;
+    const int t1 = t0 + rows_per < T ? t0 + rows_per : T;
+    const int te = k == GAE_CH - 1 ? T + 1 : t1;       // the bootstrap row T travels with the last chunk
+    for (int f = tid; f < (te - t0) * V4; f += 256) {
+      const int t = t0 + f / V4, q = (f % V4) * 4;
+      if (c0 + q < C) {
+        const int64_t g = (int64_t)t * C + c0 + q;
+        if (t < T) {
+          cp_async16(&s_v[t * CW + q], value_preds + g);
+          cp_async16(&s_w[t * CW + q], rewards + g);
+        } else {
+          cp_async16(&s_v[t * CW + q], use_gae ? next_value + c0 + q : value_preds + g);
+        }
+        cp_async16(&s_m[t * CW + q], masks + g);
+        cp_async16(&s_b[t * CW + q], bad_masks + g);
       }
     }
-    __syncthreads();
-    for (int f = tid; f < T * CW; f += 256) {
-      int t = f / CW, c = f % CW;
-      if (c0 + c < C) {
-        float r = __fadd_rn(s_w[f], s_v[f]);
-        returns[(int64_t)t * C + c0 + c] = r;
-        if (adv) adv[(int64_t)t * C + c0 + c] = __fsub_rn(r, s_v[f]);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  if (use_gae) {
+    float g = 0.f;   // running GAE of this thread's column (threads < CW)
+#pragma unroll
+    for (int k = GAE_CH - 1; k >= 0; --k) {
+      // chunks k-1 .. 0 may still be in flight
+      if (k == 3) asm volatile("cp.async.wait_group 3;\n" ::: "memory");
+      else if (k == 2) asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+      else if (k == 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      __syncthreads();
+      const int t0 = k * rows_per < T ? k * rows_per : T;
+      const int t1 = t0 + rows_per < T ? t0 + rows_per : T;
+      const int te = k == GAE_CH - 1 ? T + 1 : t1;
+      if (k == GAE_CH - 1) {  // value_preds[-1] = next_value
+        for (int f = tid; f < CW; f += 256)
+          if (c0 + f < C) value_preds[(int64_t)T * C + c0 + f] = s_v[T * CW + f];
+      }
+      for (int f = t0 * CW + tid; f < te * CW; f += 256) s_v[f] = denorm(vc, s_v[f]);
+      __syncthreads();
+      for (int f = t0 * CW + tid; f < t1 * CW; f += 256) {
+        float vn1 = s_v[f + CW], m1 = s_m[f + CW];
+        // delta = r + gamma * V^[t+1] * m[t+1] - V^[t]
+        s_w[f] = __fsub_rn(__fadd_rn(s_w[f], __fmul_rn(__fmul_rn(gamma, vn1), m1)), s_v[f]);
+      }
+      __syncthreads();
+      if (tid < CW && c0 + tid < C) {
+        // the recurrence is the critical path of the CTA: operands of 8 steps are pulled into registers first (their
+        // addresses do not depend on g), so a step costs its three dependent roundings, not a shared-memory round trip
+        for (int tb = t1 - 1; tb >= t0; tb -= 8) {
+          float w[8], am[8], bb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int t = tb - i;
+            w[i] = am[i] = 0.f;
+            bb[i] = 1.f;
+            if (t >= t0) {
+              w[i] = s_w[t * CW + tid];
+              am[i] = __fmul_rn(gl, s_m[(t + 1) * CW + tid]);
+              if (ptl) bb[i] = s_b[(t + 1) * CW + tid];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int t = tb - i;
+            if (t >= t0) {
+              g = __fadd_rn(w[i], __fmul_rn(am[i], g));
+              if (ptl) g = __fmul_rn(bb[i], g);
+              s_w[t * CW + tid] = g;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      for (int f = t0 * CW + tid; f < t1 * CW; f += 256) {
+        int t = f / CW, c = f % CW;
+        if (c0 + c < C) {
+          float r = __fadd_rn(s_w[f], s_v[f]);
+          returns[(int64_t)t * C + c0 + c] = r;
+          if (adv) adv[(int64_t)t * C + c0 + c] = __fsub_rn(r, s_v[f]);
+        }
       }
     }
   } else {
+    cp_async_wait_all();
+    __syncthreads();
+    for (int f = tid; f < (T + 1) * CW; f += 256) s_v[f] = denorm(vc, s_v[f]);
+    __syncthreads();
     // returns[-1] = next_value (raw); ret_t = (ret_{t+1}*gamma*m + r)*bad + (1-bad)*V^_t   (ptl)
     if (tid < CW && c0 + tid < C) {
       float ret = next_value[c0 + tid];
@@ -249,6 +293,8 @@ int hb_gae_returns(const float* rewards, float* value_preds, const float* masks,
     for (int w : {32, 16, 8, 4}) {
       if (per_col * w <= budget && (cw == 0 || ceil_div64(C, cw) < 148)) cw = w;
     }
+    static const int forced = getenv("HB_GAE_CW") ? atoi(getenv("HB_GAE_CW")) : 0;   // tuning knob (4 / 8 / 16 / 32)
+    if ((forced == 4 || forced == 8 || forced == 16 || forced == 32) && per_col * forced <= budget) cw = forced;
   }
 #define HB_GAE_TILED(W)                                                                                            \
   case W: {                                                                                                        \
