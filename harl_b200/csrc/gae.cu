@@ -16,6 +16,11 @@
 
 namespace hb {
 
+// gae_tma.cu
+bool launch_gae_tma(const float* rewards, float* value_preds, const float* masks, const float* bad_masks,
+                    const float* next_value, float* returns, float* advantages, int T, int64_t C, float gamma, float gl,
+                    int ptl, const float* vn, cudaStream_t st, int* rc);
+
 struct VNConst { float mean, std; int on; };
 
 __device__ __forceinline__ VNConst vn_load(const float* __restrict__ vn) {
@@ -295,6 +300,12 @@ int hb_gae_returns(const float* rewards, float* value_preds, const float* masks,
     }
     static const int forced = getenv("HB_GAE_CW") ? atoi(getenv("HB_GAE_CW")) : 0;   // tuning knob (4 / 8 / 16 / 32)
     if ((forced == 4 || forced == 8 || forced == 16 || forced == 32) && per_col * forced <= budget) cw = forced;
+  }
+  if (use_gae && cw != 0) {  // TMA-staged kernel (gae_tma.cu); falls through to the cp.async kernel if it declines
+    int rc = HB_OK;
+    if (hb::launch_gae_tma(rewards, value_preds, masks, bad_masks, next_value, returns, advantages, T, C, gamma, gamma_lambda,
+                       use_proper_time_limits, vn_state, st, &rc))
+      return rc;
   }
 #define HB_GAE_TILED(W)                                                                                            \
   case W: {                                                                                                        \
