@@ -180,7 +180,11 @@ def _algorithmic(label):
         return None, None
     name, M, N, K = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4))
     if GEMM_LABEL.match(name):
-        return "flops", 2.0 * M * N * K  # algorithmic: one fp32-accurate product (3xTF32 issues 3 MMAs for it)
+        # algorithmic FLOPs: one fp32-accurate product (3xTF32 issues 3 MMAs for it); algorithmic bytes: every operand /
+        # result row moved once -- forward reads X[M,K], writes Z and Y [M,N]; dX reads dZ[M,K'] and Z[M,N], writes dZ'[M,N];
+        # dW reads dZ[M,N] and X[M,K] (weights, <= 64 KB, excluded)
+        nbytes = 4.0 * M * (N + K) if "dw_accum" in name else 4.0 * M * (K + 2 * N)
+        return "gemm", (2.0 * M * N * K, nbytes)
     if name.startswith("policy_head_grad"):  # features + pre-LN z + dZ out (K floats each) + stats + 5 row scalars + avail
         return "bytes", M * (12.0 * K + 8 + 20 + 4 * N)
     if name.startswith("value_head_grad"):
@@ -198,9 +202,18 @@ def _rate(row, peaks):
     sec = 1e-3 * ms / cnt
     tf_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
     hbm_peak = peaks.get("hbm_gbs_sustained") or peaks.get("hbm_gbs")
-    if kind == "flops":
-        ach = amount / sec / 1e12
-        return dict(bound="tensor", achieved=ach, peak=tf_peak, unit="TFLOP/s", frac=ach / tf_peak, flops_per_launch=amount)
+    if kind == "gemm":
+        # two roofs; the binding one is the larger time bound.  At 21-32 FLOP/B these layer-wise GEMM kernels sit far
+        # below the tensor/HBM ridge (~210 FLOP/B), so HBM binds; the tensor-side numbers are kept alongside.
+        flops, nbytes = amount
+        tf, gbs = flops / sec / 1e12, nbytes / sec / 1e9
+        t_tensor, t_hbm = flops / (tf_peak * 1e12), nbytes / (hbm_peak * 1e9)
+        side = dict(flops_per_launch=flops, bytes_per_launch=nbytes, flop_per_byte=flops / nbytes,
+                    tensor_tflops=tf, tensor_peak_tflops=tf_peak, frac_of_tensor_peak=tf / tf_peak,
+                    hbm_gbs=gbs, hbm_peak_gbs=hbm_peak, frac_of_hbm_peak=gbs / hbm_peak)
+        if t_hbm >= t_tensor:
+            return dict(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak, **side)
+        return dict(bound="tensor", achieved=tf, peak=tf_peak, unit="TFLOP/s", frac=tf / tf_peak, **side)
     if kind == "bytes":
         ach = amount / sec / 1e9
         return dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, bytes_per_launch=amount)
