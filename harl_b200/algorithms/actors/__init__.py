@@ -1,5 +1,6 @@
-"""Actor registry (reference: harl/algorithms/actors/__init__.py:13-24); on-policy HA algorithms only."""
+"""Actor registry (reference: harl/algorithms/actors/__init__.py:13-24); on-policy algorithms only."""
 from .haa2c import HAA2C
 from .happo import HAPPO
+from .mappo import MAPPO
 
-ALGO_REGISTRY = {"happo": HAPPO, "haa2c": HAA2C}
+ALGO_REGISTRY = {"happo": HAPPO, "haa2c": HAA2C, "mappo": MAPPO}

@@ -1,4 +1,5 @@
-"""Runner registry (reference: harl/runners/__init__.py:7-18); the on-policy HA path only."""
+"""Runner registry (reference: harl/runners/__init__.py:7-18); the on-policy path only."""
 from .on_policy_ha_runner import OnPolicyHARunner
+from .on_policy_ma_runner import OnPolicyMARunner
 
-RUNNER_REGISTRY = {"happo": OnPolicyHARunner, "haa2c": OnPolicyHARunner}
+RUNNER_REGISTRY = {"happo": OnPolicyHARunner, "haa2c": OnPolicyHARunner, "mappo": OnPolicyMARunner}

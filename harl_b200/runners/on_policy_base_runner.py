@@ -213,7 +213,8 @@ class OnPolicyBaseRunner:
                 c.obs[i] = L.ptr(b.obs[s])
                 c.avail[i] = L.ptr(b.available_actions[s]) if b.available_actions is not None else None
                 c.actions[i], c.logp[i] = L.ptr(b.actions[s]), L.ptr(b.action_log_probs[s])
-                c.seed[i] = actor._seed
+                # a shared actor object (share_param) still needs one sampling stream per agent
+                c.seed[i] = (actor._seed + (i * 0x9E3779B97F4A7C15 if self.share_param else 0)) & (2**64 - 1)
             c.critic_desc = C.pointer(self.critic.critic.desc)
             c.critic_prepared = L.ptr(self.critic.critic.prepared)
             c.share_obs, c.critic_rows, c.values = L.ptr(cb.share_obs[s]), cb.value_preds[s].numel(), L.ptr(cb.value_preds[s])

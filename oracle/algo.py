@@ -274,3 +274,57 @@ def ha_train(actors, critic, cfg, heads, abufs, cbuf, vn, state_type, agent_orde
         factor = factor_update(factor, new_lp, old_lp, cfg)
     cinfo, _ = critic_train(critic[0], critic[1], cfg, cbuf, vn, perm_fn)
     return infos, cinfo, factors, factor
+
+
+# ------------------------------------------------------------------ MAPPO (harl/algorithms/actors/mappo.py)
+def mappo_train(p, opt, cfg, head, buf, adv, state_type, perm_fn):
+    """MAPPO.train, mappo.py:95-147: HAPPO.train without the importance-ratio factor (factor == 1)."""
+    T, N = buf["actions"].shape[:2]
+    return happo_train(p, opt, cfg, head, buf, adv, np.ones((T, N, 1), np.float32), state_type, perm_fn)
+
+
+def mappo_share_param_train(p, opt, cfg, head, abufs, adv, state_type, perm_fn):
+    """MAPPO.share_param_train, mappo.py:149-222: one shared actor; every update consumes the CONCATENATION of one
+    minibatch per agent; EP advantages are normalised over the agents' stacked active entries."""
+    A = len(abufs)
+    T, N = abufs[0]["actions"].shape[:2]
+    if state_type == "EP":
+        stack = np.stack([adv.copy() for _ in range(A)])
+        masked = stack.copy()
+        for a in range(A):
+            masked[a][abufs[a]["active_masks"][:-1] == 0.0] = np.nan
+        mean, std = np.nanmean(masked), np.nanstd(masked)
+        advs = list((stack - mean) / (std + 1e-5))
+    else:
+        advs = [adv[:, :, a] for a in range(A)]
+    ones = np.ones((T, N, 1), np.float32)
+    info = dict(policy_loss=0.0, dist_entropy=0.0, actor_grad_norm=0.0, ratio=0.0)
+    for _ in range(cfg["ppo_epoch"]):
+        gens = [actor_minibatches(abufs[a], advs[a].astype(np.float32), ones, cfg, perm_fn) for a in range(A)]
+        for _ in range(cfg["actor_num_mini_batch"]):
+            parts = [next(g) for g in gens]
+            batch = {k: torch.cat([b[k] for b in parts], dim=0) for k in parts[0]}
+            u = happo_update(p, opt, cfg, head, batch)
+            for k in info:
+                info[k] += u[k]
+    n = cfg["ppo_epoch"] * cfg["actor_num_mini_batch"]
+    return {k: v / n for k, v in info.items()}
+
+
+def ma_train(actors, critic, cfg, heads, abufs, cbuf, vn, state_type, share_param, perm_fn):
+    """OnPolicyMARunner.train, on_policy_ma_runner.py:10-60."""
+    adv = ob.advantages(cbuf["returns"], cbuf["value_preds"], vn)
+    if state_type == "FP":
+        act = np.stack([b["active_masks"] for b in abufs], axis=2)
+        adv, _, _ = ob.normalize_advantages(adv, act[:-1])
+    infos = {}
+    if share_param:
+        info = mappo_share_param_train(actors[0][0], actors[0][1], cfg, heads[0], abufs, adv.copy(), state_type, perm_fn)
+        infos = {a: info for a in range(len(abufs))}
+    else:
+        for a in range(len(abufs)):
+            p, opt = actors[a]
+            adv_a = adv.copy() if state_type == "EP" else adv[:, :, a].copy()
+            infos[a], _ = mappo_train(p, opt, cfg, heads[a], abufs[a], adv_a, state_type, perm_fn)
+    cinfo, _ = critic_train(critic[0], critic[1], cfg, cbuf, vn, perm_fn)
+    return infos, cinfo

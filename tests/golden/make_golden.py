@@ -343,6 +343,71 @@ def case_ha_train():
         save(f"ha_train_{tag}", **out)
 
 
+def case_ma_train():
+    """Full OnPolicyMARunner.train() (MAPPO, with and without parameter sharing) through the unmodified reference."""
+    from harl.algorithms.actors.mappo import MAPPO
+    from harl.runners.on_policy_ma_runner import OnPolicyMARunner
+
+    for tag, over, act_space, st, A, share in (
+        ("disc_EP", {}, Discrete(5), "EP", 3, False),
+        ("disc_EP_share", {}, Discrete(5), "EP", 3, True),
+        ("box_FP_share_mb2", dict(hidden_sizes=[32, 32, 32], actor_num_mini_batch=2, critic_num_mini_batch=2), Box(2), "FP", 2, True),
+    ):
+        torch.manual_seed(17)
+        g = torch.Generator().manual_seed(18)
+        rng = np.random.default_rng(19)
+        args = base_args(**over)
+        od, sd = 6, 9
+        ab, cb, _ = fill_buffers(rng, args, A, od, sd, act_space, st)
+        for b in ab:
+            b.factor = None
+        if share:
+            first = MAPPO(args, Box(od), act_space)
+            actors = [first] * A
+        else:
+            actors = [MAPPO(args, Box(od), act_space) for _ in range(A)]
+        critic = VCritic(args, Box(sd))
+        for a in (actors[:1] if share else actors):
+            perturb(a.actor, g)
+        perturb(critic.critic, g)
+        vn = ValueNorm(1)
+        vn.update(rng.standard_normal((64, 1)).astype(np.float32) * 2 + 0.5)
+        nv = rng.standard_normal(cb.value_preds[-1].shape).astype(np.float32)
+        cb.compute_returns(nv, vn)
+        out = {}
+        for a in range(A):
+            out.update(abuf_np(ab[a], f"a{a}."))
+            out.update(sd_np(actors[a].actor, f"actor{a}/"))
+        out.update(cbuf_np(cb))
+        out.update(sd_np(critic.critic, "critic/"))
+        out["vn_in"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+        fake = SimpleNamespace(algo_args={"train": args}, value_normalizer=vn, critic_buffer=cb, actor_buffer=ab,
+                               actor=actors, critic=critic, state_type=st, num_agents=A, share_param=share)
+        for x in actors:
+            x.prep_training()
+        critic.prep_training()
+        with PermRecorder() as pr:
+            ainfos, cinfo = OnPolicyMARunner.train(fake)
+        # the runner draws one randperm(num_agents) that only orders the info list: drop it from the replay log
+        perms = [q for q in pr.log if not (share and len(q) == A)]
+        out["n_perms"] = len(perms)
+        for i, q in enumerate(perms):
+            out[f"perm{i}"] = q
+        for a in range(A):
+            out.update(sd_np(actors[a].actor, f"out.actor{a}/"))
+            out[f"out.info{a}"] = np.array([float(ainfos[a][k]) for k in
+                                            ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio")], np.float64)
+        out.update(sd_np(critic.critic, "out.critic/"))
+        out["out.cinfo"] = np.array([float(cinfo["value_loss"]), float(cinfo["critic_grad_norm"])], np.float64)
+        out["out.vn"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+        out["share"] = np.array([int(share)])
+        out["cfg_keys"] = np.array(sorted(over.keys()))
+        out["cfg_vals"] = np.array([repr(over[k]) for k in sorted(over.keys())])
+        out["meta"] = np.array([tag, act_space.__class__.__name__, st, str(A), str(od), str(sd),
+                                str(act_space.n if hasattr(act_space, "n") else act_space.shape[0])])
+        save(f"ma_train_{tag}", **out)
+
+
 def case_single_update():
     """One HAPPO.update and one VCritic.update: raw gradients before clipping."""
     for tag, over, act_space in (("disc", {}, Discrete(5)), ("box", dict(hidden_sizes=[32, 32, 32]), Box(3))):
@@ -401,3 +466,4 @@ if __name__ == "__main__":
     case_policy()
     case_single_update()
     case_ha_train()
+    case_ma_train()

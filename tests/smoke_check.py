@@ -72,6 +72,11 @@ def oracle_iteration(runner, snap, agent_order):
     o_actors = [oracle_net(st, cfg["lr"]) for st in actors]
     o_critic = oracle_net(critic, cfg["critic_lr"])
     ident = lambda m: np.arange(m)
+    if runner.__class__.__name__ == "OnPolicyMARunner":
+        if runner.share_param:   # one shared network: every list entry is the same (params, Adam) pair
+            o_actors = [o_actors[0]] * len(o_actors)
+        infos, cinfo = oa.ma_train(o_actors, o_critic, cfg, heads, abufs, cbuf, vn, runner.state_type, runner.share_param, ident)
+        return infos, cinfo, None, o_actors, o_critic, vn
     infos, cinfo, factors, _ = oa.ha_train(o_actors, o_critic, cfg, heads, abufs, cbuf, vn, runner.state_type,
                                            agent_order, ident)
     return infos, cinfo, factors, o_actors, o_critic, vn
@@ -132,7 +137,8 @@ def check_iteration(runner, tol_w=3e-5, tol_info=2e-4):
             errs.append(f"{msg}: " + " | ".join(l.strip() for l in lines[3:6]))
 
     for a in range(runner.num_agents):
-        cmp(runner.actor_buffer[a].factor.cpu().numpy(), o_factors[a], f"factor[{a}]", rtol=3e-4, atol=3e-5)
+        if o_factors is not None:
+            cmp(runner.actor_buffer[a].factor.cpu().numpy(), o_factors[a], f"factor[{a}]", rtol=3e-4, atol=3e-5)
         for k in ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio"):
             cmp(infos[a][k], o_infos[a][k], f"{k}[{a}]", rtol=tol_info, atol=tol_info)
         for k, v in runner.actor[a].actor.state_dict().items():

@@ -69,6 +69,22 @@ def test_haa2c_iteration():
     runner.close()
 
 
+@pytest.mark.parametrize("action_type,state_type,share", [("Discrete", "EP", False), ("Discrete", "EP", True), ("Box", "FP", True),
+                                                         ("Discrete", "FP", False)])
+def test_mappo_iteration_vs_oracle(action_type, state_type, share):
+    """OnPolicyMARunner (reference on_policy_ma_runner.py:10-60) incl. MAPPO.share_param_train (mappo.py:149-222)."""
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    args, algo_args, env_args = small_config(algo="mappo", action_type=action_type, state_type=state_type)
+    algo_args["algo"]["share_param"] = share
+    runner = RUNNER_REGISTRY["mappo"](args, algo_args, env_args)
+    runner.warmup()
+    runner.logger.init(2)
+    check_iteration(runner)
+    check_iteration(runner)
+    runner.close()
+
+
 def _load_runner_from_golden(g, cfg, m):
     """A runner shell (no env / dirs) holding the golden buffers and weights."""
     from harl_b200.algorithms.actors.happo import HAPPO

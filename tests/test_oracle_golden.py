@@ -164,3 +164,34 @@ def test_ha_train_iteration(name):
     for k, v in pc.items():
         np.testing.assert_allclose(v.detach().numpy(), g["out.critic/" + k], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose([vn.running_mean, vn.running_mean_sq, vn.debiasing_term], g["out.vn"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", U.names("ma_train_"))
+def test_ma_train_iteration(name):
+    """OnPolicyMARunner.train of the unmodified reference (MAPPO, with and without parameter sharing) vs oracle.ma_train."""
+    g = U.load(name)
+    cfg, m = U.cfg_of(g), U.meta_of(g)
+    A, share = m["A"], bool(int(g["share"][0]))
+    actors, abufs = [], []
+    for a in range(A):
+        if share and a > 0:
+            actors.append(actors[0])
+        else:
+            p = U.params_of(g, f"actor{a}/", grad=True)
+            actors.append((p, oa.Adam(p, cfg["lr"], cfg["opti_eps"], cfg["weight_decay"])))
+        abufs.append(_buf(g, f"a{a}."))
+    pc = U.params_of(g, "critic/", grad=True)
+    critic = (pc, oa.Adam(pc, cfg["critic_lr"], cfg["opti_eps"], cfg["weight_decay"]))
+    vn = ob.ValueNormState()
+    vn.running_mean, vn.running_mean_sq, vn.debiasing_term = (np.float32(x) for x in g["vn_in"])
+    cb = U.sub(g, "c.")
+    infos, cinfo = oa.ma_train(actors, critic, cfg, [m["head"]] * A, abufs, cb, vn, m["state_type"], share, U.perm_replayer(g))
+    for a in range(A):
+        got = [infos[a][k] for k in ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio")]
+        np.testing.assert_allclose(got, g[f"out.info{a}"], rtol=2e-4, atol=2e-5)
+        for k, v in actors[a][0].items():
+            np.testing.assert_allclose(v.detach().numpy(), g[f"out.actor{a}/" + k], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose([cinfo["value_loss"], cinfo["critic_grad_norm"]], g["out.cinfo"], rtol=2e-4)
+    for k, v in pc.items():
+        np.testing.assert_allclose(v.detach().numpy(), g["out.critic/" + k], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose([vn.running_mean, vn.running_mean_sq, vn.debiasing_term], g["out.vn"], rtol=1e-5)
