@@ -66,6 +66,7 @@ def base_args(**over):
         use_huber_loss=True, use_policy_active_masks=True, huber_delta=10.0,
         action_aggregation="prod", share_param=False, fixed_order=True,
         episode_length=8, n_rollout_threads=6, use_valuenorm=True, use_proper_time_limits=True,
+        kl_threshold=0.01, ls_step=10, accept_ratio=0.5, backtrack_coeff=0.8,
     )
     a.update(over)
     return a
@@ -458,8 +459,161 @@ def case_single_update():
         save(f"single_update_{tag}", **out)
 
 
+def _named_flat(actor, flat):
+    """Split a flat vector in ``actor.parameters()`` order into {name: array} (trpo_util.py:28-35 order)."""
+    out, i = {}, 0
+    for n_, p in actor.named_parameters():
+        k = p.numel()
+        out[n_] = flat[i:i + k].detach().numpy().reshape(p.shape).copy()
+        i += k
+    return out
+
+
+def case_hatrpo_parts():
+    """The pieces of one HATRPO.update (hatrpo.py:37-194): surrogate gradient, one Fisher-vector product, the
+    conjugate-gradient step direction, and the whole update incl. the backtracking line search."""
+    from harl.algorithms.actors.hatrpo import HATRPO
+    from harl.utils import trpo_util as tu
+
+    for tag, over, act_space in (
+        ("disc", {}, Discrete(5)),
+        ("box", dict(hidden_sizes=[32, 32, 32], action_aggregation="mean"), Box(3)),
+        ("disc_nomask", dict(use_policy_active_masks=False, activation_func="tanh", kl_threshold=0.001), Discrete(4)),
+    ):
+        torch.manual_seed(31)
+        g = torch.Generator().manual_seed(32)
+        rng = np.random.default_rng(33)
+        args = base_args(episode_length=16, n_rollout_threads=8, **over)
+        od, sd = 6, 9
+        ab, cb, _ = fill_buffers(rng, args, 1, od, sd, act_space, "EP")
+        actor = HATRPO(args, Box(od), act_space)
+        perturb(actor.actor, g)
+        T, N = args["episode_length"], args["n_rollout_threads"]
+        factor = (1 + 0.1 * rng.standard_normal((T, N, 1))).astype(np.float32)
+        adv = rng.standard_normal((T, N, 1)).astype(np.float32)
+        ab[0].update_factor(factor)
+        # old log-probs as the rollout would have stored them: the current policy's own (ratio == 1 at theta_old)
+        fl = lambda a: a.reshape(T * N, *a.shape[2:])
+        with torch.no_grad():
+            lp, _, _ = actor.evaluate_actions(fl(ab[0].obs[:-1]), fl(ab[0].rnn_states[:-1]), fl(ab[0].actions),
+                                              fl(ab[0].masks[:-1]),
+                                              fl(ab[0].available_actions[:-1]) if ab[0].available_actions is not None else None,
+                                              fl(ab[0].active_masks[:-1]))
+        noise = 0.05 * rng.standard_normal(lp.shape).astype(np.float32)
+        ab[0].action_log_probs[:] = (lp.numpy() + noise).reshape(ab[0].action_log_probs.shape)
+        out = dict(abuf_np(ab[0], "a0."), factor=factor, adv=adv)
+        out.update(sd_np(actor.actor, "actor0/"))
+        orig = torch.randperm
+        torch.randperm = lambda n, *a, **k: torch.arange(n)
+        try:
+            sample = next(ab[0].feed_forward_generator_actor(adv, 1))
+        finally:
+            torch.randperm = orig
+        (obs_b, rnn_b, act_b, masks_b, active_b, old_lp_b, adv_b, avail_b, factor_b) = sample
+        tp = dict(dtype=torch.float32)
+        lp, ent, _ = actor.evaluate_actions(obs_b, rnn_b, act_b, masks_b, avail_b, active_b)
+        ratio = getattr(torch, args["action_aggregation"])(torch.exp(lp - torch.from_numpy(old_lp_b)), dim=-1, keepdim=True)
+        inner = torch.sum(ratio * torch.from_numpy(factor_b) * torch.from_numpy(adv_b), dim=-1, keepdim=True)
+        am = torch.from_numpy(active_b)
+        loss = (inner * am).sum() / am.sum() if args["use_policy_active_masks"] else inner.mean()
+        lg = tu.flat_grad(torch.autograd.grad(loss, actor.actor.parameters(), allow_unused=True))
+        out["loss"] = np.array([loss.item()], np.float64)
+        for k, v in _named_flat(actor.actor, lg).items():
+            out["loss_grad/" + k] = v
+        vec = torch.randn(lg.shape, generator=g)
+        fvp = tu.fisher_vector_product(actor.actor, obs_b, rnn_b, act_b, masks_b, avail_b, active_b, vec)
+        for k, v in _named_flat(actor.actor, vec).items():
+            out["vec/" + k] = v
+        for k, v in _named_flat(actor.actor, fvp).items():
+            out["fvp/" + k] = v
+        sdir = tu.conjugate_gradient(actor.actor, obs_b, rnn_b, act_b, masks_b, avail_b, active_b, lg.data, nsteps=10,
+                                     device=torch.device("cpu"))
+        for k, v in _named_flat(actor.actor, sdir).items():
+            out["step_dir/" + k] = v
+        kl, li, ei, de, rt = actor.update(sample)
+        out["update_scalars"] = np.array([float(kl.detach()), float(li), float(np.asarray(ei).reshape(-1)[0]),
+                                          float(de.detach()), float(rt.detach().mean())], np.float64)
+        out.update(sd_np(actor.actor, "out.actor0/"))
+        out["meta"] = np.array([tag, act_space.__class__.__name__, "EP", "1", str(od), str(sd),
+                                str(act_space.n if hasattr(act_space, "n") else act_space.shape[0])])
+        over2 = dict(over, episode_length=16, n_rollout_threads=8)
+        out["cfg_keys"] = np.array(sorted(over2.keys()))
+        out["cfg_vals"] = np.array([repr(over2[k]) for k in sorted(over2.keys())])
+        save(f"hatrpo_parts_{tag}", **out)
+
+
+def case_hatrpo_train():
+    """Full OnPolicyHARunner.train() with HATRPO actors (hatrpo.py:196-247) through the unmodified reference."""
+    from harl.algorithms.actors.hatrpo import HATRPO
+
+    for tag, over, act_space, st, A in (
+        ("mlp_disc_EP", {}, Discrete(5), "EP", 3),
+        ("mlp_box_FP", dict(hidden_sizes=[32, 32, 32]), Box(2), "FP", 2),
+    ):
+        torch.manual_seed(41)
+        g = torch.Generator().manual_seed(42)
+        rng = np.random.default_rng(43)
+        args = base_args(episode_length=16, n_rollout_threads=8, **over)
+        od, sd = 6, 9
+        ab, cb, _ = fill_buffers(rng, args, A, od, sd, act_space, st)
+        actors = [HATRPO(args, Box(od), act_space) for _ in range(A)]
+        critic = VCritic(args, Box(sd))
+        for a in actors:
+            perturb(a.actor, g)
+        perturb(critic.critic, g)
+        # stored log-probs near the current policies' own, as after a rollout
+        T, N = args["episode_length"], args["n_rollout_threads"]
+        fl = lambda x: x.reshape(T * N, *x.shape[2:])
+        for a in range(A):
+            with torch.no_grad():
+                lp, _, _ = actors[a].evaluate_actions(
+                    fl(ab[a].obs[:-1]), fl(ab[a].rnn_states[:-1]), fl(ab[a].actions), fl(ab[a].masks[:-1]),
+                    fl(ab[a].available_actions[:-1]) if ab[a].available_actions is not None else None,
+                    fl(ab[a].active_masks[:-1]))
+            ab[a].action_log_probs[:] = (lp.numpy() + 0.05 * rng.standard_normal(lp.shape).astype(np.float32)).reshape(
+                ab[a].action_log_probs.shape)
+        vn = ValueNorm(1)
+        vn.update(rng.standard_normal((64, 1)).astype(np.float32) * 2 + 0.5)
+        nv = rng.standard_normal(cb.value_preds[-1].shape).astype(np.float32)
+        cb.compute_returns(nv, vn)
+        out = {}
+        for a in range(A):
+            out.update(abuf_np(ab[a], f"a{a}."))
+            out.update(sd_np(actors[a].actor, f"actor{a}/"))
+        out.update(cbuf_np(cb))
+        out.update(sd_np(critic.critic, "critic/"))
+        out["vn_in"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+        fake = SimpleNamespace(algo_args={"train": args}, value_normalizer=vn, critic_buffer=cb, actor_buffer=ab,
+                               actor=actors, critic=critic, state_type=st, num_agents=A, fixed_order=True,
+                               action_aggregation=args["action_aggregation"])
+        with PermRecorder() as pr:
+            ainfos, cinfo = OnPolicyHARunner.train(fake)
+        out["n_perms"] = len(pr.log)
+        for i, p in enumerate(pr.log):
+            out[f"perm{i}"] = p
+        for a in range(A):
+            out.update(sd_np(actors[a].actor, f"out.actor{a}/"))
+            out[f"out.factor{a}"] = ab[a].factor
+            tof = lambda v: float(v.detach().reshape(-1)[0]) if torch.is_tensor(v) else float(np.asarray(v).reshape(-1)[0])
+            out[f"out.info{a}"] = np.array([tof(ainfos[a][k]) for k in
+                                            ("kl", "dist_entropy", "loss_improve", "expected_improve", "ratio")], np.float64)
+        out.update(sd_np(critic.critic, "out.critic/"))
+        out["out.cinfo"] = np.array([float(cinfo["value_loss"]), float(cinfo["critic_grad_norm"])], np.float64)
+        out["out.vn"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+        over2 = dict(over, episode_length=16, n_rollout_threads=8)
+        out["cfg_keys"] = np.array(sorted(over2.keys()))
+        out["cfg_vals"] = np.array([repr(over2[k]) for k in sorted(over2.keys())])
+        out["meta"] = np.array([tag, act_space.__class__.__name__, st, str(A), str(od), str(sd),
+                                str(act_space.n if hasattr(act_space, "n") else act_space.shape[0])])
+        save(f"hatrpo_train_{tag}", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "hatrpo":  # regenerate only the HATRPO vectors
+        case_hatrpo_parts()
+        case_hatrpo_train()
+        sys.exit(0)
     case_insert()
     case_gae()
     case_valuenorm()
@@ -467,3 +621,5 @@ if __name__ == "__main__":
     case_single_update()
     case_ha_train()
     case_ma_train()
+    case_hatrpo_parts()
+    case_hatrpo_train()

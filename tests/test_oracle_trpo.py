@@ -1,0 +1,97 @@
+"""CPU: the HATRPO oracle (oracle/trpo.py) against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py: case_hatrpo_parts / case_hatrpo_train).
+
+Tolerances: surrogate gradient 1e-4 rel; Fisher-vector product 2e-4 of the vector's max (double backward in fp32);
+conjugate-gradient direction 2e-3 of its max (10 fp32 CG steps amplify rounding); parameters after the accepted
+line-search step 2e-4 abs; scalars 2e-3 rel.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import algo as oa
+from oracle import buffers as ob
+from oracle import trpo as ot
+from tests import util as U
+
+
+def _buf(g, prefix):
+    b = U.sub(g, prefix)
+    b.setdefault("available_actions", None)
+    return b
+
+
+def _close_rel_max(got, ref, frac, msg=""):
+    scale = max(float(np.abs(ref).max()), 1e-12)
+    err = float(np.abs(got - ref).max())
+    assert err <= frac * scale, f"{msg}: max err {err:.3e} > {frac} * {scale:.3e}"
+
+
+def _parts(name):
+    g = U.load(name)
+    cfg, m = U.cfg_of(g), U.meta_of(g)
+    p = U.params_of(g, "actor0/", grad=True)
+    ident = lambda n: np.arange(n)
+    batch = next(oa.actor_minibatches(_buf(g, "a0."), g["adv"], g["factor"], cfg, ident))
+    return g, cfg, m, p, batch
+
+
+@pytest.mark.parametrize("name", U.names("hatrpo_parts_"))
+def test_surrogate_gradient_and_fvp(name):
+    g, cfg, m, p, batch = _parts(name)
+    loss, _, _ = ot.surrogate(p, cfg, m["head"], batch)
+    np.testing.assert_allclose(float(loss), g["loss"][0], rtol=2e-5, atol=1e-7)
+    names = list(p.keys())
+    gs = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
+    for k, gi in zip(names, gs):
+        _close_rel_max(gi.numpy(), g["loss_grad/" + k], 1e-4, "grad " + k)
+    vec = {k: torch.from_numpy(g["vec/" + k]) for k in names}
+    fvp = ot.fisher_vector_product(p, cfg, m["head"], batch, vec)
+    allref = np.concatenate([g["fvp/" + k].ravel() for k in names])
+    scale = np.abs(allref).max()
+    for k in names:
+        assert np.abs(fvp[k].numpy() - g["fvp/" + k]).max() <= 2e-4 * scale, k
+    # the Gauss-Newton form the CUDA kernels use is the same operator
+    gn = ot.fisher_vector_product_gn(p, cfg, m["head"], batch, vec)
+    for k in names:
+        assert np.abs(gn[k].numpy() - g["fvp/" + k]).max() <= 2e-4 * scale, "gauss-newton " + k
+
+
+@pytest.mark.parametrize("name", U.names("hatrpo_parts_"))
+def test_conjugate_gradient_and_update(name):
+    g, cfg, m, p, batch = _parts(name)
+    names = list(p.keys())
+    b = {k: torch.from_numpy(g["loss_grad/" + k]) for k in names}
+    sd = ot.conjugate_gradient(p, cfg, m["head"], batch, b)
+    allref = np.concatenate([g["step_dir/" + k].ravel() for k in names])
+    scale = np.abs(allref).max()
+    for k in names:
+        assert np.abs(sd[k].numpy() - g["step_dir/" + k]).max() <= 2e-3 * scale, k
+    u = ot.hatrpo_update(p, cfg, m["head"], batch)
+    got = [u[k] for k in ("kl", "loss_improve", "expected_improve", "dist_entropy", "ratio")]
+    np.testing.assert_allclose(got, g["update_scalars"], rtol=2e-3, atol=2e-6)
+    for k in names:
+        np.testing.assert_allclose(p[k].detach().numpy(), g["out.actor0/" + k], rtol=0, atol=2e-4, err_msg=k)
+
+
+@pytest.mark.parametrize("name", U.names("hatrpo_train_"))
+def test_ha_train_hatrpo(name):
+    """OnPolicyHARunner.train with HATRPO actors: weights, factors, infos."""
+    g = U.load(name)
+    cfg, m = U.cfg_of(g), U.meta_of(g)
+    A = m["A"]
+    actors = [U.params_of(g, f"actor{a}/", grad=True) for a in range(A)]
+    abufs = [_buf(g, f"a{a}.") for a in range(A)]
+    pc = U.params_of(g, "critic/", grad=True)
+    critic = (pc, oa.Adam(pc, cfg["critic_lr"], cfg["opti_eps"], cfg["weight_decay"]))
+    vn = ob.ValueNormState()
+    vn.running_mean, vn.running_mean_sq, vn.debiasing_term = (np.float32(x) for x in g["vn_in"])
+    infos, cinfo, factors, _ = ot.ha_train_hatrpo(actors, critic, cfg, [m["head"]] * A, abufs, U.sub(g, "c."), vn,
+                                                  m["state_type"], list(range(A)), U.perm_replayer(g))
+    for a in range(A):
+        np.testing.assert_allclose(factors[a], g[f"out.factor{a}"], rtol=2e-3, atol=1e-4)
+        got = [infos[a][k] for k in ("kl", "dist_entropy", "loss_improve", "expected_improve", "ratio")]
+        np.testing.assert_allclose(got, g[f"out.info{a}"], rtol=3e-3, atol=1e-5)
+        for k, v in actors[a].items():
+            np.testing.assert_allclose(v.detach().numpy(), g[f"out.actor{a}/" + k], rtol=0, atol=3e-4, err_msg=k)
+    np.testing.assert_allclose([cinfo["value_loss"], cinfo["critic_grad_norm"]], g["out.cinfo"], rtol=2e-4)

@@ -22,6 +22,7 @@ def base_args(**over):
         use_huber_loss=True, use_policy_active_masks=True, huber_delta=10.0,
         action_aggregation="prod", share_param=False, fixed_order=True,
         episode_length=8, n_rollout_threads=6, use_valuenorm=True, use_proper_time_limits=True,
+        kl_threshold=0.01, ls_step=10, accept_ratio=0.5, backtrack_coeff=0.8,
     )
     a.update(over)
     return a
