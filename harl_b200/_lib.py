@@ -119,6 +119,17 @@ SIGNATURES = {
     "hb_value_grad": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(CriticBatch), C.POINTER(ValueHyper), P,
                                 C.c_double, P, P, P, C.c_size_t, P]),
     "hb_clip_adam_step": (C.c_int, [C.POINTER(NetDesc), P, P, P, P, P, C.POINTER(AdamHyper), P, P]),
+    "hb_trpo_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64]),
+    "hb_trpo_old_dist": (C.c_int, [C.POINTER(NetDesc), P, C.POINTER(ActorBatch), P, P, C.c_size_t, P]),
+    "hb_trpo_fvp": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(ActorBatch), P, P, C.c_double, P, P, C.c_size_t, P]),
+    "hb_trpo_fvp_finish": (C.c_int, [C.POINTER(NetDesc), P, P, P, C.c_float, P]),
+    "hb_trpo_eval": (C.c_int, [C.POINTER(NetDesc), P, C.POINTER(ActorBatch), C.POINTER(PPOHyper), P, P, P, P,
+                               C.c_size_t, P]),
+    "hb_trpo_cg_init": (C.c_int, [P, P, P, P, P, C.c_int, P]),
+    "hb_trpo_cg_step": (C.c_int, [P, P, P, P, P, C.c_int, C.c_float, P]),
+    "hb_trpo_full_step": (C.c_int, [P, P, P, C.c_float, P, P, C.c_int, P]),
+    "hb_trpo_apply_step": (C.c_int, [P, P, P, C.c_float, C.c_int, P]),
+    "hb_vec_scale": (C.c_int, [P, C.c_float, C.c_int, P]),
 }
 
 if not os.path.exists(LIB_PATH):
@@ -136,7 +147,7 @@ HB_ERR_UNSUPPORTED = -2
 GEMM_IMPLS = {"fp32": 0, "3xtf32": 1, "tf32": 2}
 if os.environ.get("HB_GEMM_IMPL"):
     lib.hb_set_gemm_impl(GEMM_IMPLS[os.environ["HB_GEMM_IMPL"]])
-_NO_CHECK = {"hb_version", "hb_last_error", "hb_workspace_bytes", "hb_kernel_launch_count", "hb_profile_end", "hb_get_gemm_impl"}
+_NO_CHECK = {"hb_version", "hb_last_error", "hb_workspace_bytes", "hb_trpo_workspace_bytes", "hb_kernel_launch_count", "hb_profile_end", "hb_get_gemm_impl"}
 
 # launches of library entry points since import (bench.py's gpu_launches bookkeeping)
 call_count = 0

@@ -1,0 +1,162 @@
+"""HATRPO actor (reference: harl/algorithms/actors/hatrpo.py:18-247, harl/utils/trpo_util.py).
+
+One ``update`` = surrogate gradient -> 10 conjugate-gradient steps on (F + 0.1 I) x = g -> step scaling by the KL
+threshold -> backtracking line search on the surrogate and KL(old || new).  Everything that touches the batch runs
+in CUDA over the buffer rows in place (no minibatch is materialised):
+
+* gradient: the fused HAPPO kernel with clipping and the entropy bonus off (it differentiates -loss);
+* Fisher-vector product: Gauss-Newton form J^T H J v -- a tangent pass through the trunk (trpo.cu), the
+  distribution-space Hessian, and the ordinary backward kernels -- instead of the reference's double backward
+  (identical operator: at new == old the KL gradient w.r.t. the distribution parameters vanishes);
+* the old distribution is evaluated once and kept ([rows, out_dim]) rather than re-instantiating an old actor;
+* CG vector algebra stays on the device (no host sync inside the 10 iterations); the line search reads back four
+  doubles per trial, as the reference does (`.cpu().numpy()`, hatrpo.py:163).
+
+With the rollout sharded over GPUs the gradient, every Fisher-vector product and the line-search sums are
+sum-allreduced, so all ranks take the identical step.
+"""
+import torch
+
+from ... import _lib as L
+from ... import dist
+from ...nets import DeviceNet
+from .on_policy_base import OnPolicyBase, to_device
+
+
+class HATRPO(OnPolicyBase):
+    def __init__(self, args, obs_space, act_space, device=torch.device("cpu")):
+        assert act_space.__class__.__name__ != "MultiDiscrete", \
+            "only continuous and discrete action space is supported by HATRPO."
+        super().__init__(args, obs_space, act_space, device)
+        self.kl_threshold = args["kl_threshold"]
+        self.ls_step = args["ls_step"]
+        self.accept_ratio = args["accept_ratio"]
+        self.backtrack_coeff = args["backtrack_coeff"]
+        self.last_update = {}
+
+    def _hyper(self):
+        return L.PPOHyper(0.0, 0.0, int(bool(self.use_policy_active_masks)), int(self.action_aggregation == "prod"), 0)
+
+    def _update_on_batch(self, batch, norm, global_rows):
+        """hatrpo.py:37-194 on a device batch.  ``norm``: global sum(active) (or global row count)."""
+        net, d = self.actor, self.device
+        n = net.total
+        st = L.stream_ptr()
+        f32 = dict(dtype=torch.float32, device=d)
+        f64 = dict(dtype=torch.float64, device=d)
+        hyper = self._hyper()
+        # --- surrogate gradient at theta_old (hatrpo.py:67-98)
+        norm3 = torch.zeros(3, **f64)
+        norm3[2] = norm
+        scal = torch.zeros(4, **f64)
+        net.actor_grad(batch, hyper, norm3, scal)
+        dist.all_reduce_sum_(net.grad)
+        dist.all_reduce_sum_(scal)
+        g = net.grad.clone()
+        L.call("hb_vec_scale", L.ptr(g), -1.0, n, st)  # the kernel differentiates -loss
+        # --- old distribution, once (trpo_util.py:79-82)
+        old_dist = torch.empty(batch.rows, net.out_dim, **f32)
+        net.trpo_old_dist(batch, old_dist)
+        inv_rows = 1.0 / float(global_rows)
+
+        def fvp(vec, out):
+            net.trpo_fvp(batch, old_dist, vec, inv_rows, out)
+            dist.all_reduce_sum_(out)
+            net.trpo_fvp_finish(vec, out, 0.1)
+
+        # --- conjugate gradient, 10 steps (trpo_util.py:100-133)
+        x, r, p, avp = (torch.empty(n, **f32) for _ in range(4))
+        cg_state = torch.zeros(2, **f32)
+        L.call("hb_trpo_cg_init", L.ptr(g), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(cg_state), n, st)
+        for _ in range(10):
+            fvp(p, avp)
+            L.call("hb_trpo_cg_step", L.ptr(p), L.ptr(avp), L.ptr(x), L.ptr(r), L.ptr(cg_state), n, 1e-10, st)
+        # --- step scaling (hatrpo.py:112-133)
+        fvp(x, avp)
+        full = torch.empty(n, **f32)
+        out3 = torch.zeros(3, **f64)
+        L.call("hb_trpo_full_step", L.ptr(x), L.ptr(avp), L.ptr(g), float(self.kl_threshold), L.ptr(full), L.ptr(out3), n, st)
+        params0 = net.params.clone()
+        host = torch.cat([scal, out3]).cpu().numpy()  # one sync: loss sums + (shs, step_size, expected)
+        loss = -host[0] / norm
+        expected = float(host[6])
+        # --- backtracking line search (hatrpo.py:135-189)
+        flag, fraction = False, 1.0
+        kl = improve = ent = ratio = 0.0
+        ls = torch.zeros(self.ls_step, 4, **f64)
+        tried = 0
+        for i in range(self.ls_step):
+            L.call("hb_trpo_apply_step", L.ptr(net.params), L.ptr(params0), L.ptr(full), float(fraction), n, st)
+            net.prepare()
+            net.trpo_eval(batch, hyper, old_dist, params0, ls[i])
+            dist.all_reduce_sum_(ls[i])
+            s = ls[i].cpu().numpy()
+            tried = i + 1
+            new_loss = s[0] / norm
+            improve = float(new_loss - loss)
+            kl = float(s[3] / global_rows)
+            ent = float(s[1] / norm)
+            ratio = float(s[2] / global_rows)
+            if kl < self.kl_threshold and improve / expected > self.accept_ratio and improve > 0:
+                flag = True
+                break
+            expected *= self.backtrack_coeff
+            fraction *= self.backtrack_coeff
+        if not flag:
+            net.params.copy_(params0)
+            net.prepare()
+            print("policy update does not impove the surrogate")
+        self.last_update = dict(loss=float(loss), grad=g, step_dir=x, full_step=full, accepted=flag, trials=tried,
+                                fraction=fraction)
+        return kl, improve, expected, ent, ratio
+
+    def update(self, sample):
+        """Reference-compatible update on a materialised minibatch tuple (hatrpo.py:37-194).
+
+        Returns (kl, loss_improve, expected_improve, dist_entropy, ratio_mean) as floats."""
+        (obs, _rnn, actions, _masks, active, old_lp, adv, avail, factor) = sample
+        d = self.device
+        obs, actions, active, old_lp, adv, factor, avail = (to_device(x, d) for x in
+                                                             (obs, actions, active, old_lp, adv, factor, avail))
+        self._rnn_passthrough(_rnn)
+        batch = DeviceNet.actor_batch(obs, actions, old_lp, adv.reshape(-1), factor.reshape(-1), active.reshape(-1), avail)
+        cnt = torch.zeros(2, dtype=torch.float64, device=d)
+        cnt[0] = active.sum().double() if self.use_policy_active_masks else float(obs.shape[0])
+        cnt[1] = float(obs.shape[0])
+        dist.all_reduce_sum_(cnt)
+        c = cnt.cpu().numpy()
+        return self._update_on_batch(batch, float(c[0]), float(c[1]))
+
+    def train(self, actor_buffer, advantages, state_type):
+        """Reference hatrpo.py:196-247: one update on the whole buffer."""
+        info = dict(kl=0.0, dist_entropy=0.0, loss_improve=0.0, expected_improve=0.0, ratio=0.0)
+        d = self.device
+        buf = actor_buffer
+        T, N = buf.actions.shape[:2]
+        rows = T * N
+        adv = to_device(advantages, d).reshape(rows)
+        active = buf.active_masks[:-1].reshape(rows)
+        m3 = torch.zeros(3, dtype=torch.float64, device=d)
+        L.call("hb_masked_moments", L.ptr(adv), L.ptr(active), rows, L.ptr(m3), L.stream_ptr())
+        dist.all_reduce_sum_(m3)
+        n_active = m3[2].item()
+        if n_active == 0:
+            return info
+        if state_type == "EP":
+            adv_n = torch.empty_like(adv)
+            L.call("hb_normalize_by_moments", L.ptr(adv), L.ptr(adv_n), rows, L.ptr(m3), L.stream_ptr())
+            adv = adv_n
+        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
+            raise NotImplementedError("recurrent (GRU) policies are not implemented in this build")
+        fl = lambda a: a.reshape(rows, *a.shape[2:])
+        avail = None if buf.available_actions is None else fl(buf.available_actions[:-1])
+        factor = None if buf.factor is None else buf.factor.reshape(rows)
+        # the reference draws randperm(rows) for its single minibatch; a permutation of the whole buffer only
+        # reorders sums, so the rows are consumed in place
+        batch = DeviceNet.actor_batch(fl(buf.obs[:-1]), fl(buf.actions), fl(buf.action_log_probs), adv, factor, active,
+                                      avail, None, rows)
+        global_rows = float(rows * dist.world_size())
+        norm = n_active if self.use_policy_active_masks else global_rows
+        kl, improve, expected, ent, ratio = self._update_on_batch(batch, norm, global_rows)
+        info.update(kl=kl, dist_entropy=ent, loss_improve=improve, expected_improve=expected, ratio=ratio)
+        return info

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "trpo.cuh"
 
 namespace hb {
 
@@ -379,5 +380,210 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
   }
   if ((rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
   return launch_featnorm_fold(d, params, grad, st);
+}
+
+/* ------------------------------------------------------------------ trust-region (HATRPO) update */
+namespace {
+struct TrpoExtra { float* tprep; float* yd[2]; };
+
+size_t trpo_extra_floats(const hb::PrepLayout& Q, int64_t ch) {
+  return (size_t)hb::round_up(Q.tk[0], 4) + 2 * (size_t)ch * hb::hmax_of(Q);
+}
+}  // namespace
+
+size_t hb_trpo_workspace_bytes(const hb_net_desc* d, int64_t rows) {
+  hb::PrepLayout Q;
+  hb::ParamLayout P;
+  if (hb::make_layouts(d, &P, &Q, nullptr)) return 0;
+  int64_t ch = rows < hb::CHUNK_ROWS ? rows : hb::CHUNK_ROWS;
+  if (ch < 1) ch = 1;
+  return (hb::work_floats(Q, ch, 1, P.total) + trpo_extra_floats(Q, ch)) * sizeof(float);
+}
+
+int hb_trpo_old_dist(const hb_net_desc* d, const float* prepared, const hb_actor_batch* b, float* old_dist, void* ws,
+                     size_t ws_bytes, void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(prepared && b && b->obs && old_dist && b->rows >= 0, "bad argument");
+  PrepLayout Q;
+  int rc = check_net(d, nullptr, &Q, nullptr, 1);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = b->rows;
+  if (rows == 0) return HB_OK;
+  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  Work w;
+  if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
+  for (int64_t c0 = 0; c0 < rows; c0 += ch) {
+    const int64_t n = rows - c0 < ch ? rows - c0 : ch;
+    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    TrpoHeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat = w.Y[Q.n_layers - 1];
+    a.h = Q.n[Q.n_layers - 1]; a.out = d->out_dim;
+    a.hw = prepared + Q.hw; a.hbias = prepared + Q.hbias; a.log_std = prepared + Q.log_std;
+    a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;
+    a.rows = n;
+    a.index = b->index ? b->index + c0 : nullptr;
+    a.avail = b->avail ? b->avail + (b->index ? 0 : c0) * d->out_dim : nullptr;
+    a.old_dist_out = old_dist + c0 * d->out_dim;
+    if ((rc = launch_trpo_head(d->head, TR_OLD, a, st))) return rc;
+  }
+  return HB_OK;
+}
+
+int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared, const hb_actor_batch* b,
+                const float* old_dist, const float* v, double inv_rows, float* out, void* ws, size_t ws_bytes,
+                void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(params && prepared && b && b->obs && old_dist && v && out && b->rows >= 0, "bad argument");
+  ParamLayout P;
+  PrepLayout Q;
+  hb_net_layout L;
+  int rc = check_net(d, &P, &Q, &L, 1);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t ce = cudaMemsetAsync(out, 0, (size_t)L.total * sizeof(float), st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "hb_trpo_fvp(memset)");
+  const int64_t rows = b->rows;
+  if (rows == 0) return HB_OK;
+  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const size_t base = work_floats(Q, ch, 1, L.total);
+  if ((base + trpo_extra_floats(Q, ch)) * sizeof(float) > ws_bytes || ws == nullptr) {
+    set_error("hb_trpo_fvp: workspace too small: need %zu bytes, have %zu", (base + trpo_extra_floats(Q, ch)) * sizeof(float), ws_bytes);
+    return HB_ERR_WORKSPACE;
+  }
+  Work w;
+  if ((rc = carve(Q, ch, 1, ws, base * sizeof(float), &w, L.total))) return rc;
+  TrpoExtra x;
+  x.tprep = (float*)ws + base;
+  x.yd[0] = x.tprep + round_up(Q.tk[0], 4);
+  x.yd[1] = x.yd[0] + (size_t)ch * hmax_of(Q);
+  ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "hb_trpo_fvp(memset split buffer)");
+  if ((rc = launch_tangent_prepare(d, P, Q, params, v, x.tprep, st))) return rc;
+  const int Lh = Q.n_layers;
+  for (int64_t c0 = 0; c0 < rows; c0 += ch) {
+    const int64_t n = rows - c0 < ch ? rows - c0 : ch;
+    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    // tangent pass through the trunk (the normalised observations carry no tangent: their affine is folded into layer 0)
+    const float* xin = w.x0;
+    const float* xd = nullptr;
+    int ldx = Q.kpad[0];
+    for (int l = 0; l < Lh; ++l) {
+      float* yd = x.yd[l & 1];
+      rc = launch_jvp_linear_ln(d->activation, xin, ldx, xd, prepared + Q.wt[l], x.tprep + Q.wt[l], x.tprep + Q.bias[l],
+                                prepared + Q.lnw[l], x.tprep + Q.lnw[l], x.tprep + Q.lnb[l], w.Z[l], w.stats[l], yd, n,
+                                Q.n[l], Q.kpad[l], st);
+      if (rc) return rc;
+      xin = w.Y[l]; xd = yd; ldx = Q.n[l];
+    }
+    TrpoHeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat = w.Y[Lh - 1]; a.featd = xd;
+    a.h = Q.n[Lh - 1]; a.out = d->out_dim;
+    a.hw = prepared + Q.hw; a.hbias = prepared + Q.hbias; a.log_std = prepared + Q.log_std;
+    a.hwd = x.tprep + Q.hw; a.hbd = x.tprep + Q.hbias;
+    a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;
+    a.rows = n;
+    a.index = b->index ? b->index + c0 : nullptr;
+    a.avail = b->avail ? b->avail + (b->index ? 0 : c0) * d->out_dim : nullptr;
+    a.old_dist = old_dist + c0 * d->out_dim;
+    a.inv_rows = (float)inv_rows;
+    a.dfeat = w.dA;
+    a.g_hw = out + P.hw; a.g_hbias = out + P.hbias;
+    a.ln_z = w.Z[Lh - 1]; a.ln_stats = w.stats[Lh - 1]; a.ln_w = prepared + Q.lnw[Lh - 1];
+    a.g_ln_w = out + P.lnw[Lh - 1]; a.g_ln_b = out + P.lnb[Lh - 1]; a.ln_act = d->activation;
+    a.part_delta = w.dwpart - out; a.part_stride = w.ptotal;
+    if ((rc = launch_trpo_head(d->head, TR_FVP, a, st))) return rc;
+    if ((rc = trunk_backward(d, P, Q, params, prepared, out, n, w, st))) return rc;
+  }
+  if ((rc = launch_dw_reduce(out, w.dwpart, L.total, st))) return rc;
+  return launch_featnorm_fold(d, params, out, st);
+}
+
+int hb_trpo_fvp_finish(const hb_net_desc* d, const float* params, const float* v, float* out, float damping,
+                       void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(params && v && out, "NULL argument");
+  ParamLayout P;
+  hb_net_layout L;
+  int rc = check_net(d, &P, nullptr, &L, 1);
+  if (rc) return rc;
+  const bool box = d->head == HB_HEAD_BOX;
+  return launch_fvp_finish(out, v, params, damping, L.total, box ? P.log_std : 0, box ? d->out_dim : 0, d->std_x_coef,
+                           (cudaStream_t)stream);
+}
+
+int hb_trpo_eval(const hb_net_desc* d, const float* prepared, const hb_actor_batch* b, const hb_ppo_hyper* h,
+                 const float* old_dist, const float* params_old, double* scalars, void* ws, size_t ws_bytes,
+                 void* stream) {
+  using namespace hb;
+  HB_CHECK_ARG(prepared && b && h && old_dist && params_old && scalars, "NULL argument");
+  HB_CHECK_ARG(b->obs && b->actions && b->old_logp && b->adv && b->active && b->rows >= 0, "incomplete batch");
+  ParamLayout P;
+  PrepLayout Q;
+  int rc = check_net(d, &P, &Q, nullptr, 1);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = b->rows;
+  if (rows == 0) return HB_OK;
+  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  Work w;
+  if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
+  const int ad = d->head == HB_HEAD_DISCRETE ? 1 : d->out_dim;
+  for (int64_t c0 = 0; c0 < rows; c0 += ch) {
+    const int64_t n = rows - c0 < ch ? rows - c0 : ch;
+    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    const int64_t o = b->index ? 0 : c0;
+    TrpoHeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat = w.Y[Q.n_layers - 1];
+    a.h = Q.n[Q.n_layers - 1]; a.out = d->out_dim;
+    a.hw = prepared + Q.hw; a.hbias = prepared + Q.hbias; a.log_std = prepared + Q.log_std;
+    a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;
+    a.rows = n;
+    a.index = b->index ? b->index + c0 : nullptr;
+    a.avail = b->avail ? b->avail + o * d->out_dim : nullptr;
+    a.old_dist = old_dist + c0 * d->out_dim;
+    a.actions = b->actions + o * ad;
+    a.old_logp = b->old_logp + o * ad;
+    a.adv = b->adv + o;
+    a.factor = b->factor ? b->factor + o : nullptr;
+    a.active = b->active + o;
+    a.old_log_std = d->head == HB_HEAD_BOX ? params_old + P.log_std : nullptr;
+    a.use_active = h->use_policy_active_masks;
+    a.agg_prod = h->action_aggregation_prod;
+    a.scalars = scalars;
+    if ((rc = launch_trpo_head(d->head, TR_LS, a, st))) return rc;
+  }
+  return HB_OK;
+}
+
+int hb_trpo_cg_init(const float* b, float* x, float* r, float* p, float* state, int n, void* stream) {
+  HB_CHECK_ARG(b && x && r && p && state && n > 0, "bad argument");
+  return hb::launch_cg_init(b, x, r, p, state, n, (cudaStream_t)stream);
+}
+
+int hb_trpo_cg_step(float* p, const float* avp, float* x, float* r, float* state, int n, float residual_tol,
+                    void* stream) {
+  HB_CHECK_ARG(p && avp && x && r && state && n > 0, "bad argument");
+  return hb::launch_cg_step(p, avp, x, r, state, n, residual_tol, (cudaStream_t)stream);
+}
+
+int hb_trpo_full_step(const float* x, const float* fx, const float* g, float kl_threshold, float* full_step,
+                      double* out3, int n, void* stream) {
+  HB_CHECK_ARG(x && fx && g && full_step && out3 && n > 0 && kl_threshold > 0.f, "bad argument");
+  return hb::launch_full_step(x, fx, g, kl_threshold, full_step, out3, n, (cudaStream_t)stream);
+}
+
+int hb_trpo_apply_step(float* params, const float* params0, const float* full_step, float fraction, int n,
+                       void* stream) {
+  HB_CHECK_ARG(params && params0 && full_step && n > 0, "bad argument");
+  return hb::launch_apply_step(params, params0, full_step, fraction, n, (cudaStream_t)stream);
+}
+
+int hb_vec_scale(float* x, float s, int n, void* stream) {
+  HB_CHECK_ARG(x && n > 0, "bad argument");
+  return hb::launch_vec_scale(x, s, n, (cudaStream_t)stream);
 }
 }

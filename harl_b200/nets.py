@@ -241,3 +241,32 @@ class DeviceNet:
                         int(bool(use_max_grad_norm)), self.adam_steps)
         L.call("hb_clip_adam_step", C.byref(self.desc), L.ptr(self.params), L.ptr(self.grad), L.ptr(self.exp_avg),
                L.ptr(self.exp_avg_sq), L.ptr(self.prepared), C.byref(h), L.ptr(self.grad_norm), L.stream_ptr())
+
+    # ------------------------------------------------------------------ trust-region (HATRPO) calls
+    def _trpo_ws(self, rows):
+        n = L.lib.hb_trpo_workspace_bytes(C.byref(self.desc), int(rows))
+        ws = workspace(self.device, n)
+        return ws, ws.numel()
+
+    def trpo_old_dist(self, batch, old_dist):
+        self._need_cuda()
+        ws, n = self._trpo_ws(batch.rows)
+        L.call("hb_trpo_old_dist", C.byref(self.desc), L.ptr(self.prepared), C.byref(batch), L.ptr(old_dist), L.ptr(ws), n,
+               L.stream_ptr())
+
+    def trpo_fvp(self, batch, old_dist, vec, inv_rows, out):
+        """out = J^T H J vec over this rank's rows (no damping; see trpo_fvp_finish)."""
+        self._need_cuda()
+        ws, n = self._trpo_ws(batch.rows)
+        L.call("hb_trpo_fvp", C.byref(self.desc), L.ptr(self.params), L.ptr(self.prepared), C.byref(batch),
+               L.ptr(old_dist), L.ptr(vec), float(inv_rows), L.ptr(out), L.ptr(ws), n, L.stream_ptr())
+
+    def trpo_fvp_finish(self, vec, out, damping=0.1):
+        L.call("hb_trpo_fvp_finish", C.byref(self.desc), L.ptr(self.params), L.ptr(vec), L.ptr(out), float(damping),
+               L.stream_ptr())
+
+    def trpo_eval(self, batch, hyper, old_dist, params_old, scalars):
+        self._need_cuda()
+        ws, n = self._trpo_ws(batch.rows)
+        L.call("hb_trpo_eval", C.byref(self.desc), L.ptr(self.prepared), C.byref(batch), C.byref(hyper), L.ptr(old_dist),
+               L.ptr(params_old), L.ptr(scalars), L.ptr(ws), n, L.stream_ptr())

@@ -2,4 +2,5 @@
 from .on_policy_ha_runner import OnPolicyHARunner
 from .on_policy_ma_runner import OnPolicyMARunner
 
-RUNNER_REGISTRY = {"happo": OnPolicyHARunner, "haa2c": OnPolicyHARunner, "mappo": OnPolicyMARunner}
+RUNNER_REGISTRY = {"happo": OnPolicyHARunner, "hatrpo": OnPolicyHARunner, "haa2c": OnPolicyHARunner,
+                   "mappo": OnPolicyMARunner}

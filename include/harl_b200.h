@@ -274,6 +274,51 @@ int hb_clip_adam_step(const hb_net_desc* d, float* params, const float* grad, fl
                       float* exp_avg_sq, float* prepared, const hb_adam_hyper* h,
                       float* grad_norm_out, void* stream);
 
+/* ---- trust-region (HATRPO) update: harl/algorithms/actors/hatrpo.py:37-194, harl/utils/trpo_util.py ------- *
+ * The surrogate gradient is hb_ppo_actor_grad with use_clip = 0 and entropy_coef = 0 (it returns the gradient of
+ * -loss; hb_vec_scale flips the sign).  The parameter-space vectors below (v, out, x, r, p, g, full_step,
+ * params0) all use the flat hb_net_layout with zero padding words. */
+
+/* workspace for hb_trpo_fvp (covers hb_trpo_old_dist / hb_trpo_eval too) */
+size_t hb_trpo_workspace_bytes(const hb_net_desc* d, int64_t rows);
+
+/* Distribution of the CURRENT parameters per batch row -> old_dist [rows, out_dim]: torch Categorical.logits
+ * (normalised) for Discrete, the mean for Box.  Replaces the no-grad old_actor.evaluate_actions of
+ * trpo_util.py:79-82 (the old policy is evaluated once, not once per KL call). */
+int hb_trpo_old_dist(const hb_net_desc* d, const float* prepared, const hb_actor_batch* b, float* old_dist,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* fisher_vector_product (trpo_util.py:136-158) WITHOUT the + 0.1 p term: out = d2 mean_rows KL(pi || pi) / dtheta2 . v
+ * as J^T H J v (tangent pass, H / rows, backward pass), partial over this rank's rows; inv_rows = 1 / global rows.
+ * The caller sum-reduces `out` over ranks, then calls hb_trpo_fvp_finish. */
+int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared, const hb_actor_batch* b,
+                const float* old_dist, const float* v, double inv_rows, float* out, void* ws, size_t ws_bytes,
+                void* stream);
+/* out += damping * v (trpo_util.py:158), plus the DiagGaussian log_std block of the Hessian (row-independent). */
+int hb_trpo_fvp_finish(const hb_net_desc* d, const float* params, const float* v, float* out, float damping,
+                       void* stream);
+
+/* One backtracking-line-search trial (hatrpo.py:142-181): `prepared` holds the candidate parameters.
+ * scalars (device double[4]) += (sum ratio*factor*adv*w, sum entropy*w, sum ratio, sum KL(old || new)) over rows;
+ * w = active if use_policy_active_masks else 1.  params_old: flat parameters before the step (Box: old log_std). */
+int hb_trpo_eval(const hb_net_desc* d, const float* prepared, const hb_actor_batch* b, const hb_ppo_hyper* h,
+                 const float* old_dist, const float* params_old, double* scalars, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* conjugate_gradient (trpo_util.py:100-133) with the state on the device: cg_state = {rdotr, done}.
+ * cg_init: x = 0, r = p = b.  cg_step consumes avp = (F + 0.1 I) p and is a no-op once rdotr < residual_tol. */
+int hb_trpo_cg_init(const float* b, float* x, float* r, float* p, float* cg_state, int n, void* stream);
+int hb_trpo_cg_step(float* p, const float* avp, float* x, float* r, float* cg_state, int n, float residual_tol,
+                    void* stream);
+/* hatrpo.py:123-133: shs = 0.5 x.Fx; step_size = 1/sqrt(shs/kl_threshold); full_step = step_size * x;
+ * out3 (device double[3]) = (shs, step_size, expected_improve = g.full_step). */
+int hb_trpo_full_step(const float* x, const float* fx, const float* g, float kl_threshold, float* full_step,
+                      double* out3, int n, void* stream);
+/* update_model(actor, params + fraction * full_step), hatrpo.py:143-144 (follow with hb_net_prepare). */
+int hb_trpo_apply_step(float* params, const float* params0, const float* full_step, float fraction, int n,
+                       void* stream);
+int hb_vec_scale(float* x, float s, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

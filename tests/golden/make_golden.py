@@ -479,6 +479,8 @@ def case_hatrpo_parts():
         ("disc", {}, Discrete(5)),
         ("box", dict(hidden_sizes=[32, 32, 32], action_aggregation="mean"), Box(3)),
         ("disc_nomask", dict(use_policy_active_masks=False, activation_func="tanh", kl_threshold=0.001), Discrete(4)),
+        ("disc_backtrack", dict(accept_ratio=0.75), Discrete(5)),         # two trials rejected, the third accepted
+        ("box_reject", dict(accept_ratio=5.0, ls_step=3), Box(2)),        # never accepted: parameters restored
     ):
         torch.manual_seed(31)
         g = torch.Generator().manual_seed(32)

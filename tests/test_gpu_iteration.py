@@ -85,9 +85,10 @@ def test_mappo_iteration_vs_oracle(action_type, state_type, share):
     runner.close()
 
 
-def _load_runner_from_golden(g, cfg, m):
+def _load_runner_from_golden(g, cfg, m, actor_cls=None):
     """A runner shell (no env / dirs) holding the golden buffers and weights."""
     from harl_b200.algorithms.actors.happo import HAPPO
+    from harl_b200.common.buffers.on_policy_critic_buffer_fp import OnPolicyCriticBufferFP
     from harl_b200.algorithms.critics.v_critic import VCritic
     from harl_b200.common.buffers.on_policy_actor_buffer import OnPolicyActorBuffer
     from harl_b200.common.buffers.on_policy_critic_buffer_ep import OnPolicyCriticBufferEP
@@ -104,7 +105,7 @@ def _load_runner_from_golden(g, cfg, m):
     r.fixed_order, r.action_aggregation = True, cfg["action_aggregation"]
     r.actor, r.actor_buffer = [], []
     for a in range(A):
-        ac = HAPPO(cfg, Box(shape=(m["od"],)), act_space, device=dev)
+        ac = (actor_cls or HAPPO)(cfg, Box(shape=(m["od"],)), act_space, device=dev)
         ac.actor.load_state_dict(U.params_of(g, f"actor{a}/"))
         r.actor.append(ac)
         b = OnPolicyActorBuffer(cfg, Box(shape=(m["od"],)), act_space, device=dev)
@@ -115,7 +116,10 @@ def _load_runner_from_golden(g, cfg, m):
         r.actor_buffer.append(b)
     r.critic = VCritic(cfg, Box(shape=(m["sd"],)), device=dev)
     r.critic.critic.load_state_dict(U.params_of(g, "critic/"))
-    cb = OnPolicyCriticBufferEP(cfg, Box(shape=(m["sd"],)), device=dev)
+    if m["state_type"] == "FP":
+        cb = OnPolicyCriticBufferFP(cfg, Box(shape=(m["sd"],)), A, device=dev)
+    else:
+        cb = OnPolicyCriticBufferEP(cfg, Box(shape=(m["sd"],)), device=dev)
     for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks"):
         getattr(cb, k).copy_(torch.from_numpy(g["c." + k]))
     r.critic_buffer = cb
