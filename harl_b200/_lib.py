@@ -68,7 +68,7 @@ class PPOHyper(C.Structure):
 class ActorBatch(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("actions", C.c_void_p), ("old_logp", C.c_void_p), ("adv", C.c_void_p),
                 ("factor", C.c_void_p), ("active", C.c_void_p), ("avail", C.c_void_p), ("index", C.c_void_p),
-                ("rows", C.c_int64)]
+                ("rows", C.c_int64), ("rnn_states", C.c_void_p), ("masks", C.c_void_p), ("seq_len", C.c_int64)]
 
 
 class ValueHyper(C.Structure):
@@ -78,7 +78,8 @@ class ValueHyper(C.Structure):
 
 class CriticBatch(C.Structure):
     _fields_ = [("share_obs", C.c_void_p), ("value_preds", C.c_void_p), ("returns", C.c_void_p),
-                ("index", C.c_void_p), ("rows", C.c_int64)]
+                ("index", C.c_void_p), ("rows", C.c_int64), ("rnn_states", C.c_void_p), ("masks", C.c_void_p),
+                ("seq_len", C.c_int64)]
 
 
 class AdamHyper(C.Structure):
@@ -119,6 +120,9 @@ SIGNATURES = {
     "hb_value_grad": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(CriticBatch), C.POINTER(ValueHyper), P,
                                 C.c_double, P, P, P, C.c_size_t, P]),
     "hb_clip_adam_step": (C.c_int, [C.POINTER(NetDesc), P, P, P, P, P, C.POINTER(AdamHyper), P, P]),
+    "hb_policy_act_rnn": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, P, C.c_int, C.c_uint64, C.c_uint64, P, P,
+                                    P, P, C.c_size_t, P]),
+    "hb_value_forward_rnn": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, P, P, P, C.c_size_t, P]),
     "hb_trpo_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64]),
     "hb_trpo_old_dist": (C.c_int, [C.POINTER(NetDesc), P, C.POINTER(ActorBatch), P, P, C.c_size_t, P]),
     "hb_trpo_fvp": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(ActorBatch), P, P, C.c_double, P, P, C.c_size_t, P]),

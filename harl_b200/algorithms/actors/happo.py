@@ -10,6 +10,7 @@ import torch
 
 from ... import _lib as L
 from ... import dist
+from ...common import seq_index
 from ...nets import DeviceNet
 from .on_policy_base import OnPolicyBase, to_device
 
@@ -44,7 +45,15 @@ class HAPPO(OnPolicyBase):
         d = self.device
         obs, actions, active, old_lp, adv, factor, avail = (to_device(x, d) for x in
                                                              (obs, actions, active, old_lp, adv, factor, avail))
-        batch = DeviceNet.actor_batch(obs, actions, old_lp, adv.reshape(-1), factor.reshape(-1), active.reshape(-1), avail)
+        rnn = mk = None
+        seq_len = 0
+        if self.recurrent:  # the reference's generator output: states at the sequence starts, step-major rows
+            rnn = to_device(_rnn, d)
+            rnn = rnn.reshape(rnn.shape[0], -1)
+            mk = to_device(_masks, d).reshape(-1)
+            seq_len = obs.shape[0] // rnn.shape[0]
+        batch = DeviceNet.actor_batch(obs, actions, old_lp, adv.reshape(-1), factor.reshape(-1), active.reshape(-1), avail,
+                                      rnn_states=rnn, masks=mk, seq_len=seq_len)
         norm3 = torch.zeros(3, dtype=torch.float64, device=d)
         norm3[2] = active.sum().double() if self.use_policy_active_masks else float(obs.shape[0])
         dist.all_reduce_sum_(norm3)
@@ -73,8 +82,6 @@ class HAPPO(OnPolicyBase):
             adv_n = torch.empty_like(adv)
             L.call("hb_normalize_by_moments", L.ptr(adv), L.ptr(adv_n), rows, L.ptr(m3), L.stream_ptr())
             adv = adv_n
-        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
-            raise NotImplementedError("recurrent (GRU) policies are not implemented in this build")
         nmb = self.actor_num_mini_batch
         n_up = self.ppo_epoch * nmb
         scal = torch.zeros(n_up, 4, dtype=torch.float64, device=d)
@@ -84,27 +91,25 @@ class HAPPO(OnPolicyBase):
         obs, actions, old_lp = fl(buf.obs[:-1]), fl(buf.actions), fl(buf.action_log_probs)
         avail = None if buf.available_actions is None else fl(buf.available_actions[:-1])
         factor = None if buf.factor is None else buf.factor.reshape(rows)
-        global_rows = float(rows * dist.world_size())
+        # recurrent policies: the kernels also read the stored hidden states and the reset masks in place
+        rnn = buf.rnn_states.reshape((T + 1) * N, -1) if self.recurrent else None
+        masks = buf.masks.reshape((T + 1) * N) if self.recurrent else None
+        mode = seq_index.mode_of(self.use_recurrent_policy, self.use_naive_recurrent_policy)
+        world = dist.world_size()
         u = 0
         for _ in range(self.ppo_epoch):
-            if nmb == 1:
-                # a single minibatch is the whole buffer: the shuffle only reorders a mean, skip it
-                parts = [None]
-            else:
-                mb = rows // nmb
-                perm = torch.randperm(rows, device=d).to(torch.int32)
-                parts = [perm[i * mb:(i + 1) * mb].contiguous() for i in range(nmb)]
-            for idx in parts:
-                if idx is None:
-                    norms[u, 2] = n_active if self.use_policy_active_masks else global_rows
+            # a single feed-forward / naive minibatch is the whole buffer: the shuffle only reorders a mean, skip it
+            for idx, nrows, seq_len in seq_index.minibatches(T, N, nmb, mode, self.data_chunk_length, d):
+                if idx is None or nrows == rows:
+                    norms[u, 2] = n_active if self.use_policy_active_masks else float(rows * world)
                 else:
                     if self.use_policy_active_masks:
                         norms[u, 2] = active[idx.long()].sum().double()
                     else:
-                        norms[u, 2] = float(idx.numel())
+                        norms[u, 2] = float(nrows)
                     dist.all_reduce_sum_(norms[u])
-                batch = DeviceNet.actor_batch(obs, actions, old_lp, adv, factor, active, avail, idx,
-                                              rows if idx is None else idx.numel())
+                batch = DeviceNet.actor_batch(obs, actions, old_lp, adv, factor, active, avail, idx, nrows,
+                                              rnn_states=rnn, masks=masks, seq_len=seq_len)
                 self._step(batch, norms[u], scal[u])
                 gnorm[u] = self.actor.grad_norm[0]
                 u += 1

@@ -27,6 +27,9 @@ class HATRPO(OnPolicyBase):
     def __init__(self, args, obs_space, act_space, device=torch.device("cpu")):
         assert act_space.__class__.__name__ != "MultiDiscrete", \
             "only continuous and discrete action space is supported by HATRPO."
+        if args["use_recurrent_policy"] or args["use_naive_recurrent_policy"]:
+            raise NotImplementedError("HATRPO with recurrent (GRU) policies: the tangent pass of the Fisher-vector "
+                                      "product does not cover the GRU in this build")
         super().__init__(args, obs_space, act_space, device)
         self.kl_threshold = args["kl_threshold"]
         self.ls_step = args["ls_step"]

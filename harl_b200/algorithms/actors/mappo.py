@@ -9,6 +9,7 @@ import torch
 
 from ... import _lib as L
 from ... import dist
+from ...common import seq_index
 from ...nets import DeviceNet
 from .happo import HAPPO
 from .on_policy_base import to_device
@@ -22,10 +23,17 @@ class MAPPO(HAPPO):
         return super().update((obs, rnn, actions, masks, active, old_lp, adv, avail, ones))
 
     def share_param_train(self, actor_buffer, advantages, num_agents, state_type):
-        """Reference mappo.py:149-222 (non-recurrent policies)."""
+        """Reference mappo.py:149-222 (feed-forward policies).
+
+        With a recurrent policy the reference concatenates the agents' step-major chunk batches along axis 0 and then
+        lets RNNLayer re-read the result as [L, A * mb] (mappo.py:207-216, rnn.py:33-41): row (l, j) of agent a lands
+        at step (a * L * mb + l * mb + j) // (A * mb) of an unrelated sequence, so hidden states, observations and
+        masks of different agents and chunks are interleaved.  That layout cannot be expressed as an in-place index
+        into one agent's buffer; rather than silently computing something else, this combination fails loudly."""
         info = dict(policy_loss=0.0, dist_entropy=0.0, actor_grad_norm=0.0, ratio=0.0)
-        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
-            raise NotImplementedError("recurrent (GRU) policies are not implemented in this build")
+        if self.recurrent:
+            raise NotImplementedError("share_param with recurrent (GRU) policies is not implemented: the reference "
+                                      "interleaves the agents' sequences when it concatenates their minibatches")
         d = self.device
         T, N = actor_buffer[0].actions.shape[:2]
         rows = T * N
@@ -50,24 +58,29 @@ class MAPPO(HAPPO):
         gnorm = torch.zeros(n_up, dtype=torch.float32, device=d)
         norms = torch.zeros(n_up, 3, dtype=torch.float64, device=d)
         acc = torch.zeros_like(self.actor.grad)
-        mb = rows // nmb
+        mode = "ff"
+        rnns, masks = [None] * num_agents, [None] * num_agents
         u = 0
         for _ in range(self.ppo_epoch):
-            perms = [None] * num_agents if nmb == 1 else [torch.randperm(rows, device=d).to(torch.int32) for _ in range(num_agents)]
+            # one generator per agent (mappo.py:179-205): independent permutations, same minibatch sizes
+            gens = [list(seq_index.minibatches(T, N, nmb, mode, self.data_chunk_length, d)) for _ in range(num_agents)]
             for i in range(nmb):
-                idxs = [None if p is None else p[i * mb:(i + 1) * mb].contiguous() for p in perms]
+                parts = [g[i] for g in gens]
                 # global normaliser of the concatenated batch
                 for a in range(num_agents):
+                    idx, nrows, _ = parts[a]
                     if self.use_policy_active_masks:
-                        norms[u, 2] += (actives[a] if idxs[a] is None else actives[a][idxs[a].long()]).sum().double()
+                        norms[u, 2] += (actives[a] if idx is None else actives[a][idx.long()]).sum().double()
                     else:
-                        norms[u, 2] += float(rows if idxs[a] is None else idxs[a].numel())
+                        norms[u, 2] += float(nrows)
                 dist.all_reduce_sum_(norms[u])
                 acc.zero_()
                 for a, b in enumerate(actor_buffer):
+                    idx, nrows, seq_len = parts[a]
                     avail = None if b.available_actions is None else fl(b.available_actions[:-1])
                     batch = DeviceNet.actor_batch(fl(b.obs[:-1]), fl(b.actions), fl(b.action_log_probs), advs[a], None,
-                                                  actives[a], avail, idxs[a], rows if idxs[a] is None else idxs[a].numel())
+                                                  actives[a], avail, idx, nrows, rnn_states=rnns[a], masks=masks[a],
+                                                  seq_len=seq_len)
                     self.actor.actor_grad(batch, self._hyper(), norms[u], scal[u])
                     acc += self.actor.grad
                 self.actor.grad.copy_(acc)

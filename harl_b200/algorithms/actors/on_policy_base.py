@@ -56,21 +56,30 @@ class OnPolicyBase:
     def lr_decay(self, episode, episodes):
         self.cur_lr = linear_schedule_lr(episode, episodes, self.lr)
 
+    @property
+    def recurrent(self):
+        return bool(self.use_recurrent_policy or self.use_naive_recurrent_policy)
+
     def _rnn_passthrough(self, rnn_states_actor):
-        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
-            raise NotImplementedError("recurrent (GRU) policies are not implemented in this build")
         return rnn_states_actor if torch.is_tensor(rnn_states_actor) else to_device(rnn_states_actor, self.device)
 
     def get_actions(self, obs, rnn_states_actor, masks, available_actions=None, deterministic=False,
-                    actions_out=None, logp_out=None):
+                    actions_out=None, logp_out=None, rnn_out=None):
         """Sample (or take the mode of) actions for a batch of observations; returns device tensors
-        (actions [B, ad], log-probs [B, ad], rnn states)."""
+        (actions [B, ad], log-probs [B, ad], rnn states [B, recurrent_n, h] -- the GRU's new hidden state for
+        recurrent policies, the input passed through otherwise)."""
         obs = to_device(obs, self.device)
         avail = to_device(available_actions, self.device)
         B, w = obs.shape[0], self.actor.act_width
         actions = actions_out if actions_out is not None else torch.empty(B, w, **self.tpdv)
         logp = logp_out if logp_out is not None else torch.empty(B, w, **self.tpdv)
         self._draws += 1
+        if self.recurrent:
+            rnn_in = to_device(rnn_states_actor, self.device)
+            mk = to_device(masks, self.device).reshape(B)
+            rnn_new = rnn_out if rnn_out is not None else torch.empty_like(rnn_in)
+            self.actor.act(obs, avail, deterministic, self._seed, self._draws, actions, logp, rnn_in, mk, rnn_new)
+            return actions, logp, rnn_new
         self.actor.act(obs, avail, deterministic, self._seed, self._draws, actions, logp)
         return actions, logp, self._rnn_passthrough(rnn_states_actor)
 
@@ -79,11 +88,18 @@ class OnPolicyBase:
 
         The entropy and distribution object the reference also returns are consumed only by the
         loss / KL code, which here lives inside the fused gradient kernels."""
-        self._rnn_passthrough(rnn_states_actor)
         obs, action = to_device(obs, self.device), to_device(action, self.device)
         avail = to_device(available_actions, self.device)
         logp = torch.empty(obs.shape[0], self.actor.act_width, **self.tpdv)
-        self.actor.evaluate(DeviceNet.actor_batch(obs, action, avail=avail), logp_out=logp)
+        if self.recurrent:
+            # rnn.py:24: rows == states -> one step per row; otherwise T steps x N sequences, time-major rows
+            rnn = to_device(rnn_states_actor, self.device)
+            mk = to_device(masks, self.device).reshape(-1)
+            seq_len = obs.shape[0] // rnn.shape[0]
+            batch = DeviceNet.actor_batch(obs, action, avail=avail, rnn_states=rnn, masks=mk, seq_len=seq_len)
+        else:
+            batch = DeviceNet.actor_batch(obs, action, avail=avail)
+        self.actor.evaluate(batch, logp_out=logp)
         return logp, None, None
 
     def act(self, obs, rnn_states_actor, masks, available_actions=None, deterministic=False):

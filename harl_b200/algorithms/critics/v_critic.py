@@ -9,6 +9,7 @@ import torch
 
 from ... import _lib as L
 from ... import dist
+from ...common import seq_index
 from ...nets import DeviceNet
 from ...utils.envs_tools import get_shape_from_obs_space
 from ...utils.models_tools import linear_schedule_lr
@@ -46,15 +47,21 @@ class VCritic:
     def lr_decay(self, episode, episodes):
         self.cur_lr = linear_schedule_lr(episode, episodes, self.critic_lr)
 
-    def _no_rnn(self):
-        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
-            raise NotImplementedError("recurrent (GRU) critics are not implemented in this build")
+    @property
+    def recurrent(self):
+        return bool(self.use_recurrent_policy or self.use_naive_recurrent_policy)
 
-    def get_values(self, cent_obs, rnn_states_critic, masks, values_out=None):
-        """Value predictions [B, 1] and (pass-through) rnn states, as device tensors."""
-        self._no_rnn()
+    def get_values(self, cent_obs, rnn_states_critic, masks, values_out=None, rnn_out=None):
+        """Value predictions [B, 1] and rnn states (the GRU's new hidden state for a recurrent critic, the input
+        passed through otherwise), as device tensors."""
         x = to_device(cent_obs, self.device)
         v = values_out if values_out is not None else torch.empty(x.shape[0], 1, **self.tpdv)
+        if self.recurrent:
+            rnn_in = to_device(rnn_states_critic, self.device)
+            mk = to_device(masks, self.device).reshape(x.shape[0])
+            rnn_new = rnn_out if rnn_out is not None else torch.empty_like(rnn_in)
+            self.critic.values(x, v, rnn_in, mk, rnn_new)
+            return v, rnn_new
         self.critic.values(x, v)
         rnn = rnn_states_critic if torch.is_tensor(rnn_states_critic) else to_device(rnn_states_critic, self.device)
         return v, rnn
@@ -63,7 +70,8 @@ class VCritic:
         return L.ValueHyper(float(self.clip_param), float(self.huber_delta), float(self.value_loss_coef),
                             int(bool(self.use_huber_loss)), int(bool(self.use_clipped_value_loss)))
 
-    def _step(self, share_obs, value_preds, returns, index, rows, global_rows, value_normalizer, scalars_row):
+    def _step(self, share_obs, value_preds, returns, index, rows, global_rows, value_normalizer, scalars_row,
+              rnn_states=None, masks=None, seq_len=0):
         d = self.device
         if value_normalizer is not None:
             m3 = torch.zeros(3, dtype=torch.float64, device=d)
@@ -71,7 +79,7 @@ class VCritic:
             L.call("hb_masked_moments", L.ptr(src.contiguous()), None, rows, L.ptr(m3), L.stream_ptr())
             dist.all_reduce_sum_(m3)
             value_normalizer.update_from_moments(m3)
-        cb = DeviceNet.critic_batch(share_obs, value_preds, returns, index, rows)
+        cb = DeviceNet.critic_batch(share_obs, value_preds, returns, index, rows, rnn_states, masks, seq_len)
         vn = value_normalizer.state if value_normalizer is not None else None
         self.critic.value_grad(cb, self._hyper(), vn, 1.0 / global_rows, scalars_row)
         dist.all_reduce_sum_(self.critic.grad)
@@ -84,7 +92,15 @@ class VCritic:
         so, vp, rt = (to_device(x, d) for x in (share_obs, value_preds, returns))
         rows = so.shape[0]
         scal = torch.zeros(4, dtype=torch.float64, device=d)
-        self._step(so, vp.reshape(-1), rt.reshape(-1), None, rows, float(rows * dist.world_size()), value_normalizer, scal)
+        rnn = mk = None
+        seq_len = 0
+        if self.recurrent:  # the reference's generator output: states at the sequence starts, step-major rows
+            rnn = to_device(_rnn, d)
+            rnn = rnn.reshape(rnn.shape[0], -1)
+            mk = to_device(_masks, d).reshape(-1)
+            seq_len = rows // rnn.shape[0]
+        self._step(so, vp.reshape(-1), rt.reshape(-1), None, rows, float(rows * dist.world_size()), value_normalizer, scal,
+                   rnn, mk, seq_len)
         dist.all_reduce_sum_(scal)
         s = scal.cpu().numpy()
         return s[0] / s[1], self.critic.grad_norm.item()
@@ -93,29 +109,25 @@ class VCritic:
         """Reference v_critic.py:159-200.  ``defer=True`` enqueues the whole update without a host read and returns
         a closure producing the train-info (the HA runner runs the critic update on a side stream, overlapped with
         the sequential actor updates, and reads the scalars after joining the streams)."""
-        self._no_rnn()
         d = self.device
         buf = critic_buffer
         T = buf.episode_length
         rows = buf.value_preds[:-1].numel()
+        Cn = rows // T  # N envs, or N * A (env, agent) pairs for the FP critic
         so = buf.share_obs[:-1].reshape(rows, -1)
         vp = buf.value_preds[:-1].reshape(rows)
         rt = buf.returns[:-1].reshape(rows)
+        rnn = buf.rnn_states_critic.reshape((T + 1) * Cn, -1) if self.recurrent else None
+        masks = buf.masks.reshape((T + 1) * Cn) if self.recurrent else None
+        mode = seq_index.mode_of(self.use_recurrent_policy, self.use_naive_recurrent_policy)
         nmb = self.critic_num_mini_batch
         n_up = self.critic_epoch * nmb
         scal = torch.zeros(n_up, 4, dtype=torch.float64, device=d)
         gnorm = torch.zeros(n_up, dtype=torch.float32, device=d)
         u = 0
         for _ in range(self.critic_epoch):
-            if nmb == 1:
-                parts = [None]
-            else:
-                mb = rows // nmb
-                perm = torch.randperm(rows, device=d).to(torch.int32)
-                parts = [perm[i * mb:(i + 1) * mb].contiguous() for i in range(nmb)]
-            for idx in parts:
-                n = rows if idx is None else idx.numel()
-                self._step(so, vp, rt, idx, n, float(n * dist.world_size()), value_normalizer, scal[u])
+            for idx, n, seq_len in seq_index.minibatches(T, Cn, nmb, mode, self.data_chunk_length, d):
+                self._step(so, vp, rt, idx, n, float(n * dist.world_size()), value_normalizer, scal[u], rnn, masks, seq_len)
                 gnorm[u] = self.critic.grad_norm[0]
                 u += 1
         dist.all_reduce_sum_(scal)

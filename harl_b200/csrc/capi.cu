@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rnn.cuh"
 #include "trpo.cuh"
 
 namespace hb {
@@ -30,6 +31,21 @@ struct Work {
   float* dB;
   float* dwpart;   // [tc_dw_splits()][param total] split buffer of the tensor-core dW kernel (gradient mode)
   int ptotal;
+  RnnWork rnn;     // GRU buffers (recurrent networks only)
+};
+
+// rows per launch: recurrent batches are never split (a chunk would have to cut every sequence)
+static int64_t chunk_of(const hb_net_desc* d, int64_t rows) {
+  if (rows < 1) return 1;
+  return (d->rnn_layers || rows < CHUNK_ROWS) ? rows : CHUNK_ROWS;
+}
+
+// the sequence structure of a recurrent batch (RNNLayer.forward, rnn.py:22-81)
+struct SeqCtx {
+  const float* h0;      // [buffer rows, rnn_layers * h]; sequence j starts from row (index ? index[j] : j)
+  const float* masks;   // [buffer rows]
+  int64_t S;            // steps; batch rows are step-major, B = rows / S
+  float* h_out;         // nullable [B, rnn_layers * h]
 };
 
 static int hmax_of(const PrepLayout& Q) {
@@ -38,12 +54,16 @@ static int hmax_of(const PrepLayout& Q) {
   return m;
 }
 
-static size_t work_floats(const PrepLayout& Q, int64_t ch, int mode, int ptotal) {
+static size_t base_floats(const PrepLayout& Q, int64_t ch, int mode, int ptotal) {
   size_t f = (size_t)ch * Q.kpad[0];
   const size_t hm = hmax_of(Q);
   if (mode == 0) return f + 2 * (size_t)ch * hm;
   for (int l = 0; l < Q.n_layers; ++l) f += 2 * (size_t)ch * Q.n[l] + (size_t)round_up((int)(2 * ch), 4);
-  return f + 2 * (size_t)ch * hm + (size_t)tc_dw_splits() * ptotal;
+  return f + 2 * (size_t)ch * hm + (size_t)round_up(tc_dw_splits() * ptotal, 4);
+}
+
+static size_t work_floats(const PrepLayout& Q, int64_t ch, int mode, int ptotal) {
+  return base_floats(Q, ch, mode, ptotal) + rnn_work_floats(Q, ch, mode);
 }
 
 static int carve(const PrepLayout& Q, int64_t ch, int mode, void* ws, size_t ws_bytes, Work* w, int ptotal = 0) {
@@ -60,7 +80,7 @@ static int carve(const PrepLayout& Q, int64_t ch, int mode, void* ws, size_t ws_
     w->dA = p; p += (size_t)ch * hm;
     w->dB = p;
     for (int l = 0; l < Q.n_layers; ++l) { w->Z[l] = nullptr; w->stats[l] = nullptr; w->Y[l] = (l & 1) ? w->dB : w->dA; }
-    return HB_OK;
+    return carve_rnn(Q, ch, 0, (float*)ws + base_floats(Q, ch, 0, ptotal), &w->rnn);
   }
   for (int l = 0; l < Q.n_layers; ++l) {
     w->Z[l] = p; p += (size_t)ch * Q.n[l];
@@ -70,7 +90,39 @@ static int carve(const PrepLayout& Q, int64_t ch, int mode, void* ws, size_t ws_
   w->dA = p; p += (size_t)ch * hm;
   w->dB = p; p += (size_t)ch * hm;
   w->dwpart = p;
-  return HB_OK;
+  return carve_rnn(Q, ch, 1, (float*)ws + base_floats(Q, ch, 1, ptotal), &w->rnn);
+}
+
+static int trunk_forward(const hb_net_desc* d, const PrepLayout& Q, const float* prep, const float* obs,
+                         const int32_t* index, int64_t c0, int64_t rows, const Work& w, cudaStream_t st);
+
+// trunk (+ GRU + its LayerNorm): *feat = the head's input rows
+static int features_forward(const hb_net_desc* d, const PrepLayout& Q, const float* prep, const float* obs,
+                            const int32_t* index, int64_t c0, int64_t rows, const SeqCtx* seq, const Work& w,
+                            cudaStream_t st, const float** feat) {
+  int rc = trunk_forward(d, Q, prep, obs, index, c0, rows, w, st);
+  if (rc) return rc;
+  *feat = w.Y[Q.n_layers - 1];
+  if (!d->rnn_layers) return HB_OK;
+  if (seq == nullptr || seq->h0 == nullptr || seq->masks == nullptr || seq->S < 1 || rows % seq->S != 0) {
+    set_error("recurrent network: the batch needs rnn_states, masks and a seq_len dividing its %lld rows", (long long)rows);
+    return HB_ERR_INVALID;
+  }
+  rc = rnn_forward(Q, prep, *feat, seq->S, rows / seq->S, seq->h0, seq->masks, index, seq->h_out, w.rnn, st);
+  *feat = w.rnn.out;
+  return rc;
+}
+
+// recurrent networks: head wrote d/d(hs_top) into w.rnn.dtop -> BPTT -> LN/act backward of the last trunk block -> w.dA
+static int rnn_to_trunk_backward(const hb_net_desc* d, const ParamLayout& P, const PrepLayout& Q, const float* params,
+                                 const float* prep, float* grad, int64_t rows, const SeqCtx* seq, const Work& w,
+                                 cudaStream_t st) {
+  const int Lh = Q.n_layers;
+  float* dX = nullptr;
+  int rc = rnn_backward(P, Q, params, w.Y[Lh - 1], seq->S, rows / seq->S, grad, w.rnn, &dX, st);
+  if (rc) return rc;
+  return launch_ln_act_bwd(dX, w.Z[Lh - 1], w.stats[Lh - 1], prep + Q.lnw[Lh - 1], w.dA, grad + P.lnw[Lh - 1],
+                           grad + P.lnb[Lh - 1], rows, Q.n[Lh - 1], d->activation, st);
 }
 
 // feature norm + trunk for `rows` rows starting at buffer row c0 (or index + c0)
@@ -132,7 +184,6 @@ static int trunk_backward(const hb_net_desc* d, const ParamLayout& P, const Prep
 static int check_net(const hb_net_desc* d, ParamLayout* P, PrepLayout* Q, hb_net_layout* L, int want_policy) {
   int rc = make_layouts(d, P, Q, L);
   if (rc) return rc;
-  if (d->rnn_layers) { set_error("recurrent (GRU) networks are not implemented in this build"); return HB_ERR_UNSUPPORTED; }
   if (want_policy == 1 && d->head == HB_HEAD_VALUE) { set_error("expected a policy head"); return HB_ERR_INVALID; }
   if (want_policy == 0 && d->head != HB_HEAD_VALUE) { set_error("expected a value head"); return HB_ERR_INVALID; }
   return HB_OK;
@@ -171,31 +222,34 @@ size_t hb_workspace_bytes(const hb_net_desc* d, int64_t rows, int mode) {
   hb::PrepLayout Q;
   hb::ParamLayout P;
   if (hb::make_layouts(d, &P, &Q, nullptr)) return 0;
-  int64_t ch = rows < hb::CHUNK_ROWS ? rows : hb::CHUNK_ROWS;
-  if (ch < 1) ch = 1;
+  const int64_t ch = hb::chunk_of(d, rows);
   return hb::work_floats(Q, ch, mode, P.total) * sizeof(float);
 }
 
-int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
-                  int deterministic, uint64_t seed, uint64_t offset, float* actions, float* logp, void* ws,
-                  size_t ws_bytes, void* stream) {
+static int policy_act_impl(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows,
+                           const float* avail, const float* h_in, const float* masks, int deterministic, uint64_t seed,
+                           uint64_t offset, float* actions, float* logp, float* h_out, void* ws, size_t ws_bytes,
+                           void* stream) {
   using namespace hb;
   HB_CHECK_ARG(prepared && obs && actions && logp && rows >= 0, "bad argument");
   PrepLayout Q;
   int rc = check_net(d, nullptr, &Q, nullptr, 1);
   if (rc) return rc;
+  HB_CHECK_ARG(!d->rnn_layers || (h_in && masks && h_out), "recurrent policy: rnn_states, masks and rnn_states_out are required");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
   if (rows == 0) return HB_OK;
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
   const int ad = d->head == HB_HEAD_DISCRETE ? 1 : d->out_dim;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, obs, nullptr, c0, n, w, st))) return rc;
+    SeqCtx seq = {h_in, masks, 1, h_out};  // one step: S = 1, every row its own sequence (rnn.py:24-32)
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, obs, nullptr, c0, n, d->rnn_layers ? &seq : nullptr, w, st, &feat))) return rc;
     HeadArgs a;
     head_base(d, Q, prepared, &a);
-    a.feat = w.Y[Q.n_layers - 1];
+    a.feat = feat;
     a.rows = n;
     a.avail = avail ? avail + c0 * d->out_dim : nullptr;
     a.deterministic = deterministic;
@@ -208,30 +262,28 @@ int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs,
   return HB_OK;
 }
 
-int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
-                  int deterministic, uint64_t seed, uint64_t offset, float* actions, float* logp, void* ws,
-                  size_t ws_bytes, void* stream);
-int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows, float* values,
-                     void* ws, size_t ws_bytes, void* stream);
-
-int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows, float* values,
-                     void* ws, size_t ws_bytes, void* stream) {
+static int value_forward_impl(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows,
+                              const float* h_in, const float* masks, float* values, float* h_out, void* ws,
+                              size_t ws_bytes, void* stream) {
   using namespace hb;
   HB_CHECK_ARG(prepared && cent_obs && values && rows >= 0, "bad argument");
   PrepLayout Q;
   int rc = check_net(d, nullptr, &Q, nullptr, 0);
   if (rc) return rc;
+  HB_CHECK_ARG(!d->rnn_layers || (h_in && masks && h_out), "recurrent critic: rnn_states, masks and rnn_states_out are required");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return HB_OK;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, cent_obs, nullptr, c0, n, w, st))) return rc;
+    SeqCtx seq = {h_in, masks, 1, h_out};
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, cent_obs, nullptr, c0, n, d->rnn_layers ? &seq : nullptr, w, st, &feat))) return rc;
     ValueArgs a;
     memset(&a, 0, sizeof(a));
-    a.feat = w.Y[Q.n_layers - 1];
+    a.feat = feat;
     a.h = Q.n[Q.n_layers - 1];
     a.hw = prepared + Q.hw;
     a.hbias = prepared + Q.hbias;
@@ -240,6 +292,31 @@ int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* c
     if ((rc = launch_value_head(0, a, st))) return rc;
   }
   return HB_OK;
+}
+
+int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
+                  int deterministic, uint64_t seed, uint64_t offset, float* actions, float* logp, void* ws,
+                  size_t ws_bytes, void* stream) {
+  return policy_act_impl(d, prepared, obs, rows, avail, nullptr, nullptr, deterministic, seed, offset, actions, logp,
+                         nullptr, ws, ws_bytes, stream);
+}
+
+int hb_policy_act_rnn(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
+                      const float* rnn_states, const float* masks, int deterministic, uint64_t seed, uint64_t offset,
+                      float* actions, float* logp, float* rnn_states_out, void* ws, size_t ws_bytes, void* stream) {
+  return policy_act_impl(d, prepared, obs, rows, avail, rnn_states, masks, deterministic, seed, offset, actions, logp,
+                         rnn_states_out, ws, ws_bytes, stream);
+}
+
+int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows, float* values,
+                     void* ws, size_t ws_bytes, void* stream) {
+  return value_forward_impl(d, prepared, cent_obs, rows, nullptr, nullptr, values, nullptr, ws, ws_bytes, stream);
+}
+
+int hb_value_forward_rnn(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows,
+                         const float* rnn_states, const float* masks, float* values, float* rnn_states_out, void* ws,
+                         size_t ws_bytes, void* stream) {
+  return value_forward_impl(d, prepared, cent_obs, rows, rnn_states, masks, values, rnn_states_out, ws, ws_bytes, stream);
 }
 
 int hb_policy_evaluate(const hb_net_desc* d, const float* prepared, const hb_actor_batch* b, float* logp_out,
@@ -254,17 +331,19 @@ int hb_policy_evaluate(const hb_net_desc* d, const float* prepared, const hb_act
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
   const int ad = d->head == HB_HEAD_DISCRETE ? 1 : d->out_dim;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, b->obs, b->index, c0, n, d->rnn_layers ? &seq : nullptr, w, st, &feat))) return rc;
     HeadArgs a;
     head_base(d, Q, prepared, &a);
     head_batch(d, b, c0, n, &a);
-    a.feat = w.Y[Q.n_layers - 1];
+    a.feat = feat;
     a.logp_out = logp_out ? logp_out + c0 * ad : nullptr;
     a.logp_ref = logp_ref ? logp_ref + c0 * ad : nullptr;
     a.factor_inout = factor_inout ? factor_inout + c0 : nullptr;
@@ -290,20 +369,23 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_ppo_actor_grad(memset)");
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w, L.total))) return rc;
   {
     ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
     if (ce != cudaSuccess) return cuda_fail(ce, "hb_ppo_actor_grad(memset split buffer)");
   }
+  const bool rnn = d->rnn_layers != 0;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, b->obs, b->index, c0, n, rnn ? &seq : nullptr, w, st, &feat))) return rc;
     HeadArgs a;
     head_base(d, Q, prepared, &a);
     head_batch(d, b, c0, n, &a);
-    a.feat = w.Y[Q.n_layers - 1];
+    a.feat = feat;
     a.agg_prod = h->action_aggregation_prod;
     a.clip = h->clip_param;
     a.entropy_coef = h->entropy_coef;
@@ -317,8 +399,14 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
     a.scalars = scalars;
     a.ln_z = w.Z[Q.n_layers - 1]; a.ln_stats = w.stats[Q.n_layers - 1]; a.ln_w = prepared + Q.lnw[Q.n_layers - 1];
     a.g_ln_w = grad + P.lnw[Q.n_layers - 1]; a.g_ln_b = grad + P.lnb[Q.n_layers - 1]; a.ln_act = d->activation;
+    if (rnn) {  // the head's input is LayerNorm(GRU output): fuse that LN's backward (identity activation) instead
+      a.dfeat = w.rnn.dtop;
+      a.ln_z = w.rnn.hs[d->rnn_layers - 1]; a.ln_stats = w.rnn.stats; a.ln_w = prepared + Q.rnn_lnw;
+      a.g_ln_w = grad + P.rnn_lnw; a.g_ln_b = grad + P.rnn_lnb; a.ln_act = HB_ACT_IDENTITY;
+    }
     a.part_delta = w.dwpart - grad; a.part_stride = w.ptotal;
     if ((rc = launch_policy_head(d->head, MODE_GRAD, a, st))) return rc;
+    if (rnn && (rc = rnn_to_trunk_backward(d, P, Q, params, prepared, grad, n, &seq, w, st))) return rc;
     if ((rc = trunk_backward(d, P, Q, params, prepared, grad, n, w, st))) return rc;
   }
   if ((rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
@@ -341,19 +429,22 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_value_grad(memset)");
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 1, ws, ws_bytes, &w, L.total))) return rc;
   {
     ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
     if (ce != cudaSuccess) return cuda_fail(ce, "hb_value_grad(memset split buffer)");
   }
+  const bool rnn = d->rnn_layers != 0;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, b->share_obs, b->index, c0, n, w, st))) return rc;
+    SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, b->share_obs, b->index, c0, n, rnn ? &seq : nullptr, w, st, &feat))) return rc;
     ValueArgs a;
     memset(&a, 0, sizeof(a));
-    a.feat = w.Y[Q.n_layers - 1];
+    a.feat = feat;
     a.h = Q.n[Q.n_layers - 1];
     a.hw = prepared + Q.hw;
     a.hbias = prepared + Q.hbias;
@@ -374,8 +465,14 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
     a.scalars = scalars;
     a.ln_z = w.Z[Q.n_layers - 1]; a.ln_stats = w.stats[Q.n_layers - 1]; a.ln_w = prepared + Q.lnw[Q.n_layers - 1];
     a.g_ln_w = grad + P.lnw[Q.n_layers - 1]; a.g_ln_b = grad + P.lnb[Q.n_layers - 1]; a.ln_act = d->activation;
+    if (rnn) {
+      a.dfeat = w.rnn.dtop;
+      a.ln_z = w.rnn.hs[d->rnn_layers - 1]; a.ln_stats = w.rnn.stats; a.ln_w = prepared + Q.rnn_lnw;
+      a.g_ln_w = grad + P.rnn_lnw; a.g_ln_b = grad + P.rnn_lnb; a.ln_act = HB_ACT_IDENTITY;
+    }
     a.part_delta = w.dwpart - grad; a.part_stride = w.ptotal;
     if ((rc = launch_value_head(1, a, st))) return rc;
+    if (rnn && (rc = rnn_to_trunk_backward(d, P, Q, params, prepared, grad, n, &seq, w, st))) return rc;
     if ((rc = trunk_backward(d, P, Q, params, prepared, grad, n, w, st))) return rc;
   }
   if ((rc = launch_dw_reduce(grad, w.dwpart, L.total, st))) return rc;
@@ -388,6 +485,13 @@ struct TrpoExtra { float* tprep; float* yd[2]; };
 
 size_t trpo_extra_floats(const hb::PrepLayout& Q, int64_t ch) {
   return (size_t)hb::round_up(Q.tk[0], 4) + 2 * (size_t)ch * hb::hmax_of(Q);
+}
+
+// the tangent pass does not cover the GRU yet: HATRPO with recurrent policies fails loudly
+int trpo_no_rnn(const hb_net_desc* d) {
+  if (!d->rnn_layers) return HB_OK;
+  hb::set_error("the trust-region (HATRPO) kernels do not cover recurrent (GRU) policies in this build");
+  return HB_ERR_UNSUPPORTED;
 }
 }  // namespace
 
@@ -407,6 +511,7 @@ int hb_trpo_old_dist(const hb_net_desc* d, const float* prepared, const hb_actor
   PrepLayout Q;
   int rc = check_net(d, nullptr, &Q, nullptr, 1);
   if (rc) return rc;
+  if ((rc = trpo_no_rnn(d))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
@@ -441,6 +546,7 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
   hb_net_layout L;
   int rc = check_net(d, &P, &Q, &L, 1);
   if (rc) return rc;
+  if ((rc = trpo_no_rnn(d))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t ce = cudaMemsetAsync(out, 0, (size_t)L.total * sizeof(float), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_trpo_fvp(memset)");
@@ -524,6 +630,7 @@ int hb_trpo_eval(const hb_net_desc* d, const float* prepared, const hb_actor_bat
   PrepLayout Q;
   int rc = check_net(d, &P, &Q, nullptr, 1);
   if (rc) return rc;
+  if ((rc = trpo_no_rnn(d))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;

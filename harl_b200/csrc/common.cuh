@@ -46,6 +46,10 @@ struct PrepLayout {
   int k[HB_MAX_LAYERS], kpad[HB_MAX_LAYERS], n[HB_MAX_LAYERS];
   int wt[HB_MAX_LAYERS], bias[HB_MAX_LAYERS], lnw[HB_MAX_LAYERS], lnb[HB_MAX_LAYERS];
   int hw, hbias, log_std;
+  // GRU (rnn.py:8-81), rnn_layers > 0: per layer W_ih^T and W_hh^T as [h][3h] (gate order r, z, n), the two bias
+  // vectors [3h], then the output LayerNorm affine
+  int rnn_layers, rh;
+  int rnn_wih_t[2], rnn_whh_t[2], rnn_bih[2], rnn_bhh[2], rnn_lnw, rnn_lnb;
   // tcgen05 operand images (tc_gemm.cu): per layer, per 32-wide k-chunk: hi image [nt][32] then lo image
   int tk[HB_MAX_LAYERS], tk_chunks[HB_MAX_LAYERS], tk_nt[HB_MAX_LAYERS];
   // images of W^T for the backward dX GEMM (layers >= 1)
@@ -58,6 +62,7 @@ struct ParamLayout {
   int fn_w, fn_b;  // feature norm (-1 if absent)
   int w[HB_MAX_LAYERS], b[HB_MAX_LAYERS], lnw[HB_MAX_LAYERS], lnb[HB_MAX_LAYERS];
   int hw, hbias, log_std;  // head
+  int rnn_wih[2], rnn_whh[2], rnn_bih[2], rnn_bhh[2], rnn_lnw, rnn_lnb;  // GRU [3h][h] x2, [3h] x2 per layer; LN
   int total;
 };
 

@@ -76,14 +76,14 @@ int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_l
     prev = h;
   }
   for (int r = 0; r < d->rnn_layers; ++r) {
-    snprintf(nm, sizeof nm, "rnn.rnn.weight_ih_l%d", r); add_tensor(out, &cur, nm, 3 * prev, prev);
-    snprintf(nm, sizeof nm, "rnn.rnn.weight_hh_l%d", r); add_tensor(out, &cur, nm, 3 * prev, prev);
-    snprintf(nm, sizeof nm, "rnn.rnn.bias_ih_l%d", r); add_tensor(out, &cur, nm, 1, 3 * prev);
-    snprintf(nm, sizeof nm, "rnn.rnn.bias_hh_l%d", r); add_tensor(out, &cur, nm, 1, 3 * prev);
+    snprintf(nm, sizeof nm, "rnn.rnn.weight_ih_l%d", r); P.rnn_wih[r] = add_tensor(out, &cur, nm, 3 * prev, prev);
+    snprintf(nm, sizeof nm, "rnn.rnn.weight_hh_l%d", r); P.rnn_whh[r] = add_tensor(out, &cur, nm, 3 * prev, prev);
+    snprintf(nm, sizeof nm, "rnn.rnn.bias_ih_l%d", r); P.rnn_bih[r] = add_tensor(out, &cur, nm, 1, 3 * prev);
+    snprintf(nm, sizeof nm, "rnn.rnn.bias_hh_l%d", r); P.rnn_bhh[r] = add_tensor(out, &cur, nm, 1, 3 * prev);
   }
   if (d->rnn_layers) {
-    add_tensor(out, &cur, "rnn.norm.weight", 1, prev);
-    add_tensor(out, &cur, "rnn.norm.bias", 1, prev);
+    P.rnn_lnw = add_tensor(out, &cur, "rnn.norm.weight", 1, prev);
+    P.rnn_lnb = add_tensor(out, &cur, "rnn.norm.bias", 1, prev);
   }
   if (d->head == HB_HEAD_DISCRETE) {
     P.hw = add_tensor(out, &cur, "act.action_out.linear.weight", d->out_dim, prev);
@@ -116,6 +116,15 @@ int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_l
   Q.hw = c;    c += round_up(d->out_dim * prev, 4);
   Q.hbias = c; c += round_up(d->out_dim, 4);
   Q.log_std = c; c += round_up(d->out_dim, 4);
+  Q.rnn_layers = d->rnn_layers;
+  Q.rh = prev;
+  for (int r = 0; r < d->rnn_layers; ++r) {
+    Q.rnn_wih_t[r] = c; c += 3 * prev * prev;
+    Q.rnn_whh_t[r] = c; c += 3 * prev * prev;
+    Q.rnn_bih[r] = c;   c += 3 * prev;
+    Q.rnn_bhh[r] = c;   c += 3 * prev;
+  }
+  if (d->rnn_layers) { Q.rnn_lnw = c; c += prev; Q.rnn_lnb = c; c += prev; }
   for (int l = 0; l < d->n_layers; ++l) {
     Q.tk_nt[l] = tc_nt_of(Q.n[l]);
     Q.tk_chunks[l] = (Q.kpad[l] + 31) / 32;
@@ -167,6 +176,25 @@ __global__ void prepare_kernel(ParamLayout P, PrepLayout Q, int feature_norm, in
   if (i >= Q.hw && i < Q.hw + out_dim * h) { prep[i] = params[P.hw + i - Q.hw]; return; }
   if (i >= Q.hbias && i < Q.hbias + out_dim) { prep[i] = params[P.hbias + i - Q.hbias]; return; }
   if (head == HB_HEAD_BOX && i >= Q.log_std && i < Q.log_std + out_dim) { prep[i] = params[P.log_std + i - Q.log_std]; return; }
+  for (int r = 0; r < Q.rnn_layers; ++r) {
+    const int g3 = 3 * h;
+    if (i >= Q.rnn_wih_t[r] && i < Q.rnn_wih_t[r] + h * g3) {  // [h][3h] <- W_ih [3h][h]
+      int k = (i - Q.rnn_wih_t[r]) / g3, j = (i - Q.rnn_wih_t[r]) % g3;
+      prep[i] = params[P.rnn_wih[r] + j * h + k];
+      return;
+    }
+    if (i >= Q.rnn_whh_t[r] && i < Q.rnn_whh_t[r] + h * g3) {
+      int k = (i - Q.rnn_whh_t[r]) / g3, j = (i - Q.rnn_whh_t[r]) % g3;
+      prep[i] = params[P.rnn_whh[r] + j * h + k];
+      return;
+    }
+    if (i >= Q.rnn_bih[r] && i < Q.rnn_bih[r] + g3) { prep[i] = params[P.rnn_bih[r] + i - Q.rnn_bih[r]]; return; }
+    if (i >= Q.rnn_bhh[r] && i < Q.rnn_bhh[r] + g3) { prep[i] = params[P.rnn_bhh[r] + i - Q.rnn_bhh[r]]; return; }
+  }
+  if (Q.rnn_layers) {
+    if (i >= Q.rnn_lnw && i < Q.rnn_lnw + h) { prep[i] = params[P.rnn_lnw + i - Q.rnn_lnw]; return; }
+    if (i >= Q.rnn_lnb && i < Q.rnn_lnb + h) { prep[i] = params[P.rnn_lnb + i - Q.rnn_lnb]; return; }
+  }
   prep[i] = 0.f;
 }
 

@@ -1,0 +1,276 @@
+// GRU layer of the recurrent policies / critics (sm_100a): RNNLayer, harl/models/base/rnn.py:8-81.
+//
+// A recurrent batch is S steps x B sequences, rows step-major (row = s * B + j) -- the layout of the reference's
+// sequence branch ([T*N, h] time-major, rnn.py:33-78) and of its chunk generators (Appendix D of SURVEY.md).
+// The reference splits the sequence at reset steps and lets cuDNN/ATen run each segment; that is an optimisation
+// of "h <- h * mask_t before every step" (verified bit-identical on CPU), which is what runs here.
+//
+// Per layer: the input projection of ALL steps is one GEMM (gi = X W_ih^T + b_ih over S*B rows); the recurrence is
+// S x (gh = hm W_hh^T + b_hh on B rows, then one elementwise gate kernel that also writes the masked state the next
+// step multiplies).  Backward mirrors it: S x (gate backward, dhm += dgh W_hh), then the weight gradients and the
+// input gradient as three GEMMs over all S*B rows.  The output LayerNorm is a row-wise kernel; its backward is
+// fused into the head kernels (identity activation).  FP32 FFMA tiles (gemm_tile.cuh): the per-step GEMMs are
+// [B, h] x [h, 3h] with h <= 256 -- latency-bound, not tensor-pipe work.
+#include <math.h>
+
+#include "common.cuh"
+#include "gemm_tile.cuh"
+#include "kernels.cuh"
+#include "rnn.cuh"
+#include "row_helpers.cuh"
+
+namespace hb {
+
+// ------------------------------------------------------------------ Y (+)= X B + bias, any N (multiple of 4)
+template <int NT, bool ACCUM>
+__global__ void __launch_bounds__(256) linear_plain_kernel(const float* __restrict__ X, int ldx,
+                                                           const float* __restrict__ Bm, int ldb,
+                                                           const float* __restrict__ bias, float* __restrict__ Y, int ldy,
+                                                           int64_t M, int N, int Kred) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GemmSmem<NT>& s = *reinterpret_cast<GemmSmem<NT>*>(smem_raw);
+  constexpr int NCH = NT / 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * NT;
+  float acc[4][NT / 16];
+  gemm_mainloop<NT, true>(X, ldx, Bm + n0, ldb, M, Kred, N - n0, row0, s, acc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = row0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int n = n0 + c * 64 + tx * 4;
+      if (n >= N) continue;
+      float4 o = make_float4(acc[i][c * 4 + 0], acc[i][c * 4 + 1], acc[i][c * 4 + 2], acc[i][c * 4 + 3]);
+      if (bias != nullptr) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + n);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      float4* dst = reinterpret_cast<float4*>(Y + row * ldy + n);
+      if (ACCUM) { const float4 y = *dst; o.x += y.x; o.y += y.y; o.z += y.z; o.w += y.w; }
+      *dst = o;
+    }
+  }
+}
+
+int launch_linear_plain(const float* X, int ldx, const float* Bm, int ldb, const float* bias, float* Y, int ldy,
+                        int64_t M, int N, int Kred, bool accumulate, cudaStream_t st) {
+  if (M <= 0) return HB_OK;
+  constexpr int NT = 128;
+  const size_t smem = sizeof(GemmSmem<NT>);
+  dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)((N + NT - 1) / NT));
+  if (accumulate) linear_plain_kernel<NT, true><<<grid, 256, smem, st>>>(X, ldx, Bm, ldb, bias, Y, ldy, M, N, Kred);
+  else linear_plain_kernel<NT, false><<<grid, 256, smem, st>>>(X, ldx, Bm, ldb, bias, Y, ldy, M, N, Kred);
+  HB_LAUNCH_DONE(st, shape_label("rnn_linear", M, N, Kred));
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------ per-row mask gather + initial state
+// mrow[r] = masks[src(r)];  hm0[j][:] = h0[src(j)][layer][:] * mrow[j]   (rnn.py:27-31, 60-70)
+__global__ void rnn_mask_rows_kernel(const float* __restrict__ masks, const int32_t* __restrict__ index, int64_t M,
+                                     float* __restrict__ mrow) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < M) mrow[r] = masks[index ? (int64_t)index[r] : r];
+}
+
+__global__ void rnn_init_state_kernel(const float* __restrict__ h0, const int32_t* __restrict__ index, int layer,
+                                      int layers, int h, int64_t B, const float* __restrict__ mrow,
+                                      float* __restrict__ hm0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * h) return;
+  const int64_t j = i / h;
+  const int e = (int)(i % h);
+  const int64_t src = index ? (int64_t)index[j] : j;
+  hm0[i] = h0[(src * layers + layer) * h + e] * mrow[j];
+}
+
+// ------------------------------------------------------------------ gates, forward (PyTorch GRU, gate order r, z, n)
+// r = s(gi_r + gh_r); z = s(gi_z + gh_z); n = tanh(gi_n + r * gh_n); h' = (1 - z) n + z hm
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void gru_gate_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                    const float* __restrict__ hm, int h, int64_t B, float* __restrict__ hs,
+                                    float* __restrict__ gates, const float* __restrict__ mrow_next,
+                                    float* __restrict__ hm_next, float* __restrict__ h_out, int out_stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * h) return;
+  const int64_t b = i / h;
+  const int e = (int)(i % h);
+  const float* gir = gi + b * 3 * h;
+  const float* ghr = gh + b * 3 * h;
+  const float r = sigmoidf_(gir[e] + ghr[e]);
+  const float z = sigmoidf_(gir[h + e] + ghr[h + e]);
+  const float ghn = ghr[2 * h + e];
+  const float n = tanhf(gir[2 * h + e] + r * ghn);
+  const float hp = hm[i];
+  const float hn = (1.f - z) * n + z * hp;
+  hs[i] = hn;
+  if (gates != nullptr) {
+    float* g = gates + b * 4 * h;
+    g[e] = r; g[h + e] = z; g[2 * h + e] = n; g[3 * h + e] = ghn;
+  }
+  if (hm_next != nullptr) hm_next[i] = hn * mrow_next[b];
+  if (h_out != nullptr) h_out[b * out_stride + e] = hn;
+}
+
+// ------------------------------------------------------------------ gates, backward
+// dh = dY_t + dhm_{t+1} * m_{t+1};  writes dgi_t, dgh_t and the direct part dh * z of d/d(hm_t)
+__global__ void gru_gate_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ dhm_next,
+                                    const float* __restrict__ mrow_next, const float* __restrict__ gates,
+                                    const float* __restrict__ hm, int h, int64_t B, float* __restrict__ dgi,
+                                    float* __restrict__ dgh, float* __restrict__ dhm_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * h) return;
+  const int64_t b = i / h;
+  const int e = (int)(i % h);
+  float dh = dY[i];
+  if (dhm_next != nullptr) dh = fmaf(dhm_next[i], mrow_next[b], dh);
+  const float* g = gates + b * 4 * h;
+  const float r = g[e], z = g[h + e], n = g[2 * h + e], ghn = g[3 * h + e];
+  const float hp = hm[i];
+  const float dn_pre = dh * (1.f - z) * (1.f - n * n);
+  const float dz_pre = dh * (hp - n) * z * (1.f - z);
+  const float dr_pre = dn_pre * ghn * r * (1.f - r);
+  float* a = dgi + b * 3 * h;
+  float* c = dgh + b * 3 * h;
+  a[e] = dr_pre; a[h + e] = dz_pre; a[2 * h + e] = dn_pre;
+  c[e] = dr_pre; c[h + e] = dz_pre; c[2 * h + e] = dn_pre * r;
+  dhm_out[i] = dh * z;
+}
+
+// ------------------------------------------------------------------ output LayerNorm (rnn.py:21,80), warp per row
+__global__ void __launch_bounds__(ROW_THREADS) rnn_ln_fwd_kernel(const float* __restrict__ X, const float* __restrict__ lnw,
+                                                                 const float* __restrict__ lnb, float* __restrict__ Y,
+                                                                 float* __restrict__ stats, int64_t rows, int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * ROW_WARPS;
+  const float inv_n = 1.f / (float)N;
+  for (int64_t r = w0; r < rows; r += nw) {
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { int n = lane + 32 * q; v[q] = n < N ? X[r * N + n] : 0.f; s += v[q]; }
+    const float mean = warp_sum(s) * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { int n = lane + 32 * q; if (n < N) { float dlt = v[q] - mean; sq = fmaf(dlt, dlt, sq); } }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_n + 1e-5f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { int n = lane + 32 * q; if (n < N) Y[r * N + n] = (v[q] - mean) * rstd * lnw[n] + lnb[n]; }
+    if (stats != nullptr && lane == 0) { stats[r * 2] = mean; stats[r * 2 + 1] = rstd; }
+  }
+}
+
+// ------------------------------------------------------------------ workspace
+size_t rnn_work_floats(const PrepLayout& Q, int64_t M, int grad) {
+  if (!Q.rnn_layers) return 0;
+  const size_t h = Q.rh, m = (size_t)M, R = Q.rnn_layers;
+  size_t f = (m + 3) / 4 * 4;                                           // mrow
+  f += R * (m * 3 * h + m * h + m * h);                                 // gi, hm, hs per layer
+  f += m * 3 * h;                                                       // gh scratch (B <= M rows)
+  f += m * h + (size_t)round_up((int)(2 * M), 4);                       // out, stats
+  if (grad) f += R * m * 4 * h + 2 * m * 3 * h + 2 * m * h + 3 * m * h; // gates; dgi, dgh; dhm x2; dtop, dxA, dxB
+  return f;
+}
+
+int carve_rnn(const PrepLayout& Q, int64_t M, int grad, float* p, RnnWork* w) {
+  memset(w, 0, sizeof(*w));
+  if (!Q.rnn_layers) return HB_OK;
+  const size_t h = Q.rh, m = (size_t)M;
+  w->mrow = p; p += round_up((int)M, 4);
+  for (int l = 0; l < Q.rnn_layers; ++l) {
+    w->gi[l] = p; p += m * 3 * h;
+    w->hm[l] = p; p += m * h;
+    w->hs[l] = p; p += m * h;
+  }
+  w->gh = p; p += m * 3 * h;
+  w->out = p; p += m * h;
+  w->stats = p; p += round_up((int)(2 * M), 4);
+  if (grad) {
+    for (int l = 0; l < Q.rnn_layers; ++l) { w->gates[l] = p; p += m * 4 * h; }
+    w->dgi = p; p += m * 3 * h;
+    w->dgh = p; p += m * 3 * h;
+    w->dhm[0] = p; p += m * h;
+    w->dhm[1] = p; p += m * h;
+    w->dtop = p; p += m * h;
+    w->dx[0] = p; p += m * h;
+    w->dx[1] = p; p += m * h;
+  }
+  return HB_OK;
+}
+
+static inline unsigned ew_grid(int64_t n) { return (unsigned)ceil_div64(n, 256); }
+
+// ------------------------------------------------------------------ forward over S steps x B sequences
+int rnn_forward(const PrepLayout& Q, const float* prep, const float* X, int64_t S, int64_t B, const float* h0,
+                const float* masks, const int32_t* index, float* h_out, const RnnWork& w, cudaStream_t st) {
+  const int h = Q.rh, R = Q.rnn_layers;
+  const int64_t M = S * B;
+  rnn_mask_rows_kernel<<<ew_grid(M), 256, 0, st>>>(masks, index, M, w.mrow);
+  HB_LAUNCH_DONE(st, "rnn_mask_rows");
+  const float* xin = X;
+  int rc;
+  for (int l = 0; l < R; ++l) {
+    if ((rc = launch_linear_plain(xin, h, prep + Q.rnn_wih_t[l], 3 * h, prep + Q.rnn_bih[l], w.gi[l], 3 * h, M, 3 * h, h,
+                                  false, st)))
+      return rc;
+    rnn_init_state_kernel<<<ew_grid(B * h), 256, 0, st>>>(h0, index, l, R, h, B, w.mrow, w.hm[l]);
+    HB_LAUNCH_DONE(st, "rnn_init_state");
+    for (int64_t t = 0; t < S; ++t) {
+      const float* hm_t = w.hm[l] + t * B * h;
+      if ((rc = launch_linear_plain(hm_t, h, prep + Q.rnn_whh_t[l], 3 * h, prep + Q.rnn_bhh[l], w.gh, 3 * h, B, 3 * h, h,
+                                    false, st)))
+        return rc;
+      const bool last = t + 1 == S;
+      gru_gate_fwd_kernel<<<ew_grid(B * h), 256, 0, st>>>(
+          w.gi[l] + t * B * 3 * h, w.gh, hm_t, h, B, w.hs[l] + t * B * h,
+          w.gates[l] ? w.gates[l] + t * B * 4 * h : nullptr, last ? nullptr : w.mrow + (t + 1) * B,
+          last ? nullptr : w.hm[l] + (t + 1) * B * h, (last && h_out) ? h_out + (int64_t)l * h : nullptr, R * h);
+      HB_LAUNCH_DONE(st, "rnn_gru_gate_fwd");
+    }
+    xin = w.hs[l];
+  }
+  rnn_ln_fwd_kernel<<<row_grid(M), ROW_THREADS, 0, st>>>(w.hs[R - 1], prep + Q.rnn_lnw, prep + Q.rnn_lnb, w.out, w.stats, M, h);
+  HB_LAUNCH_DONE(st, shape_label("rnn_ln_fwd", M, h, 0));
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------ backward (BPTT) given w.dtop = d loss / d hs[R-1]
+// X: the layer-0 input sequence (trunk output).  Writes d loss / d X to *dX_out (one of w.dx[]).
+int rnn_backward(const ParamLayout& P, const PrepLayout& Q, const float* params, const float* X, int64_t S, int64_t B,
+                 float* grad, const RnnWork& w, float** dX_out, cudaStream_t st) {
+  const int h = Q.rh, R = Q.rnn_layers;
+  const int64_t M = S * B;
+  const float* dY = w.dtop;
+  int rc;
+  for (int l = R - 1; l >= 0; --l) {
+    int cur = 0;
+    for (int64_t t = S - 1; t >= 0; --t) {
+      const bool last = t + 1 == S;
+      float* dhm_t = w.dhm[cur ^ 1];
+      gru_gate_bwd_kernel<<<ew_grid(B * h), 256, 0, st>>>(
+          dY + t * B * h, last ? nullptr : w.dhm[cur], last ? nullptr : w.mrow + (t + 1) * B,
+          w.gates[l] + t * B * 4 * h, w.hm[l] + t * B * h, h, B, w.dgi + t * B * 3 * h, w.dgh + t * B * 3 * h, dhm_t);
+      HB_LAUNCH_DONE(st, "rnn_gru_gate_bwd");
+      // d/d(hm_t) += dgh_t W_hh   (W_hh [3h][h] as stored)
+      if (t > 0) {
+        if ((rc = launch_linear_plain(w.dgh + t * B * 3 * h, 3 * h, params + P.rnn_whh[l], h, nullptr, dhm_t, h, B, h,
+                                      3 * h, true, st)))
+          return rc;
+      }
+      cur ^= 1;
+    }
+    const float* xin = l == 0 ? X : w.hs[l - 1];
+    if ((rc = launch_dw_accum(w.dgh, 3 * h, w.hm[l], h, h, grad + P.rnn_whh[l], grad + P.rnn_bhh[l], M, st))) return rc;
+    if ((rc = launch_dw_accum(w.dgi, 3 * h, xin, h, h, grad + P.rnn_wih[l], grad + P.rnn_bih[l], M, st))) return rc;
+    float* dx = w.dx[l & 1];
+    if ((rc = launch_linear_plain(w.dgi, 3 * h, params + P.rnn_wih[l], h, nullptr, dx, h, M, h, 3 * h, false, st))) return rc;
+    dY = dx;
+    *dX_out = dx;
+  }
+  return HB_OK;
+}
+
+}  // namespace hb

@@ -184,35 +184,54 @@ class DeviceNet:
         ws = workspace(self.device, n)
         return ws, ws.numel()
 
-    def act(self, obs, avail, deterministic, seed, offset, actions_out, logp_out):
+    @property
+    def recurrent(self):
+        return self.desc.rnn_layers > 0
+
+    def act(self, obs, avail, deterministic, seed, offset, actions_out, logp_out, rnn_states=None, masks=None,
+            rnn_out=None):
         self._need_cuda()
         rows = obs.shape[0]
         ws, n = self._ws(rows, 0)
+        if self.recurrent:
+            L.call("hb_policy_act_rnn", C.byref(self.desc), L.ptr(self.prepared), L.ptr(obs), rows, L.ptr(avail),
+                   L.ptr(rnn_states), L.ptr(masks), int(bool(deterministic)), int(seed) & (2**64 - 1),
+                   int(offset) & (2**64 - 1), L.ptr(actions_out), L.ptr(logp_out), L.ptr(rnn_out), L.ptr(ws), n,
+                   L.stream_ptr())
+            return
         L.call("hb_policy_act", C.byref(self.desc), L.ptr(self.prepared), L.ptr(obs), rows, L.ptr(avail),
                int(bool(deterministic)), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), L.ptr(actions_out),
                L.ptr(logp_out), L.ptr(ws), n, L.stream_ptr())
 
-    def values(self, cent_obs, values_out):
+    def values(self, cent_obs, values_out, rnn_states=None, masks=None, rnn_out=None):
         self._need_cuda()
         rows = cent_obs.shape[0]
         ws, n = self._ws(rows, 0)
+        if self.recurrent:
+            L.call("hb_value_forward_rnn", C.byref(self.desc), L.ptr(self.prepared), L.ptr(cent_obs), rows,
+                   L.ptr(rnn_states), L.ptr(masks), L.ptr(values_out), L.ptr(rnn_out), L.ptr(ws), n, L.stream_ptr())
+            return
         L.call("hb_value_forward", C.byref(self.desc), L.ptr(self.prepared), L.ptr(cent_obs), rows,
                L.ptr(values_out), L.ptr(ws), n, L.stream_ptr())
 
     @staticmethod
-    def actor_batch(obs, actions, old_logp=None, adv=None, factor=None, active=None, avail=None, index=None, rows=None):
+    def actor_batch(obs, actions, old_logp=None, adv=None, factor=None, active=None, avail=None, index=None, rows=None,
+                    rnn_states=None, masks=None, seq_len=0):
+        """``rnn_states`` / ``masks`` / ``seq_len``: recurrent policies only (see hb_actor_batch)."""
         b = L.ActorBatch()
         b.obs, b.actions, b.old_logp, b.adv = L.ptr(obs), L.ptr(actions), L.ptr(old_logp), L.ptr(adv)
         b.factor, b.active, b.avail, b.index = L.ptr(factor), L.ptr(active), L.ptr(avail), L.ptr(index)
         b.rows = int(rows if rows is not None else (index.shape[0] if index is not None else actions.shape[0]))
-        b._keep = (obs, actions, old_logp, adv, factor, active, avail, index)  # the struct holds raw pointers only
+        b.rnn_states, b.masks, b.seq_len = L.ptr(rnn_states), L.ptr(masks), int(seq_len)
+        b._keep = (obs, actions, old_logp, adv, factor, active, avail, index, rnn_states, masks)  # raw pointers only
         return b
 
     @staticmethod
-    def critic_batch(share_obs, value_preds, returns, index=None, rows=None):
+    def critic_batch(share_obs, value_preds, returns, index=None, rows=None, rnn_states=None, masks=None, seq_len=0):
         b = L.CriticBatch(L.ptr(share_obs), L.ptr(value_preds), L.ptr(returns), L.ptr(index),
-                          int(rows if rows is not None else (index.shape[0] if index is not None else value_preds.numel())))
-        b._keep = (share_obs, value_preds, returns, index)
+                          int(rows if rows is not None else (index.shape[0] if index is not None else value_preds.numel())),
+                          L.ptr(rnn_states), L.ptr(masks), int(seq_len))
+        b._keep = (share_obs, value_preds, returns, index, rnn_states, masks)
         return b
 
     def evaluate(self, batch, logp_out=None, logp_ref=None, factor_inout=None, agg_prod=True):

@@ -312,21 +312,29 @@ class OnPolicyBaseRunner:
     def collect(self, step):
         """Actions / log-probs / values for one rollout step, written straight into slot ``step``
         of the buffers (reference :285-340).  Returns the reference 5-tuple as device tensors."""
+        new_rnn = []
         for a in range(self.num_agents):
             b = self.actor_buffer[a]
-            self.actor[a].get_actions(b.obs[step], b.rnn_states[step], b.masks[step],
-                                      b.available_actions[step] if b.available_actions is not None else None,
-                                      actions_out=b.actions[step], logp_out=b.action_log_probs[step])
+            _, _, rnn_a = self.actor[a].get_actions(b.obs[step], b.rnn_states[step], b.masks[step],
+                                                    b.available_actions[step] if b.available_actions is not None else None,
+                                                    actions_out=b.actions[step], logp_out=b.action_log_probs[step])
+            new_rnn.append(rnn_a)
         actions = torch.stack([b.actions[step] for b in self.actor_buffer], dim=1)
         action_log_probs = torch.stack([b.action_log_probs[step] for b in self.actor_buffer], dim=1)
-        rnn_states = torch.stack([b.rnn_states[step] for b in self.actor_buffer], dim=1) \
-            if self.actor_buffer[0].recurrent else None
+        rnn_states = torch.stack(new_rnn, dim=1) if self.actor_buffer[0].recurrent else None  # the GRUs' new states
         cb = self.critic_buffer
         sd = cb.share_obs.shape[-1]
-        values, _ = self.critic.get_values(cb.share_obs[step].reshape(-1, sd), None, None,
-                                           values_out=cb.value_preds[step].reshape(-1, 1))
+        if cb.recurrent:
+            R, h = cb.rnn_states_critic.shape[-2:]
+            values, rnn_c = self.critic.get_values(cb.share_obs[step].reshape(-1, sd),
+                                                   cb.rnn_states_critic[step].reshape(-1, R, h), cb.masks[step].reshape(-1, 1),
+                                                   values_out=cb.value_preds[step].reshape(-1, 1))
+            rnn_states_critic = rnn_c.reshape(cb.rnn_states_critic[step].shape)
+        else:
+            self.critic.get_values(cb.share_obs[step].reshape(-1, sd), None, None,
+                                   values_out=cb.value_preds[step].reshape(-1, 1))
+            rnn_states_critic = None
         values = cb.value_preds[step]
-        rnn_states_critic = cb.rnn_states_critic[step] if cb.recurrent else None
         self._in_place = (actions, action_log_probs)  # already sitting in their buffer slots
         return values, actions, action_log_probs, rnn_states, rnn_states_critic
 
@@ -385,7 +393,12 @@ class OnPolicyBaseRunner:
         """Bootstrap value of slot T, then the GAE / return kernel (reference :462-484)."""
         cb = self.critic_buffer
         sd = cb.share_obs.shape[-1]
-        next_value, _ = self.critic.get_values(cb.share_obs[-1].reshape(-1, sd), None, None)
+        if cb.recurrent:
+            R, h = cb.rnn_states_critic.shape[-2:]
+            next_value, _ = self.critic.get_values(cb.share_obs[-1].reshape(-1, sd),
+                                                   cb.rnn_states_critic[-1].reshape(-1, R, h), cb.masks[-1].reshape(-1, 1))
+        else:
+            next_value, _ = self.critic.get_values(cb.share_obs[-1].reshape(-1, sd), None, None)
         cb.compute_returns(next_value, self.value_normalizer)
 
     def train(self):
@@ -406,17 +419,26 @@ class OnPolicyBaseRunner:
         n = self.algo_args["eval"]["n_eval_rollout_threads"]
         eval_episode = 0
         obs, share_obs, avail = self.eval_envs.reset()
+        rec = self.actor_buffer[0].recurrent
+        eval_rnn = [torch.zeros(n, self.recurrent_n, self.rnn_hidden_size, device=self.device) for _ in range(self.num_agents)] \
+            if rec else [None] * self.num_agents
+        eval_masks = torch.ones(n, 1, device=self.device) if rec else None
         while True:
             acts = []
             obs_t = torch.as_tensor(obs, device=self.device)
             for a in range(self.num_agents):
                 av = None if avail is None else torch.as_tensor(avail, device=self.device)[:, a].contiguous()
-                act, _ = self.actor[a].act(obs_t[:, a].contiguous(), None, None, av, deterministic=True)
+                act, eval_rnn[a] = self.actor[a].act(obs_t[:, a].contiguous(), eval_rnn[a], eval_masks, av, deterministic=True)
                 acts.append(act)
             actions = torch.stack(acts, dim=1)
             obs, share_obs, rewards, dones, infos, avail = self.eval_envs.step(actions)
             self.logger.eval_per_step((obs, share_obs, rewards, dones, infos, avail))
             dones_env = _t2n(torch.as_tensor(dones)).all(axis=1)
+            if rec:  # finished envs restart from a zero state (reference :560-575)
+                done_t = torch.as_tensor(dones_env, device=self.device)
+                for a in range(self.num_agents):
+                    eval_rnn[a][done_t] = 0.0
+                eval_masks = (~done_t).float().reshape(n, 1)
             for i in range(n):
                 if dones_env[i]:
                     eval_episode += 1

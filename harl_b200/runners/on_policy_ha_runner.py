@@ -53,7 +53,12 @@ class OnPolicyHARunner(OnPolicyBaseRunner):
             buf.update_factor(factor)
             fl = lambda a: a.reshape(rows, *a.shape[2:])
             avail = None if buf.available_actions is None else fl(buf.available_actions[:-1])
-            sweep = DeviceNet.actor_batch(fl(buf.obs[:-1]), fl(buf.actions), avail=avail)
+            if actor.recurrent:  # full-buffer evaluate from rnn_states[0] (on_policy_ha_runner.py:66-83)
+                sweep = DeviceNet.actor_batch(fl(buf.obs[:-1]), fl(buf.actions), avail=avail,
+                                              rnn_states=buf.rnn_states.reshape((T + 1) * N, -1),
+                                              masks=buf.masks.reshape((T + 1) * N), seq_len=T)
+            else:
+                sweep = DeviceNet.actor_batch(fl(buf.obs[:-1]), fl(buf.actions), avail=avail)
             old_logp = torch.empty(rows, actor.actor.act_width, dtype=torch.float32, device=dev)
             actor.actor.evaluate(sweep, logp_out=old_logp)                       # :66-83
             adv_a = advantages if self.state_type == "EP" else advantages[:, :, agent_id].contiguous()

@@ -220,6 +220,13 @@ typedef struct hb_actor_batch {
   const float* avail;        /* [R, n_act] or NULL */
   const int32_t* index;      /* [rows] or NULL */
   int64_t rows;
+  /* recurrent policies only (RNNLayer sequence branch, rnn.py:33-78; generators of Appendix D): the batch is
+   * seq_len steps x (rows / seq_len) sequences, rows step-major (row = s * B + j).  rnn_states is the buffer's
+   * [R, recurrent_n * h] array: sequence j starts from buffer row (index ? index[j] : j); masks [R] multiplies
+   * the state before every step. */
+  const float* rnn_states;
+  const float* masks;
+  int64_t seq_len;
 } hb_actor_batch;
 
 /* StochasticPolicy.evaluate_actions over buffer rows (the old/new log-prob sweeps of
@@ -252,6 +259,9 @@ typedef struct hb_critic_batch {
   const float* returns;      /* [R] */
   const int32_t* index;      /* nullable */
   int64_t rows;
+  const float* rnn_states;   /* recurrent critics: as in hb_actor_batch */
+  const float* masks;
+  int64_t seq_len;
 } hb_critic_batch;
 
 /* VCritic.update forward + cal_value_loss + backward, v_critic.py:75-146.
@@ -273,6 +283,17 @@ typedef struct hb_adam_hyper {
 int hb_clip_adam_step(const hb_net_desc* d, float* params, const float* grad, float* exp_avg,
                       float* exp_avg_sq, float* prepared, const hb_adam_hyper* h,
                       float* grad_norm_out, void* stream);
+
+/* ---- recurrent (GRU) networks: one rollout step, rnn.py:24-32 ------------------------------------------ *
+ * rnn_states [rows, recurrent_n * h] and masks [rows] are the buffer slot of this step; the new hidden state goes
+ * to rnn_states_out [rows, recurrent_n * h] (StochasticPolicy.forward / VNet.forward return value). */
+int hb_policy_act_rnn(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows,
+                      const float* avail, const float* rnn_states, const float* masks, int deterministic,
+                      uint64_t seed, uint64_t offset, float* actions, float* logp, float* rnn_states_out,
+                      void* ws, size_t ws_bytes, void* stream);
+int hb_value_forward_rnn(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows,
+                         const float* rnn_states, const float* masks, float* values, float* rnn_states_out,
+                         void* ws, size_t ws_bytes, void* stream);
 
 /* ---- trust-region (HATRPO) update: harl/algorithms/actors/hatrpo.py:37-194, harl/utils/trpo_util.py ------- *
  * The surrogate gradient is hb_ppo_actor_grad with use_clip = 0 and entropy_coef = 0 (it returns the gradient of

@@ -107,6 +107,27 @@ def check_iteration(runner, tol_w=3e-5, tol_info=2e-4):
             assert np.array_equal(abufs[a]["active_masks"][t + 1], active[:, a]), "active_masks differ"
         assert np.array_equal(cbuf["masks"][t + 1], masks[:, 0] if runner.state_type == "EP" else masks)
         assert np.array_equal(cbuf["bad_masks"][t + 1], bad)
+    # ---- recurrent nets: every stored hidden state is one oracle GRU step from the previous slot (zero after a reset)
+    if runner.actor_buffer[0].recurrent:
+        from oracle import nets as on
+
+        cfg_m = {**runner.algo_args["model"], **runner.algo_args["algo"]}
+        _, _, actors_s, critic_s, _ = snap
+        tt = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+        with torch.no_grad():
+            for t in range(T):
+                for a in range(runner.num_agents):
+                    b = abufs[a]
+                    _, hx = on.features(actors_s[a]["p"], cfg_m, tt(b["obs"][t]), tt(b["rnn_states"][t]), tt(b["masks"][t]))
+                    want = hx.numpy() * b["masks"][t + 1][:, :, None]
+                    np.testing.assert_allclose(b["rnn_states"][t + 1], want, rtol=0, atol=3e-5,
+                                               err_msg=f"actor {a} hidden state at slot {t + 1}")
+                so, rc, mk = cbuf["share_obs"][t], cbuf["rnn_states_critic"][t], cbuf["masks"][t]
+                sd_, (R_, h_) = so.shape[-1], rc.shape[-2:]
+                _, hx = on.features(critic_s["p"], cfg_m, tt(so.reshape(-1, sd_)), tt(rc.reshape(-1, R_, h_)), tt(mk.reshape(-1, 1)))
+                want = hx.numpy().reshape(rc.shape) * cbuf["masks"][t + 1][..., None]
+                np.testing.assert_allclose(cbuf["rnn_states_critic"][t + 1], want, rtol=0, atol=3e-5,
+                                           err_msg=f"critic hidden state at slot {t + 1}")
     # ---- returns / advantages: bit-exact
     vn = None
     if vn_state is not None:

@@ -109,7 +109,7 @@ def _load_runner_from_golden(g, cfg, m, actor_cls=None):
         ac.actor.load_state_dict(U.params_of(g, f"actor{a}/"))
         r.actor.append(ac)
         b = OnPolicyActorBuffer(cfg, Box(shape=(m["od"],)), act_space, device=dev)
-        for k in ("obs", "actions", "action_log_probs", "masks", "active_masks"):
+        for k in ("obs", "actions", "action_log_probs", "masks", "active_masks") + (("rnn_states",) if b.recurrent else ()):
             getattr(b, k).copy_(torch.from_numpy(g[f"a{a}.{k}"]))
         if b.available_actions is not None:
             b.available_actions.copy_(torch.from_numpy(g[f"a{a}.available_actions"]))
@@ -120,7 +120,7 @@ def _load_runner_from_golden(g, cfg, m, actor_cls=None):
         cb = OnPolicyCriticBufferFP(cfg, Box(shape=(m["sd"],)), A, device=dev)
     else:
         cb = OnPolicyCriticBufferEP(cfg, Box(shape=(m["sd"],)), device=dev)
-    for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks"):
+    for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks") + (("rnn_states_critic",) if cb.recurrent else ()):
         getattr(cb, k).copy_(torch.from_numpy(g["c." + k]))
     r.critic_buffer = cb
     r.value_normalizer = ValueNorm(1, device=dev)
@@ -149,18 +149,6 @@ def test_reference_ha_train_golden(name):
     for k, v in r.critic.critic.state_dict().items():
         np.testing.assert_allclose(v.cpu().numpy(), g["out.critic/" + k], rtol=0, atol=3e-5, err_msg=k)
     np.testing.assert_allclose(r.value_normalizer.state.cpu().numpy(), g["out.vn"], rtol=1e-5)
-
-
-def test_unsupported_recurrent_fails_loudly():
-    from harl_b200.runners import RUNNER_REGISTRY
-
-    args, algo_args, env_args = small_config()
-    algo_args["model"]["use_recurrent_policy"] = True
-    runner = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
-    runner.warmup()
-    with pytest.raises(NotImplementedError):
-        runner.collect(0)
-    runner.close()
 
 
 @pytest.mark.parametrize("action_type,state_type,simple", [("Discrete", "EP", True), ("Box", "FP", False), ("Discrete", "FP", False)])
