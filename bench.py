@@ -46,6 +46,15 @@ WORKLOADS = {
     "C5": dict(desc="HAPPO MAMuJoCo Humanoid-v2 17x1 n_rollout_threads=1024 per GPU T=200",
                env="mamujoco", env_args=dict(scenario="Humanoid-v2", agent_conf="17x1"), n=1024, T=200,
                hidden=[128, 128, 128], algo=dict(clip_param=0.1, entropy_coef=0.0)),
+    # the two halves of BASELINE.json's C4 (HATRPO + GRU is the one combination not built): the trust-region update at
+    # C2 shapes, and GRU policies / FP critic at the synthetic-SMAC shapes.  Secondary workloads (--workload), run with
+    # --no-cpu-baseline --no-e2e.
+    "C2T": dict(desc="HATRPO synthetic-MPE obs_dim=18 act_dim=5 3 agents n_rollout_threads=4096 T=200",
+                env="pettingzoo_mpe", env_args=dict(scenario="simple_spread_v2", continuous_actions=False), n=4096, T=200,
+                hidden=[128, 128], algo={}, algo_name="hatrpo"),
+    "C4R": dict(desc="HAPPO synthetic-SMAC 5 agents obs_dim=128 Discrete(12) n_rollout_threads=2048 T=160 GRU chunk 10, FP critic",
+                env="smac", env_args=dict(map_name="5m_vs_6m"), n=2048, T=160, hidden=[64, 64, 64], algo=dict(gamma=0.95),
+                model=dict(use_recurrent_policy=True, data_chunk_length=10)),
 }
 
 
@@ -53,7 +62,7 @@ def make_args(wl, world, host_env=False, n_override=None):
     from harl_b200.utils.configs_tools import get_defaults_yaml_args
 
     w = WORKLOADS[wl]
-    algo_args, env_args = get_defaults_yaml_args("happo", w["env"])
+    algo_args, env_args = get_defaults_yaml_args(w.get("algo_name", "happo"), w["env"])
     env_args.update(w["env_args"])
     env_args["host"] = host_env
     n = n_override or w["n"]
@@ -62,8 +71,9 @@ def make_args(wl, world, host_env=False, n_override=None):
     algo_args["eval"]["use_eval"] = False
     algo_args["model"]["hidden_sizes"] = list(w["hidden"])
     algo_args["algo"].update(w["algo"])
+    algo_args["model"].update(w.get("model", {}))
     algo_args["logger"]["log_dir"] = tempfile.mkdtemp(prefix="harl_b200_bench_")
-    args = dict(algo="happo", env=w["env"], exp_name="bench", load_config="")
+    args = dict(algo=w.get("algo_name", "happo"), env=w["env"], exp_name="bench", load_config="")
     return args, algo_args, env_args
 
 
@@ -396,7 +406,7 @@ def main():
     base = dict(metric="env-steps/sec (whole box) HAPPO update loop", unit="env-steps/s", n_gpus=a.gpus, steps=a.steps,
                 warmup=a.warmup, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config={"workload": f"{a.workload}: {wl['desc']}", "n_rollout_threads_per_gpu": wl["n"],
-                        "episode_length": T, "algo": "happo",
+                        "episode_length": T, "algo": wl.get("algo_name", "happo"),
                         "l2_policy": "rollout buffers + activations per iteration exceed the 126 MB L2 (no flush needed)"})
 
     if a.impl == "reference":
@@ -425,7 +435,7 @@ def main():
     from harl_b200.runners import RUNNER_REGISTRY
 
     args, algo_args, env_args = make_args(a.workload, world)
-    runner = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+    runner = RUNNER_REGISTRY[args["algo"]](args, algo_args, env_args)
     runner.warmup()
     runner.logger.init(10**9)
     ms, launches, clocks = timed_iterations(runner, a.steps, a.warmup, torch, dist_on, sample_clocks=(rank == 0))
@@ -460,7 +470,7 @@ def main():
     # ---- end to end: host-resident env (pinned H2D of env outputs, D2H of actions, every rollout step)
     if not a.no_e2e:
         args, algo_args, env_args = make_args(a.workload, world, host_env=True)
-        r2 = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+        r2 = RUNNER_REGISTRY[args["algo"]](args, algo_args, env_args)
         r2.warmup()
         r2.logger.init(10**9)
         ms2, _, _ = timed_iterations(r2, max(1, min(a.steps, 3)), 1, torch, dist_on)
