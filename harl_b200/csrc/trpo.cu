@@ -183,7 +183,7 @@ int launch_jvp_linear_ln(int act, const float* X, int ldx, const float* Xd, cons
 // lane j < out holds output j.  Shared memory: hw [out][h], hwd [out][h] (FVP), bias[32], biasd[32], zero[32],
 // grad accumulators [out][h] + [32] (FVP), double scratch.
 template <int HPL, int MAXJ, int HEAD, int MODE>
-__global__ void __launch_bounds__(ROW_THREADS) trpo_head_kernel(TrpoHeadArgs a) {
+__global__ void __launch_bounds__(ROW_THREADS, (HPL * MAXJ <= 32) ? 2 : 1) trpo_head_kernel(TrpoHeadArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int h = a.h, na = a.out;
   float* shw = sm;                                        // [out][h]
@@ -230,12 +230,34 @@ __global__ void __launch_bounds__(ROW_THREADS) trpo_head_kernel(TrpoHeadArgs a) 
   }
   double s_loss = 0.0, s_ent = 0.0, s_ratio = 0.0, s_kl = 0.0;
   const int64_t w0 = (int64_t)blockIdx.x * ROW_WARPS + warp, nw = (int64_t)gridDim.x * ROW_WARPS;
+  // Software pipeline (as in the policy head kernels): the loads of row r + nw are in flight while row r is computed,
+  // so a warp keeps two rows' worth of memory requests outstanding instead of one.
+  struct RowIn { float f[HPL], fd[MODE == TR_FVP ? HPL : 1], zr[MODE == TR_FVP ? HPL : 1]; float mu, rs, od, av; int64_t src; };
+  auto fetch = [&](int64_t r, RowIn& d) {
+    d.src = a.index ? (int64_t)a.index[r] : r;
+    load_feat<HPL>(a.feat + r * h, h, lane, d.f);
+    d.mu = d.rs = d.od = 0.f;
+    d.av = 1.f;
+    if (HEAD == HB_HEAD_DISCRETE && valid && a.avail != nullptr) d.av = a.avail[d.src * na + lane];
+    if constexpr (MODE == TR_FVP) {
+      load_feat<HPL>(a.featd + r * h, h, lane, d.fd);
+      load_feat<HPL>(a.ln_z + r * h, h, lane, d.zr);
+      d.mu = a.ln_stats[r * 2];
+      d.rs = a.ln_stats[r * 2 + 1];
+    }
+    if (MODE != TR_OLD && valid) d.od = a.old_dist[r * na + lane];
+  };
+  RowIn cur, nxt;
+  if (w0 < a.rows) fetch(w0, cur);
   for (int64_t r = w0; r < a.rows; r += nw) {
-    const int64_t src = a.index ? (int64_t)a.index[r] : r;
+    if (r + nw < a.rows) fetch(r + nw, nxt);
+    const int64_t src = cur.src;
     float f[HPL];
-    load_feat<HPL>(a.feat + r * h, h, lane, f);
-    bool masked = false;
-    if (HEAD == HB_HEAD_DISCRETE && valid && a.avail != nullptr) masked = a.avail[src * na + lane] == 0.f;
+#pragma unroll
+    for (int q = 0; q < HPL; ++q) f[q] = cur.f[q];
+    const bool masked = HEAD == HB_HEAD_DISCRETE && valid && cur.av == 0.f;
+    const float od_lane = cur.od;
+    (void)src; (void)od_lane;
     if constexpr (MODE == TR_OLD) {
       float o = head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(f, shw, h, na, sb, lane);
       if (HEAD == HB_HEAD_DISCRETE) {
@@ -247,15 +269,15 @@ __global__ void __launch_bounds__(ROW_THREADS) trpo_head_kernel(TrpoHeadArgs a) 
       if (valid) a.old_dist_out[r * na + lane] = o;
     } else if constexpr (MODE == TR_FVP) {
       float fd[HPL], zr[HPL];
-      load_feat<HPL>(a.featd + r * h, h, lane, fd);
-      load_feat<HPL>(a.ln_z + r * h, h, lane, zr);
-      const float ln_mu = a.ln_stats[r * 2], ln_rs = a.ln_stats[r * 2 + 1];
+#pragma unroll
+      for (int q = 0; q < HPL; ++q) { fd[q] = cur.fd[q]; zr[q] = cur.zr[q]; }
+      const float ln_mu = cur.mu, ln_rs = cur.rs;
       float zd = head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(fd, shw, h, na, szero, lane) +
                  head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(f, shwd, h, na, sbd, lane);
       float dl = 0.f;
       if (HEAD == HB_HEAD_DISCRETE) {
         if (masked || !valid) zd = 0.f;                       // a masked logit is the constant -1e10
-        const float p = valid ? expf(a.old_dist[r * na + lane]) : 0.f;
+        const float p = valid ? expf(od_lane) : 0.f;
         const float sdot = warp_sum(p * zd);                  // d logsumexp
         const float u = valid ? (zd - sdot) * a.inv_rows : 0.f;  // H = I over every normalised logit
         const float usum = warp_sum(u);
@@ -292,7 +314,7 @@ __global__ void __launch_bounds__(ROW_THREADS) trpo_head_kernel(TrpoHeadArgs a) 
         const float mx = warp_max(valid ? o : -INFINITY);
         const float lse = mx + logf(warp_sum(valid ? expf(o - mx) : 0.f));
         const float lq = valid ? o - lse : 0.f;
-        const float lp = valid ? a.old_dist[r * na + lane] : 0.f;
+        const float lp = valid ? od_lane : 0.f;
         const float klj = valid ? (expf(lq - lp) - 1.f - lq) + lp : 0.f;  // kl_approx(p_old, q_new), trpo_util.py:49-53
         klrow = (double)warp_sum(klj);
         const int act = (int)a.actions[src];
@@ -315,7 +337,7 @@ __global__ void __launch_bounds__(ROW_THREADS) trpo_head_kernel(TrpoHeadArgs a) 
         if (valid) {  // _kl_normal_normal in float64, trpo_util.py:56-62 (p = old, q = new)
           const double sp = (double)std_old, sq = (double)std;
           const double vr = (sp / sq) * (sp / sq);
-          const double t1 = (((double)a.old_dist[r * na + lane] - (double)o) / sq);
+          const double t1 = (((double)od_lane - (double)o) / sq);
           klj = 0.5 * (vr + t1 * t1 - 1.0 - log(vr));
         }
         klrow = warp_sum_d(klj);
@@ -328,6 +350,7 @@ __global__ void __launch_bounds__(ROW_THREADS) trpo_head_kernel(TrpoHeadArgs a) 
         s_kl += klrow;
       }
     }
+    cur = nxt;
   }
   if constexpr (MODE == TR_FVP) {
 #pragma unroll

@@ -481,6 +481,8 @@ def case_hatrpo_parts():
         ("disc_nomask", dict(use_policy_active_masks=False, activation_func="tanh", kl_threshold=0.001), Discrete(4)),
         ("disc_backtrack", dict(accept_ratio=0.75), Discrete(5)),         # two trials rejected, the third accepted
         ("box_reject", dict(accept_ratio=5.0, ls_step=3), Box(2)),        # never accepted: parameters restored
+        ("gru_disc", dict(use_recurrent_policy=True, hidden_sizes=[16, 16], data_chunk_length=4), Discrete(6)),
+        ("gru2_disc", dict(use_recurrent_policy=True, hidden_sizes=[16], recurrent_n=2, data_chunk_length=8), Discrete(4)),
     ):
         torch.manual_seed(31)
         g = torch.Generator().manual_seed(32)
@@ -497,7 +499,9 @@ def case_hatrpo_parts():
         # old log-probs as the rollout would have stored them: the current policy's own (ratio == 1 at theta_old)
         fl = lambda a: a.reshape(T * N, *a.shape[2:])
         with torch.no_grad():
-            lp, _, _ = actor.evaluate_actions(fl(ab[0].obs[:-1]), fl(ab[0].rnn_states[:-1]), fl(ab[0].actions),
+            lp, _, _ = actor.evaluate_actions(fl(ab[0].obs[:-1]),
+                                              ab[0].rnn_states[0] if args["use_recurrent_policy"] else fl(ab[0].rnn_states[:-1]),
+                                              fl(ab[0].actions),
                                               fl(ab[0].masks[:-1]),
                                               fl(ab[0].available_actions[:-1]) if ab[0].available_actions is not None else None,
                                               fl(ab[0].active_masks[:-1]))
@@ -508,7 +512,10 @@ def case_hatrpo_parts():
         orig = torch.randperm
         torch.randperm = lambda n, *a, **k: torch.arange(n)
         try:
-            sample = next(ab[0].feed_forward_generator_actor(adv, 1))
+            if args["use_recurrent_policy"]:  # identity chunk order: the batch is every chunk, step-major
+                sample = next(ab[0].recurrent_generator_actor(adv, 1, args["data_chunk_length"]))
+            else:
+                sample = next(ab[0].feed_forward_generator_actor(adv, 1))
         finally:
             torch.randperm = orig
         (obs_b, rnn_b, act_b, masks_b, active_b, old_lp_b, adv_b, avail_b, factor_b) = sample
@@ -551,6 +558,7 @@ def case_hatrpo_train():
     for tag, over, act_space, st, A in (
         ("mlp_disc_EP", {}, Discrete(5), "EP", 3),
         ("mlp_box_FP", dict(hidden_sizes=[32, 32, 32]), Box(2), "FP", 2),
+        ("gru_disc_FP", dict(use_recurrent_policy=True, hidden_sizes=[16, 16], data_chunk_length=4, gamma=0.95), Discrete(6), "FP", 3),
     ):
         torch.manual_seed(41)
         g = torch.Generator().manual_seed(42)
@@ -569,7 +577,8 @@ def case_hatrpo_train():
         for a in range(A):
             with torch.no_grad():
                 lp, _, _ = actors[a].evaluate_actions(
-                    fl(ab[a].obs[:-1]), fl(ab[a].rnn_states[:-1]), fl(ab[a].actions), fl(ab[a].masks[:-1]),
+                    fl(ab[a].obs[:-1]), ab[a].rnn_states[0] if args["use_recurrent_policy"] else fl(ab[a].rnn_states[:-1]),
+                    fl(ab[a].actions), fl(ab[a].masks[:-1]),
                     fl(ab[a].available_actions[:-1]) if ab[a].available_actions is not None else None,
                     fl(ab[a].active_masks[:-1]))
             ab[a].action_log_probs[:] = (lp.numpy() + 0.05 * rng.standard_normal(lp.shape).astype(np.float32)).reshape(
