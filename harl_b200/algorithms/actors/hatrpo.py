@@ -19,6 +19,7 @@ import torch
 
 from ... import _lib as L
 from ... import dist
+from ...common import seq_index
 from ...nets import DeviceNet
 from .on_policy_base import OnPolicyBase, to_device
 
@@ -27,9 +28,6 @@ class HATRPO(OnPolicyBase):
     def __init__(self, args, obs_space, act_space, device=torch.device("cpu")):
         assert act_space.__class__.__name__ != "MultiDiscrete", \
             "only continuous and discrete action space is supported by HATRPO."
-        if args["use_recurrent_policy"] or args["use_naive_recurrent_policy"]:
-            raise NotImplementedError("HATRPO with recurrent (GRU) policies: the tangent pass of the Fisher-vector "
-                                      "product does not cover the GRU in this build")
         super().__init__(args, obs_space, act_space, device)
         self.kl_threshold = args["kl_threshold"]
         self.ls_step = args["ls_step"]
@@ -121,8 +119,15 @@ class HATRPO(OnPolicyBase):
         d = self.device
         obs, actions, active, old_lp, adv, factor, avail = (to_device(x, d) for x in
                                                              (obs, actions, active, old_lp, adv, factor, avail))
-        self._rnn_passthrough(_rnn)
-        batch = DeviceNet.actor_batch(obs, actions, old_lp, adv.reshape(-1), factor.reshape(-1), active.reshape(-1), avail)
+        rnn = mk = None
+        seq_len = 0
+        if self.recurrent:  # the reference's generator output: states at the sequence starts, step-major rows
+            rnn = to_device(_rnn, d)
+            rnn = rnn.reshape(rnn.shape[0], -1)
+            mk = to_device(_masks, d).reshape(-1)
+            seq_len = obs.shape[0] // rnn.shape[0]
+        batch = DeviceNet.actor_batch(obs, actions, old_lp, adv.reshape(-1), factor.reshape(-1), active.reshape(-1), avail,
+                                      rnn_states=rnn, masks=mk, seq_len=seq_len)
         cnt = torch.zeros(2, dtype=torch.float64, device=d)
         cnt[0] = active.sum().double() if self.use_policy_active_masks else float(obs.shape[0])
         cnt[1] = float(obs.shape[0])
@@ -149,15 +154,17 @@ class HATRPO(OnPolicyBase):
             adv_n = torch.empty_like(adv)
             L.call("hb_normalize_by_moments", L.ptr(adv), L.ptr(adv_n), rows, L.ptr(m3), L.stream_ptr())
             adv = adv_n
-        if self.use_recurrent_policy or self.use_naive_recurrent_policy:
-            raise NotImplementedError("recurrent (GRU) policies are not implemented in this build")
         fl = lambda a: a.reshape(rows, *a.shape[2:])
         avail = None if buf.available_actions is None else fl(buf.available_actions[:-1])
         factor = None if buf.factor is None else buf.factor.reshape(rows)
-        # the reference draws randperm(rows) for its single minibatch; a permutation of the whole buffer only
-        # reorders sums, so the rows are consumed in place
+        # the reference draws one permutation for its single minibatch (rows, envs or chunks, hatrpo.py:223-232); it
+        # only reorders sums (and the order of whole sequences), so the rows are consumed in place
+        mode = seq_index.mode_of(self.use_recurrent_policy, self.use_naive_recurrent_policy)
+        (idx, nrows, seq_len), = seq_index.minibatches(T, N, 1, mode, self.data_chunk_length, d)
+        rnn = buf.rnn_states.reshape((T + 1) * N, -1) if self.recurrent else None
+        masks = buf.masks.reshape((T + 1) * N) if self.recurrent else None
         batch = DeviceNet.actor_batch(fl(buf.obs[:-1]), fl(buf.actions), fl(buf.action_log_probs), adv, factor, active,
-                                      avail, None, rows)
+                                      avail, idx, nrows, rnn_states=rnn, masks=masks, seq_len=seq_len)
         global_rows = float(rows * dist.world_size())
         norm = n_active if self.use_policy_active_masks else global_rows
         kl, improve, expected, ent, ratio = self._update_on_batch(batch, norm, global_rows)

@@ -484,23 +484,17 @@ namespace {
 struct TrpoExtra { float* tprep; float* yd[2]; };
 
 size_t trpo_extra_floats(const hb::PrepLayout& Q, int64_t ch) {
-  return (size_t)hb::round_up(Q.tk[0], 4) + 2 * (size_t)ch * hb::hmax_of(Q);
+  return (size_t)hb::round_up(Q.tk[0], 4) + 2 * (size_t)ch * hb::hmax_of(Q) + hb::rnn_jvp_floats(Q, ch);
 }
 
-// the tangent pass does not cover the GRU yet: HATRPO with recurrent policies fails loudly
-int trpo_no_rnn(const hb_net_desc* d) {
-  if (!d->rnn_layers) return HB_OK;
-  hb::set_error("the trust-region (HATRPO) kernels do not cover recurrent (GRU) policies in this build");
-  return HB_ERR_UNSUPPORTED;
-}
+
 }  // namespace
 
 size_t hb_trpo_workspace_bytes(const hb_net_desc* d, int64_t rows) {
   hb::PrepLayout Q;
   hb::ParamLayout P;
   if (hb::make_layouts(d, &P, &Q, nullptr)) return 0;
-  int64_t ch = rows < hb::CHUNK_ROWS ? rows : hb::CHUNK_ROWS;
-  if (ch < 1) ch = 1;
+  const int64_t ch = hb::chunk_of(d, rows);
   return (hb::work_floats(Q, ch, 1, P.total) + trpo_extra_floats(Q, ch)) * sizeof(float);
 }
 
@@ -511,19 +505,20 @@ int hb_trpo_old_dist(const hb_net_desc* d, const float* prepared, const hb_actor
   PrepLayout Q;
   int rc = check_net(d, nullptr, &Q, nullptr, 1);
   if (rc) return rc;
-  if ((rc = trpo_no_rnn(d))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, b->obs, b->index, c0, n, d->rnn_layers ? &seq : nullptr, w, st, &feat))) return rc;
     TrpoHeadArgs a;
     memset(&a, 0, sizeof(a));
-    a.feat = w.Y[Q.n_layers - 1];
+    a.feat = feat;
     a.h = Q.n[Q.n_layers - 1]; a.out = d->out_dim;
     a.hw = prepared + Q.hw; a.hbias = prepared + Q.hbias; a.log_std = prepared + Q.log_std;
     a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;
@@ -546,13 +541,13 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
   hb_net_layout L;
   int rc = check_net(d, &P, &Q, &L, 1);
   if (rc) return rc;
-  if ((rc = trpo_no_rnn(d))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t ce = cudaMemsetAsync(out, 0, (size_t)L.total * sizeof(float), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_trpo_fvp(memset)");
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
+  const bool rnn = d->rnn_layers != 0;
   const size_t base = work_floats(Q, ch, 1, L.total);
   if ((base + trpo_extra_floats(Q, ch)) * sizeof(float) > ws_bytes || ws == nullptr) {
     set_error("hb_trpo_fvp: workspace too small: need %zu bytes, have %zu", (base + trpo_extra_floats(Q, ch)) * sizeof(float), ws_bytes);
@@ -564,13 +559,17 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
   x.tprep = (float*)ws + base;
   x.yd[0] = x.tprep + round_up(Q.tk[0], 4);
   x.yd[1] = x.yd[0] + (size_t)ch * hmax_of(Q);
+  RnnJvpWork jw;
+  carve_rnn_jvp(Q, ch, x.yd[1] + (size_t)ch * hmax_of(Q), &jw);
   ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_trpo_fvp(memset split buffer)");
   if ((rc = launch_tangent_prepare(d, P, Q, params, v, x.tprep, st))) return rc;
   const int Lh = Q.n_layers;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, b->obs, b->index, c0, n, rnn ? &seq : nullptr, w, st, &feat))) return rc;
     // tangent pass through the trunk (the normalised observations carry no tangent: their affine is folded into layer 0)
     const float* xin = w.x0;
     const float* xd = nullptr;
@@ -583,9 +582,13 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
       if (rc) return rc;
       xin = w.Y[l]; xd = yd; ldx = Q.n[l];
     }
+    if (rnn) {  // tangent through the GRU and its LayerNorm (the forward pass above saved the gates)
+      if ((rc = rnn_jvp_forward(Q, prepared, x.tprep, w.Y[Lh - 1], xd, seq.S, n / seq.S, w.rnn, jw, st))) return rc;
+      xd = jw.outd;
+    }
     TrpoHeadArgs a;
     memset(&a, 0, sizeof(a));
-    a.feat = w.Y[Lh - 1]; a.featd = xd;
+    a.feat = feat; a.featd = xd;
     a.h = Q.n[Lh - 1]; a.out = d->out_dim;
     a.hw = prepared + Q.hw; a.hbias = prepared + Q.hbias; a.log_std = prepared + Q.log_std;
     a.hwd = x.tprep + Q.hw; a.hbd = x.tprep + Q.hbias;
@@ -599,8 +602,14 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
     a.g_hw = out + P.hw; a.g_hbias = out + P.hbias;
     a.ln_z = w.Z[Lh - 1]; a.ln_stats = w.stats[Lh - 1]; a.ln_w = prepared + Q.lnw[Lh - 1];
     a.g_ln_w = out + P.lnw[Lh - 1]; a.g_ln_b = out + P.lnb[Lh - 1]; a.ln_act = d->activation;
+    if (rnn) {
+      a.dfeat = w.rnn.dtop;
+      a.ln_z = w.rnn.hs[d->rnn_layers - 1]; a.ln_stats = w.rnn.stats; a.ln_w = prepared + Q.rnn_lnw;
+      a.g_ln_w = out + P.rnn_lnw; a.g_ln_b = out + P.rnn_lnb; a.ln_act = HB_ACT_IDENTITY;
+    }
     a.part_delta = w.dwpart - out; a.part_stride = w.ptotal;
     if ((rc = launch_trpo_head(d->head, TR_FVP, a, st))) return rc;
+    if (rnn && (rc = rnn_to_trunk_backward(d, P, Q, params, prepared, out, n, &seq, w, st))) return rc;
     if ((rc = trunk_backward(d, P, Q, params, prepared, out, n, w, st))) return rc;
   }
   if ((rc = launch_dw_reduce(out, w.dwpart, L.total, st))) return rc;
@@ -630,21 +639,22 @@ int hb_trpo_eval(const hb_net_desc* d, const float* prepared, const hb_actor_bat
   PrepLayout Q;
   int rc = check_net(d, &P, &Q, nullptr, 1);
   if (rc) return rc;
-  if ((rc = trpo_no_rnn(d))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
-  const int64_t ch = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+  const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
   const int ad = d->head == HB_HEAD_DISCRETE ? 1 : d->out_dim;
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
-    if ((rc = trunk_forward(d, Q, prepared, b->obs, b->index, c0, n, w, st))) return rc;
+    SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
+    const float* feat = nullptr;
+    if ((rc = features_forward(d, Q, prepared, b->obs, b->index, c0, n, d->rnn_layers ? &seq : nullptr, w, st, &feat))) return rc;
     const int64_t o = b->index ? 0 : c0;
     TrpoHeadArgs a;
     memset(&a, 0, sizeof(a));
-    a.feat = w.Y[Q.n_layers - 1];
+    a.feat = feat;
     a.h = Q.n[Q.n_layers - 1]; a.out = d->out_dim;
     a.hw = prepared + Q.hw; a.hbias = prepared + Q.hbias; a.log_std = prepared + Q.log_std;
     a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;

@@ -273,4 +273,110 @@ int rnn_backward(const ParamLayout& P, const PrepLayout& Q, const float* params,
   return HB_OK;
 }
 
+// ------------------------------------------------------------------ tangent (forward-mode) pass, trust-region FVP
+// gate tangents from the saved gates (r, z, n, ghn), the tangents of the two projections and of the masked state:
+//   rd = r(1-r)(gid_r + ghd_r);  zd = z(1-z)(gid_z + ghd_z);  nd = (1-n^2)(gid_n + rd ghn + r ghd_n)
+//   hd = (1-z) nd + zd (hm - n) + z hmd
+__global__ void gru_gate_jvp_kernel(const float* __restrict__ gid, const float* __restrict__ ghd,
+                                    const float* __restrict__ gates, const float* __restrict__ hm,
+                                    const float* __restrict__ hmd, int h, int64_t B, float* __restrict__ hsd,
+                                    const float* __restrict__ mrow_next, float* __restrict__ hmd_next) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * h) return;
+  const int64_t b = i / h;
+  const int e = (int)(i % h);
+  const float* a = gid + b * 3 * h;
+  const float* c = ghd + b * 3 * h;
+  const float* g = gates + b * 4 * h;
+  const float r = g[e], z = g[h + e], n = g[2 * h + e], ghn = g[3 * h + e];
+  const float rd = r * (1.f - r) * (a[e] + c[e]);
+  const float zd = z * (1.f - z) * (a[h + e] + c[h + e]);
+  const float nd = (1.f - n * n) * (a[2 * h + e] + rd * ghn + r * c[2 * h + e]);
+  const float hd = (1.f - z) * nd + zd * (hm[i] - n) + z * (hmd != nullptr ? hmd[i] : 0.f);
+  hsd[i] = hd;
+  if (hmd_next != nullptr) hmd_next[i] = hd * mrow_next[b];
+}
+
+// tangent of the output LayerNorm: yd = gd xh + bd + g rstd (hd - mean(hd) - xh mean(xh hd)), xh = (hs - mu) rstd
+__global__ void __launch_bounds__(ROW_THREADS) rnn_ln_jvp_kernel(const float* __restrict__ X, const float* __restrict__ Xd,
+                                                                 const float* __restrict__ stats,
+                                                                 const float* __restrict__ lnw, const float* __restrict__ lnwd,
+                                                                 const float* __restrict__ lnbd, float* __restrict__ Yd,
+                                                                 int64_t rows, int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * ROW_WARPS;
+  const float inv_n = 1.f / (float)N;
+  for (int64_t r = w0; r < rows; r += nw) {
+    const float mu = stats[r * 2], rstd = stats[r * 2 + 1];
+    float xh[8], xd[8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int n = lane + 32 * q;
+      xh[q] = xd[q] = 0.f;
+      if (n < N) { xh[q] = (X[r * N + n] - mu) * rstd; xd[q] = Xd[r * N + n]; s1 += xd[q]; s2 = fmaf(xd[q], xh[q], s2); }
+    }
+    const float m1 = warp_sum(s1) * inv_n, m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int n = lane + 32 * q;
+      if (n < N) Yd[r * N + n] = lnwd[n] * xh[q] + lnbd[n] + lnw[n] * rstd * (xd[q] - m1 - xh[q] * m2);
+    }
+  }
+}
+
+size_t rnn_jvp_floats(const PrepLayout& Q, int64_t M) {
+  if (!Q.rnn_layers) return 0;
+  const size_t h = Q.rh, m = (size_t)M;
+  return m * 3 * h + m * 3 * h + (size_t)Q.rnn_layers * 2 * m * h + m * h;  // gid, ghd, (hmd, hsd) per layer, outd
+}
+
+int carve_rnn_jvp(const PrepLayout& Q, int64_t M, float* p, RnnJvpWork* w) {
+  memset(w, 0, sizeof(*w));
+  if (!Q.rnn_layers) return HB_OK;
+  const size_t h = Q.rh, m = (size_t)M;
+  w->gid = p; p += m * 3 * h;
+  w->ghd = p; p += m * 3 * h;
+  for (int l = 0; l < Q.rnn_layers; ++l) { w->hmd[l] = p; p += m * h; w->hsd[l] = p; p += m * h; }
+  w->outd = p;
+  return HB_OK;
+}
+
+// Xd: tangent of the layer-0 input sequence; tprep: tangent of the prepared weights (trpo.cu tangent_prepare).
+// Needs the forward pass of the SAME batch in w (gradient mode: gates saved).  Result: jw.outd = tangent of w.out.
+int rnn_jvp_forward(const PrepLayout& Q, const float* prep, const float* tprep, const float* X, const float* Xd, int64_t S,
+                    int64_t B, const RnnWork& w, const RnnJvpWork& jw, cudaStream_t st) {
+  const int h = Q.rh, R = Q.rnn_layers;
+  const int64_t M = S * B;
+  const float* xin = X;
+  const float* xd = Xd;
+  int rc;
+  for (int l = 0; l < R; ++l) {
+    // gid = Xd W_ih^T + X Wd_ih^T + bd_ih over all steps
+    if ((rc = launch_linear_plain(xd, h, prep + Q.rnn_wih_t[l], 3 * h, tprep + Q.rnn_bih[l], jw.gid, 3 * h, M, 3 * h, h, false, st))) return rc;
+    if ((rc = launch_linear_plain(xin, h, tprep + Q.rnn_wih_t[l], 3 * h, nullptr, jw.gid, 3 * h, M, 3 * h, h, true, st))) return rc;
+    for (int64_t t = 0; t < S; ++t) {
+      const float* hm_t = w.hm[l] + t * B * h;
+      const float* hmd_t = t == 0 ? nullptr : jw.hmd[l] + t * B * h;  // the stored initial state carries no tangent
+      // ghd = hmd W_hh^T + hm Wd_hh^T + bd_hh
+      if ((rc = launch_linear_plain(hm_t, h, tprep + Q.rnn_whh_t[l], 3 * h, tprep + Q.rnn_bhh[l], jw.ghd, 3 * h, B, 3 * h, h, false, st))) return rc;
+      if (hmd_t != nullptr &&
+          (rc = launch_linear_plain(hmd_t, h, prep + Q.rnn_whh_t[l], 3 * h, nullptr, jw.ghd, 3 * h, B, 3 * h, h, true, st)))
+        return rc;
+      const bool last = t + 1 == S;
+      gru_gate_jvp_kernel<<<ew_grid(B * h), 256, 0, st>>>(jw.gid + t * B * 3 * h, jw.ghd, w.gates[l] + t * B * 4 * h, hm_t,
+                                                         hmd_t, h, B, jw.hsd[l] + t * B * h,
+                                                         last ? nullptr : w.mrow + (t + 1) * B,
+                                                         last ? nullptr : jw.hmd[l] + (t + 1) * B * h);
+      HB_LAUNCH_DONE(st, "rnn_gru_gate_jvp");
+    }
+    xin = w.hs[l];
+    xd = jw.hsd[l];
+  }
+  rnn_ln_jvp_kernel<<<row_grid(M), ROW_THREADS, 0, st>>>(w.hs[R - 1], xd, w.stats, prep + Q.rnn_lnw, tprep + Q.rnn_lnw,
+                                                        tprep + Q.rnn_lnb, jw.outd, M, h);
+  HB_LAUNCH_DONE(st, shape_label("rnn_ln_jvp", M, h, 0));
+  return HB_OK;
+}
+
 }  // namespace hb

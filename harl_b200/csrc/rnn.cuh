@@ -21,6 +21,18 @@ struct RnnWork {
   float* dx[2];     // [M, h] d loss / d (layer input)
 };
 
+struct RnnJvpWork {   // tangent pass of the trust-region Fisher-vector product
+  float* gid;       // [M, 3h]
+  float* ghd;       // [B, 3h]
+  float* hmd[2];    // [M, h] tangent of the masked previous state
+  float* hsd[2];    // [M, h] tangent of each step's new state
+  float* outd;      // [M, h] tangent of LayerNorm(hs[top])
+};
+
+size_t rnn_jvp_floats(const PrepLayout& Q, int64_t M);
+int carve_rnn_jvp(const PrepLayout& Q, int64_t M, float* p, RnnJvpWork* w);
+int rnn_jvp_forward(const PrepLayout& Q, const float* prep, const float* tprep, const float* X, const float* Xd, int64_t S,
+                    int64_t B, const RnnWork& w, const RnnJvpWork& jw, cudaStream_t st);
 size_t rnn_work_floats(const PrepLayout& Q, int64_t M, int grad);
 int carve_rnn(const PrepLayout& Q, int64_t M, int grad, float* p, RnnWork* w);
 int launch_linear_plain(const float* X, int ldx, const float* Bm, int ldb, const float* bias, float* Y, int ldy,

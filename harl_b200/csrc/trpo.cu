@@ -58,6 +58,25 @@ __global__ void tangent_prepare_kernel(ParamLayout P, PrepLayout Q, int feature_
   if (i >= Q.hw && i < Q.hw + out_dim * h) { tprep[i] = v[P.hw + i - Q.hw]; return; }
   if (i >= Q.hbias && i < Q.hbias + out_dim) { tprep[i] = v[P.hbias + i - Q.hbias]; return; }
   if (head == HB_HEAD_BOX && i >= Q.log_std && i < Q.log_std + out_dim) { tprep[i] = v[P.log_std + i - Q.log_std]; return; }
+  for (int r = 0; r < Q.rnn_layers; ++r) {  // linear in the parameters: the same transposes as hb_net_prepare
+    const int g3 = 3 * h;
+    if (i >= Q.rnn_wih_t[r] && i < Q.rnn_wih_t[r] + h * g3) {
+      int k = (i - Q.rnn_wih_t[r]) / g3, j = (i - Q.rnn_wih_t[r]) % g3;
+      tprep[i] = v[P.rnn_wih[r] + j * h + k];
+      return;
+    }
+    if (i >= Q.rnn_whh_t[r] && i < Q.rnn_whh_t[r] + h * g3) {
+      int k = (i - Q.rnn_whh_t[r]) / g3, j = (i - Q.rnn_whh_t[r]) % g3;
+      tprep[i] = v[P.rnn_whh[r] + j * h + k];
+      return;
+    }
+    if (i >= Q.rnn_bih[r] && i < Q.rnn_bih[r] + g3) { tprep[i] = v[P.rnn_bih[r] + i - Q.rnn_bih[r]]; return; }
+    if (i >= Q.rnn_bhh[r] && i < Q.rnn_bhh[r] + g3) { tprep[i] = v[P.rnn_bhh[r] + i - Q.rnn_bhh[r]]; return; }
+  }
+  if (Q.rnn_layers) {
+    if (i >= Q.rnn_lnw && i < Q.rnn_lnw + h) { tprep[i] = v[P.rnn_lnw + i - Q.rnn_lnw]; return; }
+    if (i >= Q.rnn_lnb && i < Q.rnn_lnb + h) { tprep[i] = v[P.rnn_lnb + i - Q.rnn_lnb]; return; }
+  }
   tprep[i] = 0.f;
 }
 

@@ -225,15 +225,6 @@ def test_recurrent_iteration_vs_oracle(algo, over, state_type):
     runner.close()
 
 
-def test_hatrpo_with_recurrent_policy_fails_loudly():
-    from harl_b200.algorithms.actors.hatrpo import HATRPO
-    from harl_b200.envs.spaces import Box, Discrete
-
-    cfg = U.base_args(use_recurrent_policy=True)
-    with pytest.raises(NotImplementedError):
-        HATRPO(cfg, Box(shape=(6,)), Discrete(4), device=torch.device(DEV))
-
-
 def test_share_param_with_recurrent_policy_fails_loudly():
     """The reference interleaves the agents' sequences in this combination (see MAPPO.share_param_train)."""
     from harl_b200.runners import RUNNER_REGISTRY

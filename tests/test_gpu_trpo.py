@@ -38,12 +38,15 @@ def _actor(g, cfg, m):
 
 
 def _sample(g, cfg):
-    """The reference's feed-forward minibatch with the identity permutation: time-major flatten of the buffer."""
-    T, N = cfg["episode_length"], cfg["n_rollout_threads"]
-    fl = lambda a: a.reshape(T * N, *a.shape[2:])
-    avail = fl(g["a0.available_actions"][:-1]) if "a0.available_actions" in g else None
-    return (fl(g["a0.obs"][:-1]), None, fl(g["a0.actions"]), fl(g["a0.masks"][:-1]), fl(g["a0.active_masks"][:-1]),
-            fl(g["a0.action_log_probs"]), fl(g["adv"]), avail, fl(g["factor"]))
+    """The reference's single minibatch with the identity permutation (feed-forward: time-major flatten of the
+    buffer; recurrent: every chunk in order, step-major, with the hidden state stored at each chunk start)."""
+    from oracle import algo as oa
+
+    buf = U.sub(g, "a0.")
+    buf.setdefault("available_actions", None)
+    b = next(oa.actor_minibatches(buf, g["adv"], g["factor"], cfg, lambda n: np.arange(n)))
+    n = lambda k: None if b.get(k) is None else b[k].numpy()
+    return (n("obs"), n("rnn"), n("actions"), n("masks"), n("active"), n("old_logp"), n("adv"), n("avail"), n("factor"))
 
 
 def _flat(net, g, prefix):
@@ -67,10 +70,14 @@ def _device_batch(ac, g, cfg):
     from harl_b200.algorithms.actors.on_policy_base import to_device
     from harl_b200.nets import DeviceNet
 
-    obs, _, actions, _, active, old_lp, adv, avail, factor = _sample(g, cfg)
+    obs, rnn, actions, masks, active, old_lp, adv, avail, factor = _sample(g, cfg)
     d = ac.device
     t = [to_device(x, d) for x in (obs, actions, old_lp, adv, factor, active, avail)]
-    batch = DeviceNet.actor_batch(t[0], t[1], t[2], t[3].reshape(-1), t[4].reshape(-1), t[5].reshape(-1), t[6])
+    kw = {}
+    if ac.recurrent:
+        r = to_device(rnn, d)
+        kw = dict(rnn_states=r.reshape(r.shape[0], -1), masks=to_device(masks, d).reshape(-1), seq_len=obs.shape[0] // r.shape[0])
+    batch = DeviceNet.actor_batch(t[0], t[1], t[2], t[3].reshape(-1), t[4].reshape(-1), t[5].reshape(-1), t[6], **kw)
     norm = float(active.sum()) if cfg["use_policy_active_masks"] else float(obs.shape[0])
     return batch, norm, float(obs.shape[0])
 
@@ -110,10 +117,13 @@ def test_update_vs_reference(name, gemm_impl):
     ac = _actor(g, cfg, m)
     kl, improve, expected, ent, ratio = ac.update(_sample(g, cfg))
     torch.cuda.synchronize()
-    assert _max_rel(ac.actor, ac.last_update["step_dir"], g, "step_dir/") <= 5e-3
-    np.testing.assert_allclose([kl, improve, expected, ent, ratio], g["update_scalars"], rtol=3e-3, atol=2e-6)
+    # 2-layer GRU: ill-conditioned damped Fisher, two CPU evaluation orders already differ by 1.2 % in the CG direction
+    # (tests/test_oracle_trpo.py::_loose)
+    loose = "gru2" in name
+    assert _max_rel(ac.actor, ac.last_update["step_dir"], g, "step_dir/") <= (5e-2 if loose else 5e-3)
+    np.testing.assert_allclose([kl, improve, expected, ent, ratio], g["update_scalars"], rtol=5e-2 if loose else 3e-3, atol=2e-6)
     for k, v in ac.actor.state_dict().items():
-        np.testing.assert_allclose(v.cpu().numpy(), g["out.actor0/" + k], rtol=0, atol=2e-4, err_msg=k)
+        np.testing.assert_allclose(v.cpu().numpy(), g["out.actor0/" + k], rtol=0, atol=2e-3 if loose else 2e-4, err_msg=k)
     if name.endswith("box_reject"):
         assert not ac.last_update["accepted"] and ac.last_update["trials"] == cfg["ls_step"]
     if name.endswith("disc_backtrack"):
@@ -145,9 +155,12 @@ def test_reference_ha_train_hatrpo_golden(name):
     np.testing.assert_allclose([cinfo["value_loss"], cinfo["critic_grad_norm"]], g["out.cinfo"], rtol=3e-4)
 
 
-def test_hatrpo_iteration_through_runner():
+@pytest.mark.parametrize("state_type,model_over", [("EP", {}), ("FP", dict(use_recurrent_policy=True, data_chunk_length=4)),
+                                                   ("EP", dict(use_naive_recurrent_policy=True))])
+def test_hatrpo_iteration_through_runner(state_type, model_over):
     """--algo hatrpo through the public runner: rollout -> GAE -> sequential trust-region updates -> critic; the
-    update of every agent is replayed by the oracle from the same buffers and initial weights."""
+    update of every agent is replayed by the oracle from the same buffers and initial weights.  The FP / GRU case is
+    BASELINE.json's configs[3] in miniature (HATRPO, recurrent policies, per-agent critic inputs)."""
     import copy
 
     from harl_b200.runners import RUNNER_REGISTRY
@@ -156,7 +169,8 @@ def test_hatrpo_iteration_through_runner():
     from oracle import trpo as ot
     from tests.smoke_check import small_config, snapshot
 
-    args, algo_args, env_args = small_config(algo="hatrpo", n=16, T=12)
+    args, algo_args, env_args = small_config(algo="hatrpo", n=16, T=12, state_type=state_type)
+    algo_args["model"].update(model_over)
     runner = RUNNER_REGISTRY["hatrpo"](args, algo_args, env_args)
     runner.warmup()
     runner.logger.init(1)
