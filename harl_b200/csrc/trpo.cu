@@ -199,6 +199,48 @@ int launch_jvp_linear_ln(int act, const float* X, int ldx, const float* Xd, cons
 }
 
 // ------------------------------------------------------------------ head kernel (one warp per row)
+// Up to 8 outputs: out[j] = fa . Wa[j] (+ fb . Wb[j]) + bias[j] lands in lane j.  The 8 per-lane partial sums are
+// combined by a reduce-scatter (4 + 2 + 1 exchanges while the live set halves, then 2 plain butterfly steps and one
+// gather): 10 shuffles instead of the 40 of eight independent butterflies -- ncu showed the first cut of these kernels
+// issue-bound at ~1100 warp instructions per row, most of them shuffle/add pairs of the head reductions.
+template <int HPL, bool TWO>
+__device__ __forceinline__ float head_linear_rs8(const float (&fa)[HPL], const float* __restrict__ swa,
+                                                 const float (&fb)[HPL], const float* __restrict__ swb, int h, int nout,
+                                                 const float* __restrict__ sbias, int lane) {
+  float p[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p[j] = 0.f;
+    if (j < nout) {
+#pragma unroll
+      for (int q = 0; q < HPL; ++q) {
+        const int n = lane + 32 * q;
+        if (n < h) {
+          p[j] = fmaf(fa[q], swa[j * h + n], p[j]);
+          if (TWO) p[j] = fmaf(fb[q], swb[j * h + n], p[j]);
+        }
+      }
+    }
+  }
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+  float q4[4], q2[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b16 ? p[i] : p[i + 4], keep = b16 ? p[i + 4] : p[i];
+    q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b8 ? q4[i] : q4[i + 2], keep = b8 ? q4[i + 2] : q4[i];
+    q2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float q1 = (b4 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? q2[0] : q2[1], 4);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1);   // lanes 4j .. 4j+3 hold output j
+  const float v = __shfl_sync(0xffffffffu, q1, (lane & 7) << 2);
+  return lane < nout ? v + sbias[lane] : 0.f;
+}
+
 // lane j < out holds output j.  Shared memory: hw [out][h], hwd [out][h] (FVP), bias[32], biasd[32], zero[32],
 // grad accumulators [out][h] + [32] (FVP), double scratch.
 template <int HPL, int MAXJ, int HEAD, int MODE>
@@ -278,7 +320,8 @@ __global__ void __launch_bounds__(ROW_THREADS, (HPL * MAXJ <= 32) ? 2 : 1) trpo_
     const float od_lane = cur.od;
     (void)src; (void)od_lane;
     if constexpr (MODE == TR_OLD) {
-      float o = head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(f, shw, h, na, sb, lane);
+      float o = MAXJ <= 8 ? head_linear_rs8<HPL, false>(f, shw, f, shw, h, na, sb, lane)
+                          : head_linear<HPL, 8>(f, shw, h, na, sb, lane);
       if (HEAD == HB_HEAD_DISCRETE) {
         if (masked) o = -1e10f;
         const float mx = warp_max(valid ? o : -INFINITY);
@@ -291,8 +334,8 @@ __global__ void __launch_bounds__(ROW_THREADS, (HPL * MAXJ <= 32) ? 2 : 1) trpo_
 #pragma unroll
       for (int q = 0; q < HPL; ++q) { fd[q] = cur.fd[q]; zr[q] = cur.zr[q]; }
       const float ln_mu = cur.mu, ln_rs = cur.rs;
-      float zd = head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(fd, shw, h, na, szero, lane) +
-                 head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(f, shwd, h, na, sbd, lane);
+      float zd = MAXJ <= 8 ? head_linear_rs8<HPL, true>(fd, shw, f, shwd, h, na, sbd, lane)
+                           : head_linear<HPL, 8>(fd, shw, h, na, szero, lane) + head_linear<HPL, 8>(f, shwd, h, na, sbd, lane);
       float dl = 0.f;
       if (HEAD == HB_HEAD_DISCRETE) {
         if (masked || !valid) zd = 0.f;                       // a masked logit is the constant -1e10
@@ -325,7 +368,8 @@ __global__ void __launch_bounds__(ROW_THREADS, (HPL * MAXJ <= 32) ? 2 : 1) trpo_
       const float w = a.use_active ? a.active[src] : 1.f;
       const float fac = a.factor ? a.factor[src] : 1.f;
       const float adv = a.adv[src];
-      float o = head_linear<HPL, (MAXJ < 8 ? MAXJ : 8)>(f, shw, h, na, sb, lane);
+      float o = MAXJ <= 8 ? head_linear_rs8<HPL, false>(f, shw, f, shw, h, na, sb, lane)
+                          : head_linear<HPL, 8>(f, shw, h, na, sb, lane);
       float ratio, ent;
       double klrow;
       if (HEAD == HB_HEAD_DISCRETE) {

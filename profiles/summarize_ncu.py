@@ -10,7 +10,7 @@ import os
 import re
 import sys
 
-src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out"
+src = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "gpurun_out"
 out = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -87,17 +87,25 @@ def full_summary(csv_path, txt_path, title):
     return traffic
 
 
-launch_summary(os.path.join(src, "launches_update_r01.csv"), os.path.join(out, "launches_update_r01_summary.txt"),
-               "update phase of one C2 iteration (bench.py --steps 1 --warmup 1), library kernels only")
-launch_summary(os.path.join(src, "launches_rollout_r01.csv"), os.path.join(out, "launches_rollout_r01_summary.txt"),
-               "rollout steps of one C2 iteration (CUDA-graph replay) + the GAE launch")
-t1 = full_summary(os.path.join(src, "ncu_hot_r01_raw.csv"), os.path.join(out, "ncu_hot_r01_summary.txt"),
-                  "update-phase kernels at the C2 launch size (819200 rows, profiles/ncu_target.py)")
-t2 = full_summary(os.path.join(src, "ncu_rollout_r01_raw.csv"), os.path.join(out, "ncu_rollout_r01_summary.txt"),
-                  "rollout inference kernel and GAE kernel inside bench.py")
-label_of = {"tc_linear_ln_fwd_kernel<128, 0, 3>": "tc_linear_ln_fwd_3xtf32", "tc_dx_ln_bwd_kernel<128, 0, 3>": "tc_dx_ln_bwd_3xtf32",
-            "tc_dw_accum_kernel<128, 3>": "tc_dw_accum_3xtf32", "discrete_rows_kernel<8, 16, 5, 2, 0>": "policy_head_grad",
-            "discrete_rows_kernel<8, 16, 5, 1, 0>": "policy_head_eval", "value_rows_grad_kernel<8, 16, 0>": "value_head_grad"}
-traffic = {label_of[k]: v for k, v in {**t1, **t2}.items() if k in label_of}
-json.dump(traffic, open(os.path.join(out, "roofline_traffic.json"), "w"), indent=1)
-print(traffic)
+def main_r01():
+    launch_summary(os.path.join(src, "launches_update_r01.csv"), os.path.join(out, "launches_update_r01_summary.txt"),
+                   "update phase of one C2 iteration (bench.py --steps 1 --warmup 1), library kernels only")
+    launch_summary(os.path.join(src, "launches_rollout_r01.csv"), os.path.join(out, "launches_rollout_r01_summary.txt"),
+                   "rollout steps of one C2 iteration (CUDA-graph replay) + the GAE launch")
+    t1 = full_summary(os.path.join(src, "ncu_hot_r01_raw.csv"), os.path.join(out, "ncu_hot_r01_summary.txt"),
+                      "update-phase kernels at the C2 launch size (819200 rows, profiles/ncu_target.py)")
+    t2 = full_summary(os.path.join(src, "ncu_rollout_r01_raw.csv"), os.path.join(out, "ncu_rollout_r01_summary.txt"),
+                      "rollout inference kernel and GAE kernel inside bench.py")
+    label_of = {"tc_linear_ln_fwd_kernel<128, 0, 3>": "tc_linear_ln_fwd_3xtf32", "tc_dx_ln_bwd_kernel<128, 0, 3>": "tc_dx_ln_bwd_3xtf32",
+                "tc_dw_accum_kernel<128, 3>": "tc_dw_accum_3xtf32", "discrete_rows_kernel<8, 16, 5, 2, 0>": "policy_head_grad",
+                "discrete_rows_kernel<8, 16, 5, 1, 0>": "policy_head_eval", "value_rows_grad_kernel<8, 16, 0>": "value_head_grad"}
+    traffic = {label_of[k]: v for k, v in {**t1, **t2}.items() if k in label_of}
+    json.dump(traffic, open(os.path.join(out, "roofline_traffic.json"), "w"), indent=1)
+    print(traffic)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 5 and sys.argv[1] == "--full":   # python profiles/summarize_ncu.py --full raw.csv out.txt "title"
+        print(full_summary(sys.argv[2], sys.argv[3], sys.argv[4]))
+    else:
+        main_r01()
