@@ -52,6 +52,10 @@ WORKLOADS = {
     "C2T": dict(desc="HATRPO synthetic-MPE obs_dim=18 act_dim=5 3 agents n_rollout_threads=4096 T=200",
                 env="pettingzoo_mpe", env_args=dict(scenario="simple_spread_v2", continuous_actions=False), n=4096, T=200,
                 hidden=[128, 128], algo={}, algo_name="hatrpo"),
+    "C4": dict(desc="HATRPO synthetic-SMAC 5 agents obs_dim=128 Discrete(12) n_rollout_threads=2048 T=160 GRU chunk 10, FP critic "
+                    "(BASELINE.json configs[3], one GPU's worth)",
+               env="smac", env_args=dict(map_name="5m_vs_6m"), n=2048, T=160, hidden=[64, 64, 64], algo=dict(gamma=0.95),
+               model=dict(use_recurrent_policy=True, data_chunk_length=10), algo_name="hatrpo"),
     "C4R": dict(desc="HAPPO synthetic-SMAC 5 agents obs_dim=128 Discrete(12) n_rollout_threads=2048 T=160 GRU chunk 10, FP critic",
                 env="smac", env_args=dict(map_name="5m_vs_6m"), n=2048, T=160, hidden=[64, 64, 64], algo=dict(gamma=0.95),
                 model=dict(use_recurrent_policy=True, data_chunk_length=10)),

@@ -125,7 +125,8 @@ SIGNATURES = {
     "hb_value_forward_rnn": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, P, P, P, C.c_size_t, P]),
     "hb_trpo_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64]),
     "hb_trpo_old_dist": (C.c_int, [C.POINTER(NetDesc), P, C.POINTER(ActorBatch), P, P, C.c_size_t, P]),
-    "hb_trpo_fvp": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(ActorBatch), P, P, C.c_double, P, P, C.c_size_t, P]),
+    "hb_trpo_fvp": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(ActorBatch), P, P, C.c_double, C.c_int, P, P,
+                              C.c_size_t, P]),
     "hb_trpo_fvp_finish": (C.c_int, [C.POINTER(NetDesc), P, P, P, C.c_float, P]),
     "hb_trpo_eval": (C.c_int, [C.POINTER(NetDesc), P, C.POINTER(ActorBatch), C.POINTER(PPOHyper), P, P, P, P,
                                C.c_size_t, P]),

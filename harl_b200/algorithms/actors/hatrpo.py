@@ -60,8 +60,13 @@ class HATRPO(OnPolicyBase):
         net.trpo_old_dist(batch, old_dist)
         inv_rows = 1.0 / float(global_rows)
 
+        n_fvp = [0]
+
         def fvp(vec, out):
-            net.trpo_fvp(batch, old_dist, vec, inv_rows, out)
+            # products 2..11 reuse the forward activations the first one left in the workspace (nothing else touches
+            # this stream's workspace in between: CG steps and the allreduce work on the flat vectors only)
+            net.trpo_fvp(batch, old_dist, vec, inv_rows, out, reuse_forward=n_fvp[0] > 0)
+            n_fvp[0] += 1
             dist.all_reduce_sum_(out)
             net.trpo_fvp_finish(vec, out, 0.1)
 

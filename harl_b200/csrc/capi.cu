@@ -532,8 +532,8 @@ int hb_trpo_old_dist(const hb_net_desc* d, const float* prepared, const hb_actor
 }
 
 int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared, const hb_actor_batch* b,
-                const float* old_dist, const float* v, double inv_rows, float* out, void* ws, size_t ws_bytes,
-                void* stream) {
+                const float* old_dist, const float* v, double inv_rows, int reuse_forward, float* out, void* ws,
+                size_t ws_bytes, void* stream) {
   using namespace hb;
   HB_CHECK_ARG(params && prepared && b && b->obs && old_dist && v && out && b->rows >= 0, "bad argument");
   ParamLayout P;
@@ -569,7 +569,13 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
     SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
     const float* feat = nullptr;
-    if ((rc = features_forward(d, Q, prepared, b->obs, b->index, c0, n, rnn ? &seq : nullptr, w, st, &feat))) return rc;
+    if (reuse_forward && ch == rows) {
+      // the 11 products of one update share parameters and batch: the activations (and the GRU's saved gates) of the
+      // previous hb_trpo_fvp call are still in the workspace
+      feat = rnn ? w.rnn.out : w.Y[Lh - 1];
+    } else if ((rc = features_forward(d, Q, prepared, b->obs, b->index, c0, n, rnn ? &seq : nullptr, w, st, &feat))) {
+      return rc;
+    }
     // tangent pass through the trunk (the normalised observations carry no tangent: their affine is folded into layer 0)
     const float* xin = w.x0;
     const float* xd = nullptr;

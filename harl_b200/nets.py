@@ -273,12 +273,14 @@ class DeviceNet:
         L.call("hb_trpo_old_dist", C.byref(self.desc), L.ptr(self.prepared), C.byref(batch), L.ptr(old_dist), L.ptr(ws), n,
                L.stream_ptr())
 
-    def trpo_fvp(self, batch, old_dist, vec, inv_rows, out):
-        """out = J^T H J vec over this rank's rows (no damping; see trpo_fvp_finish)."""
+    def trpo_fvp(self, batch, old_dist, vec, inv_rows, out, reuse_forward=False):
+        """out = J^T H J vec over this rank's rows (no damping; see trpo_fvp_finish).  ``reuse_forward``: the previous
+        library call on this stream's workspace was trpo_fvp on the same batch and parameters."""
         self._need_cuda()
         ws, n = self._trpo_ws(batch.rows)
         L.call("hb_trpo_fvp", C.byref(self.desc), L.ptr(self.params), L.ptr(self.prepared), C.byref(batch),
-               L.ptr(old_dist), L.ptr(vec), float(inv_rows), L.ptr(out), L.ptr(ws), n, L.stream_ptr())
+               L.ptr(old_dist), L.ptr(vec), float(inv_rows), int(bool(reuse_forward)), L.ptr(out), L.ptr(ws), n,
+               L.stream_ptr())
 
     def trpo_fvp_finish(self, vec, out, damping=0.1):
         L.call("hb_trpo_fvp_finish", C.byref(self.desc), L.ptr(self.params), L.ptr(vec), L.ptr(out), float(damping),

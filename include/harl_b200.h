@@ -311,10 +311,13 @@ int hb_trpo_old_dist(const hb_net_desc* d, const float* prepared, const hb_actor
 
 /* fisher_vector_product (trpo_util.py:136-158) WITHOUT the + 0.1 p term: out = d2 mean_rows KL(pi || pi) / dtheta2 . v
  * as J^T H J v (tangent pass, H / rows, backward pass), partial over this rank's rows; inv_rows = 1 / global rows.
- * The caller sum-reduces `out` over ranks, then calls hb_trpo_fvp_finish. */
+ * The caller sum-reduces `out` over ranks, then calls hb_trpo_fvp_finish.
+ * reuse_forward = 1: the previous call on this workspace was hb_trpo_fvp with the same net, parameters and batch
+ * (the 11 products of one update) and nothing else used the workspace since -- the forward activations (and the
+ * GRU's saved gates) are taken from it instead of being recomputed (single-chunk batches only; ignored otherwise). */
 int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared, const hb_actor_batch* b,
-                const float* old_dist, const float* v, double inv_rows, float* out, void* ws, size_t ws_bytes,
-                void* stream);
+                const float* old_dist, const float* v, double inv_rows, int reuse_forward, float* out, void* ws,
+                size_t ws_bytes, void* stream);
 /* out += damping * v (trpo_util.py:158), plus the DiagGaussian log_std block of the Hessian (row-independent). */
 int hb_trpo_fvp_finish(const hb_net_desc* d, const float* params, const float* v, float* out, float damping,
                        void* stream);
