@@ -57,6 +57,9 @@ class CollectArgs(C.Structure):
         ("seed", C.c_uint64 * HB_MAX_AGENTS),
         ("critic_desc", C.POINTER(NetDesc)), ("critic_prepared", C.c_void_p), ("share_obs", C.c_void_p),
         ("critic_rows", C.c_int64), ("values", C.c_void_p), ("offset_base", C.c_void_p),
+        ("actor_rnn", C.c_void_p * HB_MAX_AGENTS), ("actor_rnn_out", C.c_void_p * HB_MAX_AGENTS),
+        ("actor_masks", C.c_void_p * HB_MAX_AGENTS),
+        ("critic_rnn", C.c_void_p), ("critic_rnn_out", C.c_void_p), ("critic_masks", C.c_void_p),
     ]
 
 

@@ -350,6 +350,23 @@ extern "C" int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_
   static thread_local InferArgs A;  // large POD: avoid re-zeroing 3 KB of stack per step
   const hb_net_desc* d0 = a->actor_desc[0];
   HB_CHECK_ARG(d0 != nullptr, "actor_desc[0] is NULL");
+  bool any_rnn = a->critic_desc != nullptr && a->critic_desc->rnn_layers != 0;
+  for (int i = 0; i < a->n_agents; ++i) any_rnn = any_rnn || (a->actor_desc[i] != nullptr && a->actor_desc[i]->rnn_layers != 0);
+  if (any_rnn) {
+    // Recurrent nets: the GRU cell is not part of the fused kernel yet -- one library call still covers all agents
+    // and the critic (no host work between them), through the per-net kernels.
+    HB_CHECK_ARG(a->offset_base == nullptr, "recurrent rollout steps take the Philox offset from the host (no graph replay)");
+    for (int i = 0; i < a->n_agents; ++i) {
+      int rc = hb_policy_act_rnn(a->actor_desc[i], a->actor_prepared[i], a->obs[i], a->rows, a->avail[i], a->actor_rnn[i],
+                                 a->actor_masks[i], a->deterministic, a->seed[i], a->offset, a->actions[i], a->logp[i],
+                                 a->actor_rnn_out[i], ws, ws_bytes, stream);
+      if (rc) return rc;
+    }
+    if (a->critic_desc != nullptr)
+      return hb_value_forward_rnn(a->critic_desc, a->critic_prepared, a->share_obs, a->critic_rows, a->critic_rnn,
+                                  a->critic_masks, a->values, a->critic_rnn_out, ws, ws_bytes, stream);
+    return HB_OK;
+  }
   A.n_nets = a->n_agents + (a->critic_desc ? 1 : 0);
   A.n_layers = d0->n_layers;
   A.act = d0->activation;
@@ -366,7 +383,6 @@ extern "C" int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_
     PrepLayout Q;
     int rc = make_layouts(d, nullptr, &Q, nullptr);
     if (rc) return rc;
-    if (d->rnn_layers) { set_error("recurrent (GRU) networks are not implemented in this build"); return HB_ERR_UNSUPPORTED; }
     bool same = d->n_layers == d0->n_layers && d->activation == d0->activation && d->feature_norm == d0->feature_norm;
     for (int l = 0; same && l < d->n_layers; ++l) same = d->hidden[l] == d0->hidden[l];
     if (!same) { set_error("fused rollout inference needs one trunk architecture for all actors and the critic"); return HB_ERR_UNSUPPORTED; }

@@ -177,8 +177,7 @@ class OnPolicyBaseRunner:
         if getattr(self, "_fast", None) is None:
             ok = (self.device.type == "cuda" and hasattr(self.envs, "step_into")
                   and (getattr(self.envs, "device", None) == self.device or getattr(self.envs, "host_staged", False))
-                  and not self.actor_buffer[0].recurrent
-                  and not self.critic_buffer.recurrent and not getattr(self, "disable_fast_rollout", False))
+                  and not getattr(self, "disable_fast_rollout", False))
             self._fast = self._build_fast_path() if ok else False
         return bool(self._fast)
 
@@ -218,11 +217,24 @@ class OnPolicyBaseRunner:
             c.critic_desc = C.pointer(self.critic.critic.desc)
             c.critic_prepared = L.ptr(self.critic.critic.prepared)
             c.share_obs, c.critic_rows, c.values = L.ptr(cb.share_obs[s]), cb.value_preds[s].numel(), L.ptr(cb.value_preds[s])
+            # recurrent nets: hidden state in from slot s, out to slot s + 1 (the insert kernel zeroes finished envs)
+            for i, b in enumerate(self.actor_buffer):
+                if b.recurrent:
+                    c.actor_rnn[i], c.actor_rnn_out[i] = L.ptr(b.rnn_states[s]), L.ptr(b.rnn_states[s + 1])
+                    c.actor_masks[i] = L.ptr(b.masks[s])
+            if cb.recurrent:
+                c.critic_rnn, c.critic_rnn_out = L.ptr(cb.rnn_states_critic[s]), L.ptr(cb.rnn_states_critic[s + 1])
+                c.critic_masks = L.ptr(cb.masks[s])
             collect.append(c)
             a = L.InsertArgs()
             a.n_envs, a.n_agents, a.state_type_fp = N, A, int(fp)
             a.dones, a.bad_transition = L.ptr(self._dones_u8), L.ptr(self._bad_u8)
+            rec = self.actor_buffer[0].recurrent
+            a.actor_rnn_row = self.recurrent_n * self.rnn_hidden_size if rec else 0
+            a.critic_rnn_row = self.recurrent_n * self.rnn_hidden_size if cb.recurrent else 0
+            a.critic_rnn_next = L.ptr(cb.rnn_states_critic[s + 1]) if cb.recurrent else None
             for i, b in enumerate(self.actor_buffer):
+                a.actor_rnn_next[i] = L.ptr(b.rnn_states[s + 1]) if rec else None
                 a.actor_masks_next[i], a.actor_active_next[i] = L.ptr(b.masks[s + 1]), L.ptr(b.active_masks[s + 1])
             a.critic_masks_next, a.critic_bad_next = L.ptr(cb.masks[s + 1]), L.ptr(cb.bad_masks[s + 1])
             # logger bookkeeping reads the reward where it already is: the critic slot (team reward, or FP per-agent
@@ -253,7 +265,9 @@ class OnPolicyBaseRunner:
         T = len(f["collect"])
         period = getattr(self.envs, "graph_period", lambda: None)()
         use_graph = (period is not None and T % period == 0 and getattr(self, "use_cuda_graph_rollout", True)
-                     and not getattr(self, "time_phases_no_graph", False))
+                     and not getattr(self, "time_phases_no_graph", False)
+                     # recurrent steps draw their Philox offset on the host (hb_rollout_collect): eager loop
+                     and not self.actor_buffer[0].recurrent and not self.critic_buffer.recurrent)
         if use_graph and f.get("graph") is not None:
             f["graph"].replay()
             self._draws += T

@@ -166,6 +166,15 @@ typedef struct hb_collect_args {
   const uint64_t* offset_base;                   /* device counter added to `offset` inside the kernel, or NULL:
                                                     lets a CUDA graph of T rollout steps be replayed with fresh
                                                     random streams (see hb_counter_add) */
+  /* recurrent (GRU) nets only: this step's hidden-state / mask slots and where the new states go (normally the next
+   * slot; hb_rollout_insert_masks then zeroes the rows of finished envs).  With any recurrent net the step runs the
+   * per-net kernels (trunk, GRU cell, head) instead of the single fused launch and offset_base must be NULL. */
+  const float* actor_rnn[HB_MAX_AGENTS];         /* [rows, recurrent_n * h] */
+  float* actor_rnn_out[HB_MAX_AGENTS];
+  const float* actor_masks[HB_MAX_AGENTS];       /* [rows] */
+  const float* critic_rnn;                       /* [critic_rows, recurrent_n * h] */
+  float* critic_rnn_out;
+  const float* critic_masks;                     /* [critic_rows] */
 } hb_collect_args;
 int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_bytes, void* stream);
 /* *counter += inc on the device (one thread).  Stream-ordered; capturable into a CUDA graph. */

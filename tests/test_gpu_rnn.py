@@ -246,3 +246,45 @@ def test_share_param_with_recurrent_policy_fails_loudly():
         runner.train()
     torch.cuda.synchronize()
     runner.close()
+
+
+@pytest.mark.parametrize("state_type,over", [("EP", dict(use_recurrent_policy=True)), ("FP", dict(use_naive_recurrent_policy=True))])
+def test_recurrent_zero_copy_rollout_equals_generic_rollout(state_type, over):
+    """The lean rollout loop (one hb_rollout_collect per step for all agents + critic, env.step_into, insert kernel
+    with the hidden-state reset) must fill the buffers -- hidden states included -- exactly like the reference-shaped
+    collect / step / insert loop: both run the same per-net kernels with the same sampling streams."""
+    from harl_b200.runners import RUNNER_REGISTRY
+    from tests.smoke_check import small_config
+
+    runners = []
+    for fast in (True, False):
+        args, algo_args, env_args = small_config(state_type=state_type, T=12)
+        algo_args["model"].update(data_chunk_length=4, **over)
+        algo_args["algo"]["fixed_order"] = True
+        algo_args["train"]["log_interval"] = 10**9
+        r = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+        r.disable_fast_rollout = not fast
+        r.warmup()
+        r.logger.init(2)
+        r.run_iteration(1, 2)
+        torch.cuda.synchronize()
+        assert bool(r._fast) == fast
+        snap = {}
+        for a in range(r.num_agents):
+            b = r.actor_buffer[a]
+            for k in ("obs", "rnn_states", "actions", "action_log_probs", "masks", "active_masks", "available_actions"):
+                if getattr(b, k) is not None:
+                    snap[f"a{a}.{k}"] = getattr(b, k).clone()
+        for k in ("share_obs", "rnn_states_critic", "value_preds", "returns", "rewards", "masks", "bad_masks"):
+            snap["c." + k] = getattr(r.critic_buffer, k).clone()
+        r.snap = snap
+        runners.append(r)
+    f, g = runners
+    assert f.snap.keys() == g.snap.keys()
+    for k in f.snap:
+        assert torch.equal(f.snap[k], g.snap[k]), k
+    for a in range(f.num_agents):
+        for (k, v), (_, w) in zip(f.actor[a].actor.state_dict().items(), g.actor[a].actor.state_dict().items()):
+            np.testing.assert_allclose(v.cpu().numpy(), w.cpu().numpy(), rtol=0, atol=1e-4, err_msg=k)
+    for r in runners:
+        r.close()
