@@ -123,7 +123,7 @@ SIGNATURES = {
     "hb_value_grad": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(CriticBatch), C.POINTER(ValueHyper), P,
                                 C.c_double, P, P, P, C.c_size_t, P]),
     "hb_clip_adam_step": (C.c_int, [C.POINTER(NetDesc), P, P, P, P, P, C.POINTER(AdamHyper), P, P]),
-    "hb_policy_act_rnn": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, P, C.c_int, C.c_uint64, C.c_uint64, P, P,
+    "hb_policy_act_rnn": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, P, C.c_int, C.c_uint64, C.c_uint64, P, P, P,
                                     P, P, C.c_size_t, P]),
     "hb_value_forward_rnn": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, P, P, P, C.c_size_t, P]),
     "hb_trpo_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64]),

@@ -228,8 +228,8 @@ size_t hb_workspace_bytes(const hb_net_desc* d, int64_t rows, int mode) {
 
 static int policy_act_impl(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows,
                            const float* avail, const float* h_in, const float* masks, int deterministic, uint64_t seed,
-                           uint64_t offset, float* actions, float* logp, float* h_out, void* ws, size_t ws_bytes,
-                           void* stream) {
+                           uint64_t offset, const uint64_t* offset_base, float* actions, float* logp, float* h_out,
+                           void* ws, size_t ws_bytes, void* stream) {
   using namespace hb;
   HB_CHECK_ARG(prepared && obs && actions && logp && rows >= 0, "bad argument");
   PrepLayout Q;
@@ -255,6 +255,7 @@ static int policy_act_impl(const hb_net_desc* d, const float* prepared, const fl
     a.deterministic = deterministic;
     a.seed = seed;
     a.offset = offset + (uint64_t)c0 * 0x9E3779B97F4A7C15ull;  // distinct Philox streams per chunk
+    a.offset_base = reinterpret_cast<const unsigned long long*>(offset_base);
     a.actions_out = actions + c0 * ad;
     a.logp_out = logp + c0 * ad;
     if ((rc = launch_policy_head(d->head, MODE_ACT, a, st))) return rc;
@@ -297,15 +298,16 @@ static int value_forward_impl(const hb_net_desc* d, const float* prepared, const
 int hb_policy_act(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
                   int deterministic, uint64_t seed, uint64_t offset, float* actions, float* logp, void* ws,
                   size_t ws_bytes, void* stream) {
-  return policy_act_impl(d, prepared, obs, rows, avail, nullptr, nullptr, deterministic, seed, offset, actions, logp,
-                         nullptr, ws, ws_bytes, stream);
+  return policy_act_impl(d, prepared, obs, rows, avail, nullptr, nullptr, deterministic, seed, offset, nullptr, actions,
+                         logp, nullptr, ws, ws_bytes, stream);
 }
 
 int hb_policy_act_rnn(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows, const float* avail,
                       const float* rnn_states, const float* masks, int deterministic, uint64_t seed, uint64_t offset,
-                      float* actions, float* logp, float* rnn_states_out, void* ws, size_t ws_bytes, void* stream) {
-  return policy_act_impl(d, prepared, obs, rows, avail, rnn_states, masks, deterministic, seed, offset, actions, logp,
-                         rnn_states_out, ws, ws_bytes, stream);
+                      const uint64_t* offset_base, float* actions, float* logp, float* rnn_states_out, void* ws,
+                      size_t ws_bytes, void* stream) {
+  return policy_act_impl(d, prepared, obs, rows, avail, rnn_states, masks, deterministic, seed, offset, offset_base, actions,
+                         logp, rnn_states_out, ws, ws_bytes, stream);
 }
 
 int hb_value_forward(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows, float* values,

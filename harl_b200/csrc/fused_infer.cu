@@ -355,11 +355,10 @@ extern "C" int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_
   if (any_rnn) {
     // Recurrent nets: the GRU cell is not part of the fused kernel yet -- one library call still covers all agents
     // and the critic (no host work between them), through the per-net kernels.
-    HB_CHECK_ARG(a->offset_base == nullptr, "recurrent rollout steps take the Philox offset from the host (no graph replay)");
     for (int i = 0; i < a->n_agents; ++i) {
       int rc = hb_policy_act_rnn(a->actor_desc[i], a->actor_prepared[i], a->obs[i], a->rows, a->avail[i], a->actor_rnn[i],
-                                 a->actor_masks[i], a->deterministic, a->seed[i], a->offset, a->actions[i], a->logp[i],
-                                 a->actor_rnn_out[i], ws, ws_bytes, stream);
+                                 a->actor_masks[i], a->deterministic, a->seed[i], a->offset, a->offset_base, a->actions[i],
+                                 a->logp[i], a->actor_rnn_out[i], ws, ws_bytes, stream);
       if (rc) return rc;
     }
     if (a->critic_desc != nullptr)

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(MODE == MODE_GRAD ? RT_GRAD : RT_EVAL, MODE ==
     float lp[MAXJ], pj[MAXJ];
     const float ent = categorical<MAXJ>(lg, sb, na, avm, lp, pj);
     if constexpr (MODE == MODE_ACT) {
-      const int pick = categorical_pick<MAXJ>(pj, na, a.deterministic != 0, a.deterministic ? 0.f : row_uniform(r, a.seed, a.offset));
+      const int pick = categorical_pick<MAXJ>(pj, na, a.deterministic != 0, a.deterministic ? 0.f : row_uniform(r, a.seed, a.offset + (a.offset_base ? *a.offset_base : 0ull)));
       const float lpp = select<MAXJ>(lp, pick);
       if (ok && s == 0) { a.actions_out[r] = (float)pick; a.logp_out[r] = lpp; }
       __syncwarp();

@@ -18,6 +18,7 @@ struct HeadArgs {
   // act
   int deterministic;
   uint64_t seed, offset;
+  const unsigned long long* offset_base;  // device counter added to offset inside the kernel (CUDA-graph replays), nullable
   float* actions_out;    // [rows, ad]
   float* logp_out;       // [rows, ad]
   // evaluate / grad (buffer-row indexed)

@@ -233,8 +233,9 @@ __global__ void __launch_bounds__(ROW_THREADS) discrete_head_kernel(HeadArgs a) 
         unsigned b = __ballot_sync(0xffffffffu, valid && p == pm);
         act = __ffs(b) - 1;
       } else {
-        uint4 rnd = philox4x32(make_uint4((uint32_t)r, (uint32_t)((uint64_t)r >> 32), 0u, (uint32_t)a.offset),
-                               make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32)));
+        const uint64_t off = a.offset + (a.offset_base ? *a.offset_base : 0ull);
+        uint4 rnd = philox4x32(make_uint4((uint32_t)r, (uint32_t)((uint64_t)r >> 32), 0u, (uint32_t)off),
+                               make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)(off >> 32)));
         float u = u01(rnd.x);
         float c = p;  // inclusive prefix sum
 #pragma unroll
@@ -384,8 +385,9 @@ __global__ void __launch_bounds__(ROW_THREADS) box_head_kernel(HeadArgs a) {
     if constexpr (MODE == MODE_ACT) {
       float act = mean;
       if (!a.deterministic) {
-        uint4 rnd = philox4x32(make_uint4((uint32_t)r, (uint32_t)((uint64_t)r >> 32), (uint32_t)lane, (uint32_t)a.offset),
-                               make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32)));
+        const uint64_t off = a.offset + (a.offset_base ? *a.offset_base : 0ull);
+        uint4 rnd = philox4x32(make_uint4((uint32_t)r, (uint32_t)((uint64_t)r >> 32), (uint32_t)lane, (uint32_t)off),
+                               make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)(off >> 32)));
         float u1 = u01(rnd.x), u2 = u01(rnd.y);
         float z = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
         act = mean + std * z;

@@ -196,7 +196,7 @@ class DeviceNet:
         if self.recurrent:
             L.call("hb_policy_act_rnn", C.byref(self.desc), L.ptr(self.prepared), L.ptr(obs), rows, L.ptr(avail),
                    L.ptr(rnn_states), L.ptr(masks), int(bool(deterministic)), int(seed) & (2**64 - 1),
-                   int(offset) & (2**64 - 1), L.ptr(actions_out), L.ptr(logp_out), L.ptr(rnn_out), L.ptr(ws), n,
+                   int(offset) & (2**64 - 1), None, L.ptr(actions_out), L.ptr(logp_out), L.ptr(rnn_out), L.ptr(ws), n,
                    L.stream_ptr())
             return
         L.call("hb_policy_act", C.byref(self.desc), L.ptr(self.prepared), L.ptr(obs), rows, L.ptr(avail),

@@ -265,9 +265,7 @@ class OnPolicyBaseRunner:
         T = len(f["collect"])
         period = getattr(self.envs, "graph_period", lambda: None)()
         use_graph = (period is not None and T % period == 0 and getattr(self, "use_cuda_graph_rollout", True)
-                     and not getattr(self, "time_phases_no_graph", False)
-                     # recurrent steps draw their Philox offset on the host (hb_rollout_collect): eager loop
-                     and not self.actor_buffer[0].recurrent and not self.critic_buffer.recurrent)
+                     and not getattr(self, "time_phases_no_graph", False))
         if use_graph and f.get("graph") is not None:
             f["graph"].replay()
             self._draws += T

@@ -168,7 +168,7 @@ typedef struct hb_collect_args {
                                                     random streams (see hb_counter_add) */
   /* recurrent (GRU) nets only: this step's hidden-state / mask slots and where the new states go (normally the next
    * slot; hb_rollout_insert_masks then zeroes the rows of finished envs).  With any recurrent net the step runs the
-   * per-net kernels (trunk, GRU cell, head) instead of the single fused launch and offset_base must be NULL. */
+   * per-net kernels (trunk, GRU cell, head) instead of the single fused launch. */
   const float* actor_rnn[HB_MAX_AGENTS];         /* [rows, recurrent_n * h] */
   float* actor_rnn_out[HB_MAX_AGENTS];
   const float* actor_masks[HB_MAX_AGENTS];       /* [rows] */
@@ -295,11 +295,12 @@ int hb_clip_adam_step(const hb_net_desc* d, float* params, const float* grad, fl
 
 /* ---- recurrent (GRU) networks: one rollout step, rnn.py:24-32 ------------------------------------------ *
  * rnn_states [rows, recurrent_n * h] and masks [rows] are the buffer slot of this step; the new hidden state goes
- * to rnn_states_out [rows, recurrent_n * h] (StochasticPolicy.forward / VNet.forward return value). */
+ * to rnn_states_out [rows, recurrent_n * h] (StochasticPolicy.forward / VNet.forward return value).
+ * offset_base (nullable): device counter added to `offset` inside the sampling kernel, as in hb_collect_args. */
 int hb_policy_act_rnn(const hb_net_desc* d, const float* prepared, const float* obs, int64_t rows,
                       const float* avail, const float* rnn_states, const float* masks, int deterministic,
-                      uint64_t seed, uint64_t offset, float* actions, float* logp, float* rnn_states_out,
-                      void* ws, size_t ws_bytes, void* stream);
+                      uint64_t seed, uint64_t offset, const uint64_t* offset_base, float* actions, float* logp,
+                      float* rnn_states_out, void* ws, size_t ws_bytes, void* stream);
 int hb_value_forward_rnn(const hb_net_desc* d, const float* prepared, const float* cent_obs, int64_t rows,
                          const float* rnn_states, const float* masks, float* values, float* rnn_states_out,
                          void* ws, size_t ws_bytes, void* stream);

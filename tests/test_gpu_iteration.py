@@ -248,8 +248,10 @@ def test_host_staged_rollout_equals_device_rollout(action_type, state_type, simp
         r.close()
 
 
-@pytest.mark.parametrize("action_type,state_type,simple", [("Discrete", "EP", True), ("Box", "FP", False), ("Discrete", "EP", False)])
-def test_cuda_graph_rollout_equals_eager_rollout(action_type, state_type, simple):
+@pytest.mark.parametrize("action_type,state_type,simple,recurrent", [
+    ("Discrete", "EP", True, False), ("Box", "FP", False, False), ("Discrete", "EP", False, False),
+    ("Discrete", "FP", False, True), ("Box", "EP", False, True)])
+def test_cuda_graph_rollout_equals_eager_rollout(action_type, state_type, simple, recurrent):
     """The T-step rollout replayed from a CUDA graph (iterations >= 2) must fill the buffers bit-identically to the
     eager loop: same kernels, the Philox offsets advanced through the device counter.  Learning rates are zero so
     that the two runs see identical weights in every iteration."""
@@ -263,6 +265,8 @@ def test_cuda_graph_rollout_equals_eager_rollout(action_type, state_type, simple
             env_args.update(death_prob=0.0, terminate_prob=0.0, avail_prob=1.0)
         algo_args["model"]["lr"] = 0.0
         algo_args["model"]["critic_lr"] = 0.0
+        if recurrent:  # GRU actors and critic: per-net kernels inside the graph, hidden states carried across replays
+            algo_args["model"].update(use_recurrent_policy=True, data_chunk_length=4)
         algo_args["train"]["use_linear_lr_decay"] = False
         algo_args["train"]["log_interval"] = 10**9
         algo_args["algo"]["fixed_order"] = True
@@ -277,10 +281,10 @@ def test_cuda_graph_rollout_equals_eager_rollout(action_type, state_type, simple
             snap = {}
             for a in range(r.num_agents):
                 b = r.actor_buffer[a]
-                for k in ("obs", "actions", "action_log_probs", "masks", "active_masks", "available_actions"):
+                for k in ("obs", "actions", "action_log_probs", "masks", "active_masks", "available_actions") + (("rnn_states",) if recurrent else ()):
                     if getattr(b, k) is not None:
                         snap[f"a{a}.{k}"] = getattr(b, k).clone()
-            for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks"):
+            for k in ("share_obs", "value_preds", "returns", "rewards", "masks", "bad_masks") + (("rnn_states_critic",) if recurrent else ()):
                 snap["c." + k] = getattr(r.critic_buffer, k).clone()
             per_iter.append(snap)
         assert (r._fast.get("graph") is not None) == graph
