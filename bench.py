@@ -354,7 +354,7 @@ def cpu_reference_run(wl, steps, warmup, n_sample):
     from oracle.runner import NumpySyntheticEnv, OracleRunner
 
     args, algo_args, env_args = make_args(wl, 1, n_override=n_sample)
-    cfg = {**algo_args["model"], **algo_args["algo"], **algo_args["train"]}
+    cfg = {**algo_args["model"], **algo_args["algo"], **algo_args["train"], "algo_name": args["algo"]}
     shapes = resolve_shapes(args["env"], env_args)
     env = NumpySyntheticEnv(shapes, n_sample, seed=1)
     r = OracleRunner(cfg, env, state_type=shapes["state_type"], seed=1)

@@ -7,7 +7,9 @@ rollout step with host<->tensor conversions, per-iteration Python GAE loop, mate
 minibatches (including the unused rnn-state gather) -- so its cost profile is the reference's.
 
 Restates harl/runners/on_policy_base_runner.py:171-497 (run / warmup / collect / insert /
-compute / after_update) on top of oracle.algo.ha_train (on_policy_ha_runner.py:11-130).
+compute / after_update) on top of oracle.algo.ha_train (on_policy_ha_runner.py:11-130) or, with
+``cfg["algo_name"] == "hatrpo"``, oracle.trpo.ha_train_hatrpo; recurrent policies propagate their GRU
+hidden states through the rollout (reset at episode ends) exactly as the reference runner does.
 """
 import numpy as np
 import torch
@@ -15,6 +17,7 @@ import torch
 from . import algo as oa
 from . import buffers as ob
 from . import nets as on
+from . import trpo as ot
 
 
 class OracleRunner:
@@ -63,10 +66,12 @@ class OracleRunner:
     def collect(self, step):
         """on_policy_base_runner.py:285-340."""
         acts, lps = [], []
+        self._new_rnn = [None] * self.A
         for a in range(self.A):
             b, (p, _) = self.abufs[a], self.actors[a]
             obs = torch.from_numpy(b["obs"][step])
-            feat, _ = on.features(p, self.cfg, obs, torch.from_numpy(b["rnn_states"][step]), torch.from_numpy(b["masks"][step]))
+            feat, hx = on.features(p, self.cfg, obs, torch.from_numpy(b["rnn_states"][step]), torch.from_numpy(b["masks"][step]))
+            self._new_rnn[a] = hx.numpy()
             if self.heads[a] == "Discrete":
                 logits = on.categorical_logits(p, feat, torch.from_numpy(b["available_actions"][step]))
                 act = torch.multinomial(logits.exp(), 1)
@@ -80,18 +85,21 @@ class OracleRunner:
             lps.append(lp.numpy())
         actions = np.array(acts).transpose(1, 0, 2)
         logps = np.array(lps).transpose(1, 0, 2)
-        so = self.cbuf["share_obs"][step]
-        v, _ = on.critic_values(self.critic[0], self.cfg, torch.from_numpy(so.reshape(-1, so.shape[-1])), None, None)
+        so, rc, mk = self.cbuf["share_obs"][step], self.cbuf["rnn_states_critic"][step], self.cbuf["masks"][step]
+        v, hc = on.critic_values(self.critic[0], self.cfg, torch.from_numpy(so.reshape(-1, so.shape[-1])),
+                                 torch.from_numpy(rc.reshape(-1, *rc.shape[-2:])), torch.from_numpy(mk.reshape(-1, 1)))
+        self._new_rnn_critic = hc.numpy().reshape(rc.shape)
         values = v.numpy().reshape(self.cbuf["value_preds"][step].shape)
         return values, actions, logps
 
     def insert(self, step, obs, share_obs, rewards, dones, bad, avail, values, actions, logps):
         """on_policy_base_runner.py:342-460."""
-        masks, active, bad_masks, _ = ob.derive_masks(dones, bad, self.state_type)
+        masks, active, bad_masks, dones_env = ob.derive_masks(dones, bad, self.state_type)
+        keep = (~np.asarray(dones_env, bool)).astype(np.float32)  # finished envs restart from a zero state (:358-386)
         for a in range(self.A):
             b = self.abufs[a]
             b["obs"][step + 1] = obs[:, a].copy()
-            b["rnn_states"][step + 1] = 0.0
+            b["rnn_states"][step + 1] = self._new_rnn[a] * keep[:, None, None]
             b["actions"][step] = actions[:, a].copy()
             b["action_log_probs"][step] = logps[:, a].copy()
             b["masks"][step + 1] = masks[:, a].copy()
@@ -101,7 +109,7 @@ class OracleRunner:
         c = self.cbuf
         ep = self.state_type == "EP"
         c["share_obs"][step + 1] = share_obs[:, 0].copy() if ep else share_obs.copy()
-        c["rnn_states_critic"][step + 1] = 0.0
+        c["rnn_states_critic"][step + 1] = self._new_rnn_critic * keep.reshape(-1, *([1] * (self._new_rnn_critic.ndim - 1)))
         c["value_preds"][step] = values.copy()
         c["rewards"][step] = rewards[:, 0].copy() if ep else rewards.copy()
         c["masks"][step + 1] = masks[:, 0].copy() if ep else masks.copy()
@@ -111,8 +119,9 @@ class OracleRunner:
     def compute(self):
         """on_policy_base_runner.py:462-484 + compute_returns."""
         c = self.cbuf
-        so = c["share_obs"][-1]
-        nv, _ = on.critic_values(self.critic[0], self.cfg, torch.from_numpy(so.reshape(-1, so.shape[-1])), None, None)
+        so, rc, mk = c["share_obs"][-1], c["rnn_states_critic"][-1], c["masks"][-1]
+        nv, _ = on.critic_values(self.critic[0], self.cfg, torch.from_numpy(so.reshape(-1, so.shape[-1])),
+                                 torch.from_numpy(rc.reshape(-1, *rc.shape[-2:])), torch.from_numpy(mk.reshape(-1, 1)))
         nv = nv.numpy().reshape(c["value_preds"][-1].shape)
         ret, vp = ob.compute_returns(c["rewards"], c["value_preds"], c["masks"], c["bad_masks"], nv, self.cfg["gamma"],
                                      self.cfg["gae_lambda"], self.cfg["use_gae"], self.cfg["use_proper_time_limits"], self.vn)
@@ -135,8 +144,12 @@ class OracleRunner:
         self.compute()
         order = list(range(self.A)) if self.cfg["fixed_order"] else list(torch.randperm(self.A).numpy())
         perm = lambda n: torch.randperm(n).numpy()
-        infos, cinfo, _, _ = oa.ha_train(self.actors, self.critic, self.cfg, self.heads, self.abufs, self.cbuf, self.vn,
-                                         self.state_type, order, perm)
+        if self.cfg.get("algo_name") == "hatrpo":
+            infos, cinfo, _, _ = ot.ha_train_hatrpo([p for p, _ in self.actors], self.critic, self.cfg, self.heads,
+                                                    self.abufs, self.cbuf, self.vn, self.state_type, order, perm)
+        else:
+            infos, cinfo, _, _ = oa.ha_train(self.actors, self.critic, self.cfg, self.heads, self.abufs, self.cbuf, self.vn,
+                                             self.state_type, order, perm)
         self.after_update()
         return infos, cinfo
 
