@@ -435,9 +435,10 @@ __global__ void __launch_bounds__(ROW_THREADS, (HPL * MAXJ <= 32) ? 2 : 1) trpo_
 template <int HEAD, int MODE>
 static int launch_trpo_head_mode(const TrpoHeadArgs& a, cudaStream_t st) {
   const int hpl = a.h <= 32 ? 1 : a.h <= 64 ? 2 : a.h <= 128 ? 4 : 8;
-  int maxj = 8;
+  // MAXJ selects the head reduction in every mode (<= 8 outputs: reduce-scatter; wider heads: the generic butterflies)
+  // and sizes the per-lane gradient accumulators of the FVP mode
+  const int maxj = a.out <= 8 ? 8 : a.out <= 16 ? 16 : 32;
   if (MODE == TR_FVP) {
-    maxj = a.out <= 8 ? 8 : a.out <= 16 ? 16 : 32;
     if (maxj * hpl > 64) {
       set_error("trust-region head: out_dim %d with hidden %d exceeds the register-accumulator budget", a.out, a.h);
       return HB_ERR_UNSUPPORTED;
