@@ -5,9 +5,13 @@ threshold -> backtracking line search on the surrogate and KL(old || new).  Ever
 in CUDA over the buffer rows in place (no minibatch is materialised):
 
 * gradient: the fused HAPPO kernel with clipping and the entropy bonus off (it differentiates -loss);
-* Fisher-vector product: Gauss-Newton form J^T H J v -- a tangent pass through the trunk (trpo.cu), the
-  distribution-space Hessian, and the ordinary backward kernels -- instead of the reference's double backward
-  (identical operator: at new == old the KL gradient w.r.t. the distribution parameters vanishes);
+* Fisher-vector product: Gauss-Newton form J^T H J v -- a tangent pass through the trunk (trpo.cu) and, for
+  recurrent policies, through the GRU and its LayerNorm (rnn.cu: rnn_jvp_forward), the distribution-space Hessian, and
+  the ordinary backward kernels (BPTT included) -- instead of the reference's double backward (identical operator: at
+  new == old the KL gradient w.r.t. the distribution parameters vanishes); products 2..11 of an update reuse the
+  forward activations the first one left in the workspace;
+* recurrent policies: the single minibatch is every data_chunk_length chunk (hatrpo.py:223-227), read in place through
+  the chunk index map with the hidden state stored at each chunk start;
 * the old distribution is evaluated once and kept ([rows, out_dim]) rather than re-instantiating an old actor;
 * CG vector algebra stays on the device (no host sync inside the 10 iterations); the line search reads back four
   doubles per trial, as the reference does (`.cpu().numpy()`, hatrpo.py:163).
