@@ -8,7 +8,6 @@ available-action masks.  It follows the reference's batched-env call contract
 SURVEY.md section 1 "L4 -> L0") but returns tensors resident on the training device, so the rollout
 never crosses the host.  Per-step cost is a pool lookup; the pool is generated once.
 """
-import numpy as np
 import torch
 
 from .spaces import Box, Discrete

@@ -11,9 +11,7 @@ sum-allreduced.
 """
 import ctypes as C
 import os
-import time
 
-import numpy as np
 import torch
 
 from .. import _lib as L

@@ -158,8 +158,6 @@ class NumpySyntheticEnv:
     """Host twin of harl_b200.envs.synthetic (same shapes, same termination schedule, NumPy outputs)."""
 
     def __init__(self, shapes, n_threads, seed=0, pool=8):
-        from types import SimpleNamespace
-
         c = shapes
         self.n_agents = A = c["n_agents"]
         N = self.N = n_threads
