@@ -483,6 +483,9 @@ def case_hatrpo_parts():
         ("box_reject", dict(accept_ratio=5.0, ls_step=3), Box(2)),        # never accepted: parameters restored
         ("gru_disc", dict(use_recurrent_policy=True, hidden_sizes=[16, 16], data_chunk_length=4), Discrete(6)),
         ("gru2_disc", dict(use_recurrent_policy=True, hidden_sizes=[16], recurrent_n=2, data_chunk_length=8), Discrete(4)),
+        # synthetic-SMAC head / trunk widths (BASELINE configs[3]): 12 actions, hidden 64
+        ("disc12_h64", dict(hidden_sizes=[64, 64]), Discrete(12)),
+        ("gru_disc12_h64", dict(use_recurrent_policy=True, hidden_sizes=[64, 64], data_chunk_length=4), Discrete(12)),
     ):
         torch.manual_seed(31)
         g = torch.Generator().manual_seed(32)
