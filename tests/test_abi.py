@@ -119,3 +119,27 @@ def test_workspace_sizing_and_argument_checks(L):
     assert big == L.lib.hb_workspace_bytes(C.byref(d), 20_000_000, 1)
     rc = L.lib.hb_gae_returns(None, None, None, None, None, None, None, 10, 10, 0.99, 0.94, 1, 1, None, None)
     assert rc == -1 and b"NULL" in L.lib.hb_last_error()
+
+
+def test_recurrent_and_trust_region_workspace_sizing(L):
+    """Host-only sizing calls: recurrent batches are never chunked (a chunk would cut every sequence), so their
+    workspace keeps growing with the row count; the trust-region workspace covers the gradient workspace plus the
+    tangent buffers (and the GRU tangent buffers for recurrent nets)."""
+    from harl_b200.nets import make_desc
+
+    mlp = make_desc(U.base_args(hidden_sizes=[64, 64]), 30, L.HEAD_DISCRETE, 12)
+    gru = make_desc(U.base_args(hidden_sizes=[64, 64], use_recurrent_policy=True), 30, L.HEAD_DISCRETE, 12)
+    gru2 = make_desc(U.base_args(hidden_sizes=[64, 64], use_recurrent_policy=True, recurrent_n=2), 30, L.HEAD_DISCRETE, 12)
+    ws = lambda d, rows, mode: L.lib.hb_workspace_bytes(C.byref(d), rows, mode)
+    tws = lambda d, rows: L.lib.hb_trpo_workspace_bytes(C.byref(d), rows)
+    for rows in (4096, 100_000):
+        assert ws(mlp, rows, 0) < ws(gru, rows, 0) < ws(gru2, rows, 0)
+        assert ws(mlp, rows, 1) < ws(gru, rows, 1) < ws(gru2, rows, 1)
+        assert ws(mlp, rows, 1) < tws(mlp, rows) and ws(gru, rows, 1) < tws(gru, rows)
+        assert tws(gru, rows) - ws(gru, rows, 1) > tws(mlp, rows) - ws(mlp, rows, 1)   # GRU tangent buffers
+    assert ws(mlp, 20_000_000, 1) == ws(mlp, 10_000_000, 1)        # feed-forward nets: chunked
+    assert ws(gru, 4_000_000, 1) > ws(gru, 2_000_000, 1) * 1.9     # recurrent nets: one chunk, linear in the rows
+    # argument checks of the new entry points happen before any CUDA call
+    assert L.lib.hb_trpo_cg_init(None, None, None, None, None, 10, None) == -1 and b"bad argument" in L.lib.hb_last_error()
+    assert L.lib.hb_trpo_full_step(None, None, None, 0.01, None, None, 10, None) == -1
+    assert L.lib.hb_vec_scale(None, 1.0, 10, None) == -1
