@@ -707,6 +707,13 @@ int hb_trpo_apply_step(float* params, const float* params0, const float* full_st
   return hb::launch_apply_step(params, params0, full_step, fraction, n, (cudaStream_t)stream);
 }
 
+int hb_set_rnn_impl(int impl) {
+  HB_CHECK_ARG(impl == 0 || impl == 1, "impl must be 0 (launch per step) or 1 (experimental persistent recurrence)");
+  hb::set_rnn_impl(impl);
+  return HB_OK;
+}
+int hb_get_rnn_impl(void) { return hb::rnn_impl(); }
+
 int hb_vec_scale(float* x, float s, int n, void* stream) {
   HB_CHECK_ARG(x && n > 0, "bad argument");
   return hb::launch_vec_scale(x, s, n, (cudaStream_t)stream);

@@ -12,6 +12,9 @@
 // fused into the head kernels (identity activation).  FP32 FFMA tiles (gemm_tile.cuh): the per-step GEMMs are
 // [B, h] x [h, 3h] with h <= 256 -- latency-bound, not tensor-pipe work.
 #include <math.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "common.cuh"
 #include "gemm_tile.cuh"
@@ -163,6 +166,91 @@ __global__ void __launch_bounds__(ROW_THREADS) rnn_ln_fwd_kernel(const float* __
   }
 }
 
+// ------------------------------------------------------------------ persistent per-sequence recurrence (opt-in)
+// EXPERIMENTAL -- compiled, not yet run on a GPU (written after this round's GPU budget was spent); selected only by
+// hb_set_rnn_impl(1) / HB_RNN_IMPL=persistent, h = 64.  One warp owns one sequence for all S steps: W_hh^T (64 x 192
+// floats, regrouped so that lane l finds the r, z, n weights of its two hidden units 2l, 2l+1 in two LDS.128 per input
+// unit) stays in shared memory, the state stays in registers (unit i lives in lane i/2, broadcast by shuffle), and per
+// step the warp reads its gi row and the reset mask and writes hm / hs / gates exactly as the per-step kernels do.
+// Accumulation order matches the tiled GEMM (ascending input unit from zero, bias added last), so the results are
+// meant to be bit-identical to the launch-per-step path.  Replaces 2 S launches per layer by one.
+constexpr int GP_H = 64;
+__global__ void __launch_bounds__(256) gru_seq_fwd_kernel(const float* __restrict__ whh_t /* [64][192] */,
+                                                          const float* __restrict__ bhh /* [192] */,
+                                                          const float* __restrict__ gi /* [S*B, 192] */,
+                                                          const float* __restrict__ h0, const int32_t* __restrict__ index,
+                                                          int layer, int layers, const float* __restrict__ mrow,
+                                                          int64_t S, int64_t B, float* __restrict__ hm,
+                                                          float* __restrict__ hs, float* __restrict__ gates,
+                                                          float* __restrict__ h_out) {
+  // [64 input units][2 parts][32 lanes][4]: part 0 = {r0, r1, z0, z1}, part 1 = {n0, n1, -, -} of lane l's units 2l, 2l+1
+  // (consecutive lanes read consecutive float4: conflict-free LDS.128)
+  extern __shared__ __align__(16) float gp_w[];
+  for (int f = threadIdx.x; f < GP_H * 2 * 32 * 4; f += 256) {
+    const int i = f >> 8, part = (f >> 7) & 1, l = (f >> 2) & 31, c = part * 4 + (f & 3);
+    gp_w[f] = c < 6 ? whh_t[i * 3 * GP_H + (c >> 1) * GP_H + 2 * l + (c & 1)] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = 2 * lane;
+  const float2 br = *reinterpret_cast<const float2*>(bhh + e), bz = *reinterpret_cast<const float2*>(bhh + GP_H + e),
+               bn = *reinterpret_cast<const float2*>(bhh + 2 * GP_H + e);
+  for (int64_t j = (int64_t)blockIdx.x * 8 + warp; j < B; j += (int64_t)gridDim.x * 8) {
+    const int64_t src = index ? (int64_t)index[j] : j;
+    float2 h = *reinterpret_cast<const float2*>(h0 + (src * layers + layer) * GP_H + e);
+    for (int64_t t = 0; t < S; ++t) {
+      const int64_t row = t * B + j;
+      const float m = mrow[row];
+      const float hm0 = h.x * m, hm1 = h.y * m;
+      *reinterpret_cast<float2*>(hm + row * GP_H + e) = make_float2(hm0, hm1);
+      float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int ii = 0; ii < 32; ++ii) {
+        const float v0 = __shfl_sync(0xffffffffu, hm0, ii), v1 = __shfl_sync(0xffffffffu, hm1, ii);
+        const float4* w0 = reinterpret_cast<const float4*>(gp_w + ((2 * ii) * 64 + lane) * 4);      // unit 2 ii
+        const float4* w1 = reinterpret_cast<const float4*>(gp_w + ((2 * ii + 1) * 64 + lane) * 4);  // unit 2 ii + 1
+        const float4 p = w0[0], q = w0[32];
+        a[0] = fmaf(v0, p.x, a[0]); a[1] = fmaf(v0, p.y, a[1]); a[2] = fmaf(v0, p.z, a[2]);
+        a[3] = fmaf(v0, p.w, a[3]); a[4] = fmaf(v0, q.x, a[4]); a[5] = fmaf(v0, q.y, a[5]);
+        const float4 p1 = w1[0], q1 = w1[32];
+        a[0] = fmaf(v1, p1.x, a[0]); a[1] = fmaf(v1, p1.y, a[1]); a[2] = fmaf(v1, p1.z, a[2]);
+        a[3] = fmaf(v1, p1.w, a[3]); a[4] = fmaf(v1, q1.x, a[4]); a[5] = fmaf(v1, q1.y, a[5]);
+      }
+      const float* g = gi + row * 3 * GP_H;
+      const float2 gr = *reinterpret_cast<const float2*>(g + e), gz = *reinterpret_cast<const float2*>(g + GP_H + e),
+                   gn = *reinterpret_cast<const float2*>(g + 2 * GP_H + e);
+      const float ghr0 = a[0] + br.x, ghr1 = a[1] + br.y, ghz0 = a[2] + bz.x, ghz1 = a[3] + bz.y;
+      const float ghn0 = a[4] + bn.x, ghn1 = a[5] + bn.y;
+      const float r0 = sigmoidf_(gr.x + ghr0), r1 = sigmoidf_(gr.y + ghr1);
+      const float z0 = sigmoidf_(gz.x + ghz0), z1 = sigmoidf_(gz.y + ghz1);
+      const float n0 = tanhf(gn.x + r0 * ghn0), n1 = tanhf(gn.y + r1 * ghn1);
+      h.x = (1.f - z0) * n0 + z0 * hm0;
+      h.y = (1.f - z1) * n1 + z1 * hm1;
+      *reinterpret_cast<float2*>(hs + row * GP_H + e) = h;
+      if (gates != nullptr) {
+        float* gt = gates + row * 4 * GP_H;
+        *reinterpret_cast<float2*>(gt + e) = make_float2(r0, r1);
+        *reinterpret_cast<float2*>(gt + GP_H + e) = make_float2(z0, z1);
+        *reinterpret_cast<float2*>(gt + 2 * GP_H + e) = make_float2(n0, n1);
+        *reinterpret_cast<float2*>(gt + 3 * GP_H + e) = make_float2(ghn0, ghn1);
+      }
+    }
+    if (h_out != nullptr) *reinterpret_cast<float2*>(h_out + (j * layers + layer) * GP_H + e) = h;
+  }
+}
+
+static std::atomic<int> g_rnn_impl{-1};  // -1: read HB_RNN_IMPL once; 0 = launch per step (default), 1 = persistent
+int rnn_impl() {
+  int v = g_rnn_impl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HB_RNN_IMPL");
+    v = (e != nullptr && strcmp(e, "persistent") == 0) ? 1 : 0;
+    g_rnn_impl.store(v);
+  }
+  return v;
+}
+void set_rnn_impl(int v) { g_rnn_impl.store(v ? 1 : 0); }
+
 // ------------------------------------------------------------------ workspace
 size_t rnn_work_floats(const PrepLayout& Q, int64_t M, int grad) {
   if (!Q.rnn_layers) return 0;
@@ -216,6 +304,21 @@ int rnn_forward(const PrepLayout& Q, const float* prep, const float* X, int64_t 
     if ((rc = launch_linear_plain(xin, h, prep + Q.rnn_wih_t[l], 3 * h, prep + Q.rnn_bih[l], w.gi[l], 3 * h, M, 3 * h, h,
                                   false, st)))
       return rc;
+    if (rnn_impl() == 1 && h == GP_H) {  // experimental persistent recurrence (see gru_seq_fwd_kernel)
+      const size_t smem = (size_t)GP_H * 32 * 8 * sizeof(float);
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+      }
+      int64_t g = ceil_div64(B, 8);
+      if (g > 148 * 3) g = 148 * 3;
+      gru_seq_fwd_kernel<<<(unsigned)g, 256, smem, st>>>(prep + Q.rnn_whh_t[l], prep + Q.rnn_bhh[l], w.gi[l], h0, index, l, R,
+                                                        w.mrow, S, B, w.hm[l], w.hs[l], w.gates[l], h_out);
+      HB_LAUNCH_DONE(st, shape_label("rnn_gru_seq_fwd", S * B, h, (int)S));
+      xin = w.hs[l];
+      continue;
+    }
     rnn_init_state_kernel<<<ew_grid(B * h), 256, 0, st>>>(h0, index, l, R, h, B, w.mrow, w.hm[l]);
     HB_LAUNCH_DONE(st, "rnn_init_state");
     for (int64_t t = 0; t < S; ++t) {

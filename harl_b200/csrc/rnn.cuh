@@ -29,6 +29,8 @@ struct RnnJvpWork {   // tangent pass of the trust-region Fisher-vector product
   float* outd;      // [M, h] tangent of LayerNorm(hs[top])
 };
 
+int rnn_impl();            // 0 = launch per step (default), 1 = experimental persistent per-sequence recurrence
+void set_rnn_impl(int v);
 size_t rnn_jvp_floats(const PrepLayout& Q, int64_t M);
 int carve_rnn_jvp(const PrepLayout& Q, int64_t M, float* p, RnnJvpWork* w);
 int rnn_jvp_forward(const PrepLayout& Q, const float* prep, const float* tprep, const float* X, const float* Xd, int64_t S,

@@ -305,6 +305,11 @@ int hb_value_forward_rnn(const hb_net_desc* d, const float* prepared, const floa
                          const float* rnn_states, const float* masks, float* values, float* rnn_states_out,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* GRU recurrence implementation: 0 = one GEMM + one gate kernel per step (default, GPU-verified), 1 = EXPERIMENTAL
+ * persistent per-sequence kernel (h = 64 only; compiled but not yet run on a GPU).  Env: HB_RNN_IMPL=persistent. */
+int hb_set_rnn_impl(int impl);
+int hb_get_rnn_impl(void);
+
 /* ---- trust-region (HATRPO) update: harl/algorithms/actors/hatrpo.py:37-194, harl/utils/trpo_util.py ------- *
  * The surrogate gradient is hb_ppo_actor_grad with use_clip = 0 and entropy_coef = 0 (it returns the gradient of
  * -loss; hb_vec_scale flips the sign).  The parameter-space vectors below (v, out, x, r, p, g, full_step,

@@ -288,3 +288,41 @@ def test_recurrent_zero_copy_rollout_equals_generic_rollout(state_type, over):
             np.testing.assert_allclose(v.cpu().numpy(), w.cpu().numpy(), rtol=0, atol=1e-4, err_msg=k)
     for r in runners:
         r.close()
+
+
+@pytest.mark.skip(reason="experimental persistent GRU recurrence (hb_set_rnn_impl(1)): written after the round's GPU "
+                         "budget was spent, not yet run on a GPU -- unskip in the next round")
+@pytest.mark.parametrize("recurrent_n", [1, 2])
+def test_persistent_recurrence_equals_per_step_kernels(recurrent_n):
+    """hb_set_rnn_impl(1) must reproduce the launch-per-step path (same accumulation order: bit-identical states)."""
+    from harl_b200 import _lib as L
+    from harl_b200.nets import DeviceNet
+    from oracle import nets as on
+
+    T, N, od, h, na = 12, 40, 9, 64, 6
+    cfg = U.base_args(hidden_sizes=[h, h], recurrent_n=recurrent_n, use_recurrent_policy=True)
+    torch.manual_seed(3)
+    p = on.init_params(cfg, od, "Discrete", na)
+    net = _net(cfg, od, "Discrete", na, {k: v + 0.1 * torch.randn(v.shape) for k, v in p.items()})
+    g = torch.Generator().manual_seed(4)
+    B = T * N
+    obs = torch.randn(B, od, generator=g).to(DEV)
+    acts = torch.randint(0, na, (B, 1), generator=g).float().to(DEV)
+    masks = (torch.rand(B, generator=g) > 0.2).float().to(DEV)
+    hx = torch.randn(N, recurrent_n * h, generator=g).to(DEV)
+    outs = []
+    for impl in (0, 1):
+        L.call("hb_set_rnn_impl", impl)
+        try:
+            lp = torch.zeros(B, 1, device=DEV)
+            net.evaluate(DeviceNet.actor_batch(obs, acts, rnn_states=hx, masks=masks, seq_len=T), logp_out=lp)
+            a = torch.zeros(N, 1, device=DEV)
+            l1 = torch.zeros(N, 1, device=DEV)
+            hn = torch.zeros(N, recurrent_n * h, device=DEV)
+            net.act(obs[:N].contiguous(), None, True, 0, 0, a, l1, hx, masks[:N].contiguous(), hn)
+            torch.cuda.synchronize()
+            outs.append((lp.clone(), hn.clone()))
+        finally:
+            L.call("hb_set_rnn_impl", 0)
+    np.testing.assert_allclose(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy(), rtol=0, atol=1e-6)
