@@ -1,8 +1,8 @@
-"""CPU: the oracle half of tests/test_gpu_trpo.py::test_fvp_wide_head_vs_oracle (keeps that test's setup exercised
+"""CPU: the oracle half of tests/test_gpu_zz_wide_heads.py::test_fvp_wide_head_vs_oracle (keeps that test's setup exercised
 where no GPU is available)."""
 import torch
 
-from tests.test_gpu_trpo import _wide_case
+from tests.test_gpu_zz_wide_heads import _wide_case
 
 
 def test_wide_case_oracle_side_runs_on_cpu():
