@@ -622,8 +622,70 @@ def case_hatrpo_train():
         save(f"hatrpo_train_{tag}", **out)
 
 
+def case_generators():
+    """Which buffer rows the reference's minibatch generators gather: every buffer element encodes its own (t, n[, a]),
+    so the yielded batches ARE the index maps.  Actor buffer + EP and FP critic buffers, the
+    three generator kinds, two minibatches each, with the permutation the reference drew."""
+    T, N, A, L = 8, 6, 3, 4
+    args = base_args(episode_length=T, n_rollout_threads=N, hidden_sizes=[8], data_chunk_length=L,
+                     use_recurrent_policy=True)
+    out = dict(T=np.array(T), N=np.array(N), A=np.array(A), L=np.array(L))
+    enc = (np.arange(T + 1)[:, None] * 1000 + np.arange(N)[None, :]).astype(np.float32)        # t*1000 + n
+    ab = OnPolicyActorBuffer(args, Box(3), Discrete(4))
+    ab.obs[:] = enc[:, :, None]
+    ab.rnn_states[:] = enc[:, :, None, None]
+    ab.masks[:] = enc[:, :, None]
+    ab.active_masks[:] = enc[:, :, None]
+    ab.actions[:] = enc[:T, :, None]
+    ab.action_log_probs[:] = enc[:T, :, None]
+    adv = enc[:T, :, None].copy()
+    gens = dict(ff=lambda: ab.feed_forward_generator_actor(adv, 2), naive=lambda: ab.naive_recurrent_generator_actor(adv, 2),
+                chunk=lambda: ab.recurrent_generator_actor(adv, 2, L))
+    for kind, mk in gens.items():
+        with PermRecorder() as pr:
+            batches = list(mk())
+        out[f"actor.{kind}.perm"] = pr.log[0]
+        for i, b in enumerate(batches):
+            out[f"actor.{kind}.{i}.obs"] = b[0][:, 0]
+            out[f"actor.{kind}.{i}.rnn"] = b[1][:, 0, 0]
+            out[f"actor.{kind}.{i}.actions"] = b[2][:, 0]
+            out[f"actor.{kind}.{i}.masks"] = b[3][:, 0]
+            out[f"actor.{kind}.{i}.adv"] = b[6][:, 0]
+    for st in ("EP", "FP"):
+        if st == "EP":
+            cb = OnPolicyCriticBufferEP(args, Box(5))
+            code = enc
+            cb.share_obs[:] = code[:, :, None]
+            cb.rnn_states_critic[:] = code[:, :, None, None]
+            for k in ("value_preds", "returns", "masks"):
+                getattr(cb, k)[:] = code[:, :, None]
+        else:
+            cb = OnPolicyCriticBufferFP(args, Box(5), A)
+            code = (np.arange(T + 1)[:, None, None] * 10000 + np.arange(N)[None, :, None] * 10
+                    + np.arange(A)[None, None, :]).astype(np.float32)                            # t*10000 + n*10 + a
+            cb.share_obs[:] = code[:, :, :, None]
+            cb.rnn_states_critic[:] = code[:, :, :, None, None]
+            for k in ("value_preds", "returns", "masks"):
+                getattr(cb, k)[:] = code[:, :, :, None]
+        gens = dict(ff=lambda: cb.feed_forward_generator_critic(2), naive=lambda: cb.naive_recurrent_generator_critic(2),
+                    chunk=lambda: cb.recurrent_generator_critic(2, L))
+        for kind, mk in gens.items():
+            with PermRecorder() as pr:
+                batches = list(mk())
+            out[f"critic{st}.{kind}.perm"] = pr.log[0]
+            for i, b in enumerate(batches):
+                out[f"critic{st}.{kind}.{i}.share_obs"] = b[0][:, 0]
+                out[f"critic{st}.{kind}.{i}.rnn"] = b[1].reshape(b[1].shape[0], -1)[:, 0]
+                out[f"critic{st}.{kind}.{i}.value_preds"] = b[2][:, 0]
+                out[f"critic{st}.{kind}.{i}.masks"] = b[4][:, 0]
+    save("generators_index_maps", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "generators":
+        case_generators()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "hatrpo":  # regenerate only the HATRPO vectors
         case_hatrpo_parts()
         case_hatrpo_train()
@@ -637,3 +699,4 @@ if __name__ == "__main__":
     case_ma_train()
     case_hatrpo_parts()
     case_hatrpo_train()
+    case_generators()

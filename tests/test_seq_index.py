@@ -118,3 +118,48 @@ def test_reference_compatible_generators_agree_with_index_maps():
         np.testing.assert_array_equal(obs, flat[idx.numpy()])
         np.testing.assert_array_equal(masks, flat[idx.numpy()])
         np.testing.assert_array_equal(h0, flat[idx.numpy()[:rows // seq_len]])
+
+
+@pytest.mark.parametrize("which", ["actor", "criticEP", "criticFP"])
+@pytest.mark.parametrize("kind", ["ff", "naive", "chunk"])
+def test_index_maps_reproduce_the_reference_generators(which, kind):
+    """tests/golden/generators_index_maps.npz: batches the UNMODIFIED reference generators yielded from buffers whose
+    elements encode their own (t, n[, a]) -- i.e. the reference's index maps themselves -- with the permutation it drew.
+    Reading the encoded buffer in place through seq_index's index (and taking the hidden state of sequence j from buffer
+    row index[j]) must give exactly those batches."""
+    from tests import util as U
+
+    g = U.load("generators_index_maps")
+    T, N, A, L = (int(g[k]) for k in ("T", "N", "A", "L"))
+    perm = g[f"{which}.{kind}.perm"]
+    if which == "criticFP":
+        C = N * A
+        code = (np.arange(T + 1)[:, None, None] * 10000 + np.arange(N)[None, :, None] * 10 + np.arange(A)[None, None, :])
+    else:
+        C = N
+        code = np.arange(T + 1)[:, None] * 1000 + np.arange(N)[None, :]
+    flat = code.reshape(-1).astype(np.float32)   # time-major flatten, (n, a) -> n * A + a
+    orig, fake, _ = _replay(perm)
+    torch.randperm = fake
+    try:
+        parts = list(seq_index.minibatches(T, C, 2, kind, L, torch.device("cpu")))
+    finally:
+        torch.randperm = orig
+    assert len(parts) == 2
+    rows_key = "obs" if which == "actor" else "share_obs"
+    for i, (idx, rows, seq_len) in enumerate(parts):
+        want = g[f"{which}.{kind}.{i}.{rows_key}"]
+        assert rows == len(want)
+        np.testing.assert_array_equal(flat[idx.numpy()], want)
+        np.testing.assert_array_equal(flat[idx.numpy()], g[f"{which}.{kind}.{i}.masks"])
+        if which == "actor":
+            np.testing.assert_array_equal(flat[idx.numpy()], g[f"{which}.{kind}.{i}.actions"])   # [T, N] arrays: same row index
+            np.testing.assert_array_equal(flat[idx.numpy()], g[f"{which}.{kind}.{i}.adv"])
+        else:
+            np.testing.assert_array_equal(flat[idx.numpy()], g[f"{which}.{kind}.{i}.value_preds"])
+        rnn = g[f"{which}.{kind}.{i}.rnn"]
+        if kind == "ff":      # one state per row (unused by feed-forward nets)
+            np.testing.assert_array_equal(flat[idx.numpy()], rnn)
+        else:                 # one state per sequence: the row the first step of sequence j points at
+            assert seq_len == (T if kind == "naive" else L) and len(rnn) == rows // seq_len
+            np.testing.assert_array_equal(flat[idx.numpy()[:len(rnn)]], rnn)
