@@ -7,6 +7,8 @@
 // activations then stream through HBM.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "rnn.cuh"
@@ -483,11 +485,16 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
 
 /* ------------------------------------------------------------------ trust-region (HATRPO) update */
 namespace {
-struct TrpoExtra { float* tprep; float* yd[2]; };
+struct TrpoExtra { float* tprep; float* yd[2]; float* ttiles; };
 
+// tangent-prepared weights, two tangent activation buffers, GRU tangent buffers, and (experimental tensor-core tangent
+// block) the UMMA images of the tangent weights -- same size as the forward images
 size_t trpo_extra_floats(const hb::PrepLayout& Q, int64_t ch) {
-  return (size_t)hb::round_up(Q.tk[0], 4) + 2 * (size_t)ch * hb::hmax_of(Q) + hb::rnn_jvp_floats(Q, ch);
+  return (size_t)hb::round_up(Q.tk[0], 4) + 2 * (size_t)ch * hb::hmax_of(Q) + hb::rnn_jvp_floats(Q, ch) +
+         (size_t)hb::round_up(Q.total - Q.tk[0], 4);
 }
+
+std::atomic<int> g_trpo_jvp_impl{0};  // 0 = FP32 FFMA tangent block (default, GPU-verified), 1 = tcgen05 (experimental)
 
 
 }  // namespace
@@ -563,10 +570,18 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
   x.yd[1] = x.yd[0] + (size_t)ch * hmax_of(Q);
   RnnJvpWork jw;
   carve_rnn_jvp(Q, ch, x.yd[1] + (size_t)ch * hmax_of(Q), &jw);
+  x.ttiles = x.yd[1] + (size_t)ch * hmax_of(Q) + rnn_jvp_floats(Q, ch);
+  const bool tc_jvp = g_trpo_jvp_impl.load(std::memory_order_relaxed) == 1 && gemm_impl() != 0;
   ce = cudaMemsetAsync(w.dwpart, 0, (size_t)tc_dw_splits() * L.total * sizeof(float), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_trpo_fvp(memset split buffer)");
   if ((rc = launch_tangent_prepare(d, P, Q, params, v, x.tprep, st))) return rc;
   const int Lh = Q.n_layers;
+  if (tc_jvp) {  // UMMA images of the tangent weights (W^T layout of tprep: src(n, k) = wt[k * n_l + n])
+    for (int l = 0; l < Lh; ++l)
+      if ((rc = launch_pack_umma_tiles(x.tprep + Q.wt[l], 1, Q.n[l], nullptr, Q.n[l], Q.k[l], Q.tk_nt[l], Q.tk_chunks[l],
+                                       x.ttiles + (Q.tk[l] - Q.tk[0]), st)))
+        return rc;
+  }
   for (int64_t c0 = 0; c0 < rows; c0 += ch) {
     const int64_t n = rows - c0 < ch ? rows - c0 : ch;
     SeqCtx seq = {b->rnn_states, b->masks, b->seq_len, nullptr};
@@ -584,9 +599,15 @@ int hb_trpo_fvp(const hb_net_desc* d, const float* params, const float* prepared
     int ldx = Q.kpad[0];
     for (int l = 0; l < Lh; ++l) {
       float* yd = x.yd[l & 1];
-      rc = launch_jvp_linear_ln(d->activation, xin, ldx, xd, prepared + Q.wt[l], x.tprep + Q.wt[l], x.tprep + Q.bias[l],
-                                prepared + Q.lnw[l], x.tprep + Q.lnw[l], x.tprep + Q.lnb[l], w.Z[l], w.stats[l], yd, n,
-                                Q.n[l], Q.kpad[l], st);
+      if (tc_jvp)
+        rc = launch_tc_jvp_linear_ln(gemm_impl() == 1 ? 3 : 1, d->activation, xin, ldx, xd, prepared + Q.tk[l],
+                                     x.ttiles + (Q.tk[l] - Q.tk[0]), Q.tk_chunks[l], x.tprep + Q.bias[l],
+                                     prepared + Q.lnw[l], x.tprep + Q.lnw[l], x.tprep + Q.lnb[l], w.Z[l], w.stats[l], yd, n,
+                                     Q.n[l], Q.kpad[l], st);
+      else
+        rc = launch_jvp_linear_ln(d->activation, xin, ldx, xd, prepared + Q.wt[l], x.tprep + Q.wt[l], x.tprep + Q.bias[l],
+                                  prepared + Q.lnw[l], x.tprep + Q.lnw[l], x.tprep + Q.lnb[l], w.Z[l], w.stats[l], yd, n,
+                                  Q.n[l], Q.kpad[l], st);
       if (rc) return rc;
       xin = w.Y[l]; xd = yd; ldx = Q.n[l];
     }
@@ -706,6 +727,13 @@ int hb_trpo_apply_step(float* params, const float* params0, const float* full_st
   HB_CHECK_ARG(params && params0 && full_step && n > 0, "bad argument");
   return hb::launch_apply_step(params, params0, full_step, fraction, n, (cudaStream_t)stream);
 }
+
+int hb_set_trpo_jvp_impl(int impl) {
+  HB_CHECK_ARG(impl == 0 || impl == 1, "impl must be 0 (FP32 FFMA tangent block) or 1 (experimental tcgen05 tangent block)");
+  g_trpo_jvp_impl.store(impl);
+  return HB_OK;
+}
+int hb_get_trpo_jvp_impl(void) { return g_trpo_jvp_impl.load(); }
 
 int hb_set_rnn_impl(int impl) {
   HB_CHECK_ARG(impl == 0 || impl == 1, "impl must be 0 (launch per step) or 1 (experimental persistent recurrence)");

@@ -84,6 +84,13 @@ int launch_tc_dx_ln_bwd(int passes, int act, const float* dZ, int N, const float
                         int Np, int64_t part_delta, int64_t part_stride, cudaStream_t st);
 int launch_tc_dw_accum(int passes, const float* dZ, int N, const float* X, int ldx, int K, float* dW, float* db,
                        int64_t M, int64_t part_stride, cudaStream_t st);
+// EXPERIMENTAL tensor-core tangent block (tc_gemm.cu), selected by hb_set_trpo_jvp_impl(1)
+int launch_tc_jvp_linear_ln(int passes, int act, const float* X, int ldx, const float* Xd, const float* tiles,
+                            const float* tiles_d, int nchunks, const float* bd, const float* lnw, const float* lnwd,
+                            const float* lnbd, const float* Z, const float* stats, float* Yd, int64_t M, int N, int Kred,
+                            cudaStream_t st);
+int launch_pack_umma_tiles(const float* W, int ldn, int ldk, const float* scale, int N, int K, int NT, int nchunks,
+                           float* dst, cudaStream_t st);
 int tc_dw_splits();
 int launch_dw_reduce(float* grad, const float* part, int total, cudaStream_t st);
 

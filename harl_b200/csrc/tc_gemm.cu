@@ -591,6 +591,223 @@ int launch_tc_dx_ln_bwd(int passes, int act, const float* dZ, int N, const float
   return HB_ERR_UNSUPPORTED;
 }
 
+// ---- EXPERIMENTAL (compiled, not yet run on a GPU; opt-in through hb_set_trpo_jvp_impl(1)): tangent of one
+// Linear -> act -> LayerNorm block on tensor cores, for the trust-region Fisher-vector product (trpo.cu).
+//   acc = Xd W^T + X Wd^T  as ONE accumulation over 2 x nchunks operand chunks (phase 0: A = Xd, B = the forward
+//   weight images; phase 1: A = X, B = images of the tangent weights packed per product by pack_umma_tiles), then
+//   ad = act'(Z) (acc + bd);  xh = (act(Z) - mu) rstd;  yd = gd xh + betad + g rstd (ad - mean(ad) - xh mean(xh ad)).
+// Mainloop and Z-tile staging are those of tc_dx_ln_bwd_kernel (thread = row in the epilogue); pbias <- bd, plnw <- g,
+// plnb <- gd, betad is read from global memory (broadcast).  Xd == nullptr (first layer: the normalised observations
+// carry no tangent) runs phase 1 only.
+template <int NT, int ACT, int PASSES>
+__global__ void __launch_bounds__(128, 1) tc_jvp_linear_ln_kernel(const float* __restrict__ X, int ldx,
+                                                                  const float* __restrict__ Xd,
+                                                                  const float* __restrict__ tiles,
+                                                                  const float* __restrict__ tiles_d, int nchunks,
+                                                                  const float* __restrict__ bd, const float* __restrict__ lnw,
+                                                                  const float* __restrict__ lnwd, const float* __restrict__ lnbd,
+                                                                  const float* __restrict__ Zp, const float* __restrict__ stats_p,
+                                                                  float* __restrict__ Yd, int64_t M, int Np, int Kred) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem<NT>& s = *reinterpret_cast<TcSmem<NT>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
+  const int64_t row = row0 + tid;
+  constexpr uint32_t B_BYTES = 2u * NT * TC_KC * sizeof(float);
+  for (int i = tid; i < NT; i += 128) {
+    s.pbias[i] = i < Np ? bd[i] : 0.f;
+    s.plnw[i] = i < Np ? lnw[i] : 0.f;
+    s.plnb[i] = i < Np ? lnwd[i] : 0.f;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full_b[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"((uint32_t)NT) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  constexpr uint32_t idesc = umma_idesc_tf32(NT);
+  uint32_t ph_full[2] = {0, 0}, ph_empty[2] = {0, 0};
+  const int first = Xd != nullptr ? 0 : nchunks;   // chunk counter runs over [first, 2 nchunks)
+  const int total = 2 * nchunks;
+  for (int cc = first; cc < total; ++cc) {
+    const int st = (cc - first) % TC_STAGES;
+    const bool tangent_w = cc >= nchunks;          // phase 1: A = X, B = tangent weight images
+    const int c = tangent_w ? cc - nchunks : cc;
+    if (cc - first >= TC_STAGES) { mbar_wait(&s.empty[st], ph_empty[st]); ph_empty[st] ^= 1; }
+    if (tid == 0) {
+      mbar_expect_tx(&s.full_b[st], B_BYTES);
+      tma_bulk_g2s(s.b[st], (tangent_w ? tiles_d : tiles) + (int64_t)c * (2 * NT * TC_KC), B_BYTES, &s.full_b[st]);
+    }
+    {
+      float* ahi = s.a[st][0];
+      float* alo = s.a[st][1];
+      const int base = ((tid >> 3) * 8) * 32 + (tid & 7) * 4;
+      const float* xr = (tangent_w ? X : Xd) + row * ldx + c * TC_KC;
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M && c * TC_KC + kc * 4 < Kred) v = *reinterpret_cast<const float4*>(xr + kc * 4);
+        float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        *reinterpret_cast<float4*>(ahi + base + kc * 32) = h;
+        if (PASSES == 3) *reinterpret_cast<float4*>(alo + base + kc * 32) = make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(&s.full_b[st], ph_full[st]);
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(s.a[st][0]), a_lo = smem_u32(s.a[st][1]);
+      const uint32_t b_hi = smem_u32(s.b[st]), b_lo = b_hi + NT * TC_KC * sizeof(float);
+#pragma unroll
+      for (int j = 0; j < TC_KC / 8; ++j) {
+        const uint32_t off = j * 256;
+        const uint64_t dah = umma_desc(a_hi + off, 128, 1024), dbh = umma_desc(b_hi + off, 128, 1024);
+        umma_tf32(tmem, dah, dbh, idesc, ((cc - first) | j) != 0);
+        if (PASSES == 3) {
+          const uint64_t dal = umma_desc(a_lo + off, 128, 1024), dbl = umma_desc(b_lo + off, 128, 1024);
+          umma_tf32(tmem, dal, dbh, idesc, 1);
+          umma_tf32(tmem, dah, dbl, idesc, 1);
+        }
+      }
+      umma_commit(&s.empty[st]);
+      if (cc == total - 1) umma_commit(&s.done);
+    }
+    ph_full[st] ^= 1;
+  }
+  mbar_wait(&s.done, 0);
+  tc_fence_after();
+
+  // ---- epilogue (thread = row): Z tile staged through the idle operand stage, transformed in place into yd
+  constexpr int CPR = NT / 4;
+  constexpr bool kViaSmem = (size_t)TC_BM * NT * 4 <= sizeof(s.a) + sizeof(s.b);
+  float4* tile = reinterpret_cast<float4*>(&s.a[0][0][0]);
+  const int nvalid = (int)(M - row0 < TC_BM ? M - row0 : TC_BM);
+  if (kViaSmem) {
+    for (int i = tid; i < TC_BM * CPR; i += 128) {
+      const int r = i / CPR, lc = i % CPR;
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nvalid && lc * 4 < Np) z = *reinterpret_cast<const float4*>(Zp + (row0 + r) * Np + lc * 4);
+      tile[r * CPR + (lc ^ (r & (CPR - 1) & 31))] = z;
+    }
+  }
+  __syncthreads();
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const bool rok = row < M;
+  const int sw = tid & (CPR - 1) & 31;
+  float mu = 0.f, rstd = 0.f;
+  if (rok) { mu = stats_p[row * 2]; rstd = stats_p[row * 2 + 1]; }
+  const float inv_n = 1.f / (float)Np;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c0 = 0; c0 < Np; c0 += 32) {
+    float v[32];
+    tmem_ld32(trow + c0, v);
+#pragma unroll
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+      if (c0 + j4 < Np) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kViaSmem) z = tile[tid * CPR + (((c0 + j4) >> 2) ^ sw)];
+        else if (rok) z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        const float4 b4 = *reinterpret_cast<const float4*>(&s.pbias[c0 + j4]);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float ad = rok ? act_bwd<ACT>(zz[q]) * (v[j4 + q] + bb[q]) : 0.f;
+          const float x = rok ? (act_fwd<ACT>(zz[q]) - mu) * rstd : 0.f;
+          s1 += ad;
+          s2 = fmaf(ad, x, s2);
+        }
+      }
+    }
+  }
+  const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+  for (int c0 = 0; c0 < Np; c0 += 32) {
+    float v[32];
+    tmem_ld32(trow + c0, v);
+#pragma unroll
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+      if (c0 + j4 < Np) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int slot = tid * CPR + (((c0 + j4) >> 2) ^ sw);
+        if (kViaSmem) z = tile[slot];
+        else if (rok) z = *reinterpret_cast<const float4*>(Zp + row * Np + c0 + j4);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        const float4 b4 = *reinterpret_cast<const float4*>(&s.pbias[c0 + j4]);
+        const float4 g4 = *reinterpret_cast<const float4*>(&s.plnw[c0 + j4]);
+        const float4 d4 = *reinterpret_cast<const float4*>(&s.plnb[c0 + j4]);
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(lnbd + c0 + j4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float ad = act_bwd<ACT>(zz[q]) * (v[j4 + q] + bb[q]);
+          const float x = (act_fwd<ACT>(zz[q]) - mu) * rstd;
+          o[q] = dd[q] * x + ee[q] + gg[q] * rstd * (ad - m1 - x * m2);
+        }
+        const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+        if (kViaSmem) tile[slot] = o4;
+        else if (rok) *reinterpret_cast<float4*>(Yd + row * Np + c0 + j4) = o4;
+      }
+    }
+  }
+  if (kViaSmem) {
+    __syncthreads();
+    for (int i = tid; i < TC_BM * CPR; i += 128) {
+      const int r = i / CPR, lc = i % CPR;
+      if (r < nvalid && lc * 4 < Np)
+        *reinterpret_cast<float4*>(Yd + (row0 + r) * Np + lc * 4) = tile[r * CPR + (lc ^ (r & (CPR - 1) & 31))];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NT) : "memory");
+}
+
+template <int NT, int PASSES>
+static int launch_tc_jvp_nt(int act, const float* X, int ldx, const float* Xd, const float* tiles, const float* tiles_d,
+                            int nchunks, const float* bd, const float* lnw, const float* lnwd, const float* lnbd,
+                            const float* Z, const float* stats, float* Yd, int64_t M, int N, int Kred, cudaStream_t st) {
+  const size_t smem = sizeof(TcSmem<NT>) + 1024;
+  dim3 grid((unsigned)ceil_div64(M, TC_BM));
+#define HB_TC_CASE(A)                                                                                       \
+  case A: {                                                                                                 \
+    auto kern = tc_jvp_linear_ln_kernel<NT, A, PASSES>;                                                     \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+    kern<<<grid, 128, smem, st>>>(X, ldx, Xd, tiles, tiles_d, nchunks, bd, lnw, lnwd, lnbd, Z, stats, Yd, M, N, Kred); \
+  } break;
+  switch (act) {
+    HB_TC_CASE(HB_ACT_RELU) HB_TC_CASE(HB_ACT_TANH) HB_TC_CASE(HB_ACT_SIGMOID) HB_TC_CASE(HB_ACT_LEAKY_RELU)
+    HB_TC_CASE(HB_ACT_SELU) HB_TC_CASE(HB_ACT_HARDSWISH) HB_TC_CASE(HB_ACT_IDENTITY)
+    default: set_error("activation %d", act); return HB_ERR_UNSUPPORTED;
+  }
+#undef HB_TC_CASE
+  HB_LAUNCH_DONE(st, shape_label(PASSES == 3 ? "tc_jvp_linear_ln_3xtf32" : "tc_jvp_linear_ln_tf32", M, N, Kred));
+  return HB_OK;
+}
+
+int launch_tc_jvp_linear_ln(int passes, int act, const float* X, int ldx, const float* Xd, const float* tiles,
+                            const float* tiles_d, int nchunks, const float* bd, const float* lnw, const float* lnwd,
+                            const float* lnbd, const float* Z, const float* stats, float* Yd, int64_t M, int N, int Kred,
+                            cudaStream_t st) {
+  if (M <= 0) return HB_OK;
+#define HB_TC_NT(NTV)                                                                                                   \
+  case NTV:                                                                                                             \
+    return passes == 3 ? launch_tc_jvp_nt<NTV, 3>(act, X, ldx, Xd, tiles, tiles_d, nchunks, bd, lnw, lnwd, lnbd, Z, stats, Yd, M, N, Kred, st) \
+                       : launch_tc_jvp_nt<NTV, 1>(act, X, ldx, Xd, tiles, tiles_d, nchunks, bd, lnw, lnwd, lnbd, Z, stats, Yd, M, N, Kred, st);
+  switch (tc_nt_of(N)) { HB_TC_NT(32) HB_TC_NT(64) HB_TC_NT(128) HB_TC_NT(256) }
+#undef HB_TC_NT
+  return HB_ERR_UNSUPPORTED;
+}
+
 // ---- dW[n][k] += sum_r dZ[r][n] X[r][k].  The row index r is the MMA K dimension, so both operands are staged
 // TRANSPOSED into the same K-major image the forward kernels use:  image(f, r) = [f/8][r/4][f%8][r%4].
 // Thread t owns feature t: it reads 4 consecutive rows of its column with scalar loads (coalesced across the

@@ -309,6 +309,11 @@ int hb_value_forward_rnn(const hb_net_desc* d, const float* prepared, const floa
  * persistent per-sequence kernel (h = 64 only; compiled but not yet run on a GPU).  Env: HB_RNN_IMPL=persistent. */
 int hb_set_rnn_impl(int impl);
 int hb_get_rnn_impl(void);
+/* Tangent block of the trust-region Fisher-vector product: 0 = FP32 FFMA tiles (default, GPU-verified), 1 = EXPERIMENTAL
+ * tcgen05 kernel (K-doubled product, LayerNorm-tangent epilogue; compiled but not yet run on a GPU; needs the
+ * tensor-core GEMM mode).  */
+int hb_set_trpo_jvp_impl(int impl);
+int hb_get_trpo_jvp_impl(void);
 
 /* ---- trust-region (HATRPO) update: harl/algorithms/actors/hatrpo.py:37-194, harl/utils/trpo_util.py ------- *
  * The surrogate gradient is hb_ppo_actor_grad with use_clip = 0 and entropy_coef = 0 (it returns the gradient of
