@@ -346,8 +346,69 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "B200_PROFILING.md fallback (of fallback)"}
 
 
-def cpu_reference_run(wl, steps, warmup, n_sample):
-    """The CPU oracle port on a bounded sample (n_sample rollout threads) of the workload."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _ref_spec(wl, n, steps, warmup, cuda, threads, budget_s):
+    """JSON spec for baseline/ref_runner.py: the reference's own argument dicts for this workload."""
+    from harl_b200.envs.synthetic import resolve_shapes
+
+    args, algo_args, env_args = make_args(wl, 1, n_override=n)
+    shapes = resolve_shapes(args["env"], env_args)
+    env_args = {k: v for k, v in env_args.items() if k != "host"}
+    env_args["state_type"] = shapes["state_type"]
+    if args["env"] in ("smac", "smacv2"):
+        # labels only (the env itself is the synthetic one): the SMAC loggers of the reference use np.int (removed from
+        # NumPy >= 1.24, SURVEY.md section 8(c)); the MPE logger is the plain base logger
+        args = dict(args, env="pettingzoo_mpe")
+        env_args.update(scenario="simple_spread_v2", continuous_actions=False)
+    return dict(args=args, algo_args=algo_args, env_args=env_args, shapes=shapes, n_rollout_threads=n, steps=steps,
+                warmup=warmup, cuda=bool(cuda), torch_threads=threads, budget_s=budget_s)
+
+
+def _ref_subprocess(spec, timeout_s):
+    env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH", "RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_runner.py"), json.dumps(spec)],
+                       cwd=os.path.join(ROOT, "baseline"), env=env, capture_output=True, text=True, timeout=timeout_s)
+    if r.returncode != 0:
+        raise RuntimeError("baseline/ref_runner.py failed:\n" + r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def reference_run(wl, steps, warmup, n, cuda=False, budget_s=150.0):
+    """The UNMODIFIED reference (baseline/_ref, kind "reference") through its own OnPolicy*Runner.run() on this box's
+    host cores (or, cuda=True, with device.cuda=True -- the secondary bar of BASELINE.md) at n rollout threads.
+    Falls back to the oracle CPU port (kind "port") when baseline/_ref is absent."""
+    ncpu = os.cpu_count() or 1
+    w = WORKLOADS[wl]
+    if not os.path.isdir(os.path.join(REF_DIR, "harl")):
+        res = cpu_port_run(wl, max(1, min(steps, 3)), min(warmup, 1), min(n, 512))
+        res["fallback"] = "baseline/_ref not present: oracle port"
+        return res
+    # torch thread count: the reference default (device.torch_threads=4, happo.yaml) and wider settings are probed on a
+    # small sample (256 rollout threads, 1 + 1 iterations each); the fastest runs the measurement
+    probe = {}
+    cands = [4] if cuda else sorted({4, min(16, ncpu), min(32, ncpu)})
+    if len(cands) > 1:
+        for th in cands:
+            probe[th] = _ref_subprocess(_ref_spec(wl, min(n, 256), 1, 1, False, th, 1e9), 600)["seconds_per_step"]
+        threads = min(probe, key=probe.get)
+    else:
+        threads = cands[0]
+    out = _ref_subprocess(_ref_spec(wl, n, steps, warmup, cuda, threads, budget_s), 3600)
+    dev = "device.cuda=True on cuda:0" if cuda else f"host cores, torch threads={threads} (fastest of {sorted(probe) or cands} on a 256-thread probe)"
+    return dict(value=out["value"], unit="env-steps/s", cores=threads, kind="reference", seconds_per_step=out["seconds_per_step"],
+                host_cpus=ncpu, thread_probe_s={str(k): round(v, 3) for k, v in probe.items()},
+                timed_iterations=out["timed_iterations"], warmup_iterations=out["warmup_iterations"],
+                iterations_s=out["iterations_s"], n_rollout_threads=n, cuda=bool(cuda), harl_file=out["harl_file"],
+                versions={"torch": out["torch"], "numpy": out["numpy"]},
+                sample=f"{w['desc']}" + ("" if n == w["n"] else f" with n_rollout_threads reduced to {n} (cost is linear in it)") +
+                       f"; {out['timed_iterations']} timed iteration(s) after {out['warmup_iterations']} warm-up of the unmodified "
+                       f"reference runner (baseline/_ref: pip install --no-deps --target of /root/reference), {dev}")
+
+
+def cpu_port_run(wl, steps, warmup, n_sample):
+    """The CPU oracle port on a bounded sample (n_sample rollout threads) of the workload (cross-check of the reference arm)."""
     import torch
 
     from harl_b200.envs.synthetic import resolve_shapes
@@ -359,8 +420,6 @@ def cpu_reference_run(wl, steps, warmup, n_sample):
     env = NumpySyntheticEnv(shapes, n_sample, seed=1)
     r = OracleRunner(cfg, env, state_type=shapes["state_type"], seed=1)
     r.warmup()
-    # thread count: the reference default (torch_threads=4, happo.yaml:13) and wider settings are probed on one
-    # iteration each; the fastest is used (tiny per-step tensors make "all cores" slower than a few threads)
     ncpu = os.cpu_count() or 1
     probe = {}
     for th in sorted({4, min(16, ncpu), min(32, ncpu)}):
@@ -393,6 +452,10 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=256, help="n_rollout_threads of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-n", type=int, default=0, help="--impl reference: n_rollout_threads (default: the workload's own)")
+    ap.add_argument("--ref-cuda", action="store_true", help="--impl reference: device.cuda=True (the reference on the B200)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-time budget of the timed run")
+    ap.add_argument("--ref-cross-check", action="store_true", help="--impl reference: also time the oracle CPU port")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default="", help="write the per-kernel event profile of one iteration here")
     a = ap.parse_args()
@@ -416,13 +479,19 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        n_sample = min(a.cpu_sample * 2, wl["n"])
-        res = cpu_reference_run(a.workload, max(1, a.steps), min(a.warmup, 1), n_sample)
+        # the unmodified reference at the bench configuration itself (same n_rollout_threads, T, networks), a bounded
+        # number of iterations: >= 3 timed ones, stopping once --ref-budget-s of wall time is spent
+        n_ref = a.ref_n or wl["n"]
+        res = reference_run(a.workload, max(3, a.steps), max(1, min(a.warmup, 1)), n_ref, cuda=a.ref_cuda, budget_s=a.ref_budget_s)
         line = dict(base, impl="reference", value=res["value"], ms_per_step=1e3 * res["seconds_per_step"],
                     cpu_baseline=res, gpu_launches=0,
                     e2e={"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-        line["config"]["reference_note"] = ("PKU-MARL/HARL is pure Python and /root/reference is not on the GPU box; this arm "
-                                            "times the oracle CPU port of the same path (kind=port)")
+        line["reference"] = {"kind": res["kind"], "n_rollout_threads": n_ref, "same_config": n_ref == wl["n"],
+                             "timed_iterations": res.get("timed_iterations"), "cuda": bool(a.ref_cuda),
+                             "note": "unmodified PKU-MARL/HARL OnPolicy*Runner.run() from baseline/_ref (two shims: tensorboardX "
+                                     "stub, synthetic batched env), see baseline/ref_runner.py"}
+        if a.ref_cross_check and res["kind"] == "reference":
+            line["reference"]["oracle_port_cross_check"] = cpu_port_run(a.workload, 1, 1, min(256, wl["n"]))
         print(json.dumps(line), file=real_stdout, flush=True)
         return
 
@@ -496,7 +565,7 @@ def main():
         r2.close()
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_run(a.workload, 1, 1, min(a.cpu_sample, wl["n"]))
+        line["cpu_baseline"] = reference_run(a.workload, 3, 1, min(a.cpu_sample, wl["n"]), budget_s=30.0)
     if rank == 0:
         print(json.dumps(line), file=real_stdout, flush=True)
     if dist_on:

@@ -494,7 +494,13 @@ size_t trpo_extra_floats(const hb::PrepLayout& Q, int64_t ch) {
          (size_t)hb::round_up(Q.total - Q.tk[0], 4);
 }
 
-std::atomic<int> g_trpo_jvp_impl{0};  // 0 = FP32 FFMA tangent block (default, GPU-verified), 1 = tcgen05 (experimental)
+// 0 = FP32 FFMA tangent block, 1 = tcgen05 tangent block (both GPU-verified against each other:
+// tests/test_gpu_zz_wide_heads.py::test_tensor_core_tangent_block_equals_ffma).  Env HB_TRPO_JVP_IMPL overrides the default.
+int trpo_jvp_default() {
+  const char* e = getenv("HB_TRPO_JVP_IMPL");
+  return e ? (atoi(e) != 0) : 0;
+}
+std::atomic<int> g_trpo_jvp_impl{trpo_jvp_default()};
 
 
 }  // namespace
