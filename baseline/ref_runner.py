@@ -34,11 +34,14 @@ def _install_shims():
     sys.path.insert(0, REF)
 
     class SummaryWriter:  # configs_tools.init_dir / base_logger use these three
+        scalars = []        # (tag, value dict, step) of every add_scalars call: the reference's own logged curves
+
         def __init__(self, *a, **k):
             pass
 
-        def add_scalars(self, *a, **k):
-            pass
+        def add_scalars(self, tag, values, step=None, *a, **k):
+            if tag in ("train_episode_rewards", "eval_average_episode_rewards"):
+                SummaryWriter.scalars.append((tag, {k_: float(v) for k_, v in values.items()}, int(step)))
 
         def add_scalar(self, *a, **k):
             pass
@@ -168,12 +171,21 @@ def main():
 
     assert os.path.realpath(harl.__file__).startswith(os.path.realpath(REF)), harl.__file__
     shapes, N = spec["shapes"], spec["n_rollout_threads"]
-    rb.make_train_env = lambda env_name, seed, n_threads, env_args: SyntheticEnv(shapes, n_threads, seed=1)
+    if spec.get("env_kind") == "mpe_spread":
+        # the learnable task: NumPy twin of the batched simple_spread env (harl_b200/envs/mpe_spread.py); the repo root goes
+        # LAST on sys.path so that `harl` keeps resolving to baseline/_ref
+        sys.path.append(os.path.dirname(HERE))
+        from harl_b200.envs.mpe_spread import SimpleSpreadNumpy
+
+        rb.make_train_env = lambda env_name, seed, n_threads, env_args: SimpleSpreadNumpy(seed, n_threads, env_args)
+    else:
+        rb.make_train_env = lambda env_name, seed, n_threads, env_args: SyntheticEnv(shapes, n_threads, seed=1)
     args, algo_args, env_args = spec["args"], spec["algo_args"], spec["env_args"]
     W, K, budget = spec["warmup"], spec["steps"], float(spec.get("budget_s", 1e9))
     min_timed = min(K, int(spec.get("min_timed", 3)))
     T = algo_args["train"]["episode_length"]
-    algo_args["train"].update(n_rollout_threads=N, num_env_steps=(W + K) * T * N, log_interval=10**9, eval_interval=10**9)
+    algo_args["train"].update(n_rollout_threads=N, num_env_steps=(W + K) * T * N, log_interval=int(spec.get("log_interval", 10**9)),
+                              eval_interval=10**9)
     algo_args["eval"]["use_eval"] = False
     algo_args["device"].update(cuda=bool(spec["cuda"]), torch_threads=int(spec["torch_threads"]))
     algo_args["logger"]["log_dir"] = tempfile.mkdtemp(prefix="harl_ref_bench_")
@@ -208,6 +220,9 @@ def main():
                n_rollout_threads=N, episode_length=T, cuda=bool(spec["cuda"]), torch_threads=torch.get_num_threads(),
                host_cpus=os.cpu_count(), torch=torch.__version__, numpy=np.__version__,
                harl_file=os.path.relpath(harl.__file__, os.path.dirname(HERE)))
+    if spec.get("log_interval"):
+        out["train_episode_rewards"] = [(st, v["aver_rewards"]) for tag, v, st in sys.modules["tensorboardX"].SummaryWriter.scalars
+                                        if tag == "train_episode_rewards"]
     print(json.dumps(out), flush=True)
 
 

@@ -91,6 +91,18 @@ class AdamHyper(C.Structure):
                 ("step", C.c_int32)]
 
 
+HB_MPE_MAX_AGENTS = 8
+
+
+class MpeArgs(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("n_agents", C.c_int32), ("n_landmarks", C.c_int32), ("continuous", C.c_int32),
+                ("max_cycles", C.c_int32), ("reset_all", C.c_int32), ("seed", C.c_uint64),
+                ("pos", C.c_void_p), ("vel", C.c_void_p), ("landmarks", C.c_void_p), ("step_count", C.c_void_p),
+                ("episode", C.c_void_p), ("actions", C.c_void_p * HB_MPE_MAX_AGENTS),
+                ("obs_out", C.c_void_p * HB_MPE_MAX_AGENTS), ("share_obs_out", C.c_void_p), ("rewards_out", C.c_void_p),
+                ("rewards_na_out", C.c_void_p), ("dones_out", C.c_void_p), ("bad_out", C.c_void_p)]
+
+
 P = C.c_void_p
 # name -> (restype, argtypes); every symbol include/harl_b200.h declares
 SIGNATURES = {
@@ -142,6 +154,7 @@ SIGNATURES = {
     "hb_trpo_full_step": (C.c_int, [P, P, P, C.c_float, P, P, C.c_int, P]),
     "hb_trpo_apply_step": (C.c_int, [P, P, P, C.c_float, C.c_int, P]),
     "hb_vec_scale": (C.c_int, [P, C.c_float, C.c_int, P]),
+    "hb_mpe_spread_step": (C.c_int, [C.POINTER(MpeArgs), P]),
 }
 
 if not os.path.exists(LIB_PATH):

@@ -363,6 +363,31 @@ int hb_trpo_apply_step(float* params, const float* params0, const float* full_st
                        void* stream);
 int hb_vec_scale(float* x, float s, int n, void* stream);
 
+/* ---- batched MPE simple_spread environment --------------------------------------- *
+ * Replaces, for `pettingzoo_mpe` / `simple_spread_v2`, the per-env PettingZooMPEEnv.step + ShareSubprocVecEnv of
+ * harl/envs/pettingzoo_mpe/pettingzoo_mpe_env.py:41-88 and harl/envs/env_wrappers.py by ONE launch over all rollout
+ * threads that writes the next observations / state / team reward / done flags straight into the rollout-buffer slots.
+ * World state (device, owned by the caller): pos, vel [n_envs, n_agents, 2], landmarks [n_envs, n_landmarks, 2],
+ * step_count [n_envs] int32, episode [n_envs] uint64.  reset_all = 1: (re)initialise every world (episode 0) and
+ * write observations / state only.  Initial positions: Philox4x32-10 keyed by (seed, env, episode). */
+#define HB_MPE_MAX_AGENTS 8
+typedef struct hb_mpe_args {
+  int32_t n_envs, n_agents, n_landmarks;
+  int32_t continuous;        /* 0: Discrete(5) action index as float [n_envs, 1]; 1: Box(5) [n_envs, 5] */
+  int32_t max_cycles;        /* truncation length (25), pettingzoo_mpe_env.py:22-27 */
+  int32_t reset_all;
+  uint64_t seed;
+  float* pos; float* vel; float* landmarks;
+  int32_t* step_count; uint64_t* episode;
+  const float* actions[HB_MPE_MAX_AGENTS];
+  float* obs_out[HB_MPE_MAX_AGENTS];   /* [n_envs, 4 + 2 n_landmarks + 4 (n_agents - 1)] per agent */
+  float* share_obs_out;                /* [n_envs, n_agents * obs_dim] (EP state), nullable */
+  float* rewards_out;                  /* [n_envs] team reward, nullable */
+  float* rewards_na_out;               /* [n_envs, n_agents], nullable */
+  uint8_t* dones_out; uint8_t* bad_out;/* [n_envs, n_agents], nullable */
+} hb_mpe_args;
+int hb_mpe_spread_step(const hb_mpe_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
