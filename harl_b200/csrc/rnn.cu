@@ -239,12 +239,14 @@ __global__ void __launch_bounds__(256) gru_seq_fwd_kernel(const float* __restric
   }
 }
 
-static std::atomic<int> g_rnn_impl{-1};  // -1: read HB_RNN_IMPL once; 0 = launch per step (default), 1 = persistent
+// -1: read HB_RNN_IMPL once; 0 = launch per step ("per_step"), 1 = persistent per-sequence kernel (default since round 2:
+// GPU-verified bit-for-bit against the per-step kernels, tests/test_gpu_rnn.py; h = 64 only, other widths run per step)
+static std::atomic<int> g_rnn_impl{-1};
 int rnn_impl() {
   int v = g_rnn_impl.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("HB_RNN_IMPL");
-    v = (e != nullptr && strcmp(e, "persistent") == 0) ? 1 : 0;
+    v = (e != nullptr && strcmp(e, "per_step") == 0) ? 0 : 1;
     g_rnn_impl.store(v);
   }
   return v;

@@ -305,13 +305,14 @@ int hb_value_forward_rnn(const hb_net_desc* d, const float* prepared, const floa
                          const float* rnn_states, const float* masks, float* values, float* rnn_states_out,
                          void* ws, size_t ws_bytes, void* stream);
 
-/* GRU recurrence implementation: 0 = one GEMM + one gate kernel per step (default, GPU-verified), 1 = EXPERIMENTAL
- * persistent per-sequence kernel (h = 64 only; compiled but not yet run on a GPU).  Env: HB_RNN_IMPL=persistent. */
+/* GRU recurrence implementation: 0 = one GEMM + one gate kernel per step, 1 = persistent per-sequence kernel (h = 64; other
+ * widths run per step).  Default 1 since round 2 (bit-identical to 0 on a B200: tests/test_gpu_rnn.py).
+ * Env: HB_RNN_IMPL=per_step selects 0. */
 int hb_set_rnn_impl(int impl);
 int hb_get_rnn_impl(void);
-/* Tangent block of the trust-region Fisher-vector product: 0 = FP32 FFMA tiles (default, GPU-verified), 1 = EXPERIMENTAL
- * tcgen05 kernel (K-doubled product, LayerNorm-tangent epilogue; compiled but not yet run on a GPU; needs the
- * tensor-core GEMM mode).  */
+/* Tangent block of the trust-region Fisher-vector product: 0 = FP32 FFMA tiles, 1 = tcgen05 kernel (K-doubled product,
+ * LayerNorm-tangent epilogue; needs the tensor-core GEMM mode).  Default 1 since round 2 (verified against 0 on a B200:
+ * tests/test_gpu_zz_wide_heads.py).  Env: HB_TRPO_JVP_IMPL=0 selects 0. */
 int hb_set_trpo_jvp_impl(int impl);
 int hb_get_trpo_jvp_impl(void);
 

@@ -292,8 +292,6 @@ def test_recurrent_zero_copy_rollout_equals_generic_rollout(state_type, over):
         r.close()
 
 
-@pytest.mark.skipif(os.environ.get("HB_RUN_EXPERIMENTAL") != "1", reason="experimental persistent GRU recurrence (hb_set_rnn_impl(1)): written after the round's GPU "
-                         "budget was spent, not yet run on a GPU -- set HB_RUN_EXPERIMENTAL=1 to run")
 @pytest.mark.parametrize("recurrent_n", [1, 2])
 def test_persistent_recurrence_equals_per_step_kernels(recurrent_n):
     """hb_set_rnn_impl(1) must reproduce the launch-per-step path (same accumulation order: bit-identical states)."""

@@ -115,8 +115,6 @@ def test_fvp_wide_head_vs_oracle(recurrent, gemm_impl):
         assert np.abs(gotf[k] - want_f[k].numpy()).max() <= 5e-4 * fscale, "fvp " + k
 
 
-@pytest.mark.skipif(os.environ.get("HB_RUN_EXPERIMENTAL") != "1", reason="experimental tcgen05 tangent block (hb_set_trpo_jvp_impl(1)): written after the round's GPU "
-                         "budget was spent, not yet run on a GPU -- set HB_RUN_EXPERIMENTAL=1 to run")
 @pytest.mark.parametrize("name", ["hatrpo_parts_disc", "hatrpo_parts_box", "hatrpo_parts_disc12_h64"])
 def test_tensor_core_tangent_block_equals_ffma(name):
     """The Fisher-vector product with the tensor-core tangent block (3xTF32) vs the FP32 FFMA one."""
