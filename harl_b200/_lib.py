@@ -114,6 +114,8 @@ SIGNATURES = {
     "hb_profile_end": (C.c_int, [C.c_char_p, C.c_int]),
     "hb_set_gemm_impl": (C.c_int, [C.c_int]),
     "hb_get_gemm_impl": (C.c_int, []),
+    "hb_set_fused_update": (C.c_int, [C.c_int]),
+    "hb_get_fused_update": (C.c_int, []),
     "hb_net_layout_of": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetLayout)]),
     "hb_net_prepare": (C.c_int, [C.POINTER(NetDesc), P, P, P]),
     "hb_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64, C.c_int]),
@@ -172,7 +174,7 @@ HB_ERR_UNSUPPORTED = -2
 GEMM_IMPLS = {"fp32": 0, "3xtf32": 1, "tf32": 2}
 if os.environ.get("HB_GEMM_IMPL"):
     lib.hb_set_gemm_impl(GEMM_IMPLS[os.environ["HB_GEMM_IMPL"]])
-_NO_CHECK = {"hb_version", "hb_last_error", "hb_workspace_bytes", "hb_trpo_workspace_bytes", "hb_kernel_launch_count", "hb_profile_end", "hb_get_gemm_impl", "hb_get_rnn_impl", "hb_get_trpo_jvp_impl"}
+_NO_CHECK = {"hb_version", "hb_last_error", "hb_workspace_bytes", "hb_trpo_workspace_bytes", "hb_kernel_launch_count", "hb_profile_end", "hb_get_gemm_impl", "hb_get_rnn_impl", "hb_get_trpo_jvp_impl", "hb_get_fused_update"}
 
 # launches of library entry points since import (bench.py's gpu_launches bookkeeping)
 call_count = 0

@@ -14,6 +14,8 @@
 #include "rnn.cuh"
 #include "trpo.cuh"
 
+#include "fused_args.cuh"
+
 namespace hb {
 
 // Rows per kernel launch.  HB_CHUNK_ROWS overrides it for tuning runs (read once).
@@ -335,6 +337,17 @@ int hb_policy_evaluate(const hb_net_desc* d, const float* prepared, const hb_act
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = b->rows;
   if (rows == 0) return HB_OK;
+  if (Q.fz_ok && fused_enabled()) {  // one fused launch: feature norm -> trunk -> head, nothing round-trips HBM
+    ParamLayout P;
+    if ((rc = make_layouts(d, &P, nullptr, nullptr))) return rc;
+    fz::Args fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.obs = b->obs; fa.index = b->index; fa.rows = rows;
+    fa.actions = b->actions; fa.avail = b->avail;
+    fa.logp_out = logp_out; fa.logp_ref = logp_ref; fa.factor_inout = factor_inout;
+    fa.agg_prod = action_aggregation_prod;
+    return launch_fused_update(d, Q, P, prepared, fa, 1, nullptr, st);
+  }
   const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
@@ -369,6 +382,21 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
   int rc = check_net(d, &P, &Q, &L, 1);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (Q.fz_ok && fused_enabled() && b->rows > 0) {
+    // fused forward + loss + backward: the workspace only holds the per-CTA slots of the weight-gradient sums
+    const size_t need = (size_t)fused_max_slots() * L.total * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) { set_error("hb_ppo_actor_grad: workspace too small: need %zu bytes, have %zu", need, ws_bytes); return HB_ERR_WORKSPACE; }
+    fz::Args fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.obs = b->obs; fa.index = b->index; fa.rows = b->rows;
+    fa.actions = b->actions; fa.avail = b->avail; fa.old_logp = b->old_logp; fa.adv = b->adv; fa.factor = b->factor; fa.active = b->active;
+    fa.clip = h->clip_param; fa.entropy_coef = h->entropy_coef; fa.use_active = h->use_policy_active_masks;
+    fa.use_clip = h->use_clip; fa.agg_prod = h->action_aggregation_prod;
+    fa.part = (float*)ws; fa.part_stride = L.total; fa.scalars = scalars;
+    int slots = 0;
+    if ((rc = launch_fused_update(d, Q, P, prepared, fa, 0, &slots, st))) return rc;
+    return launch_fused_finish(d, P, params, grad, (const float*)ws, slots, L.total, norm3, 1.0, st);
+  }
   cudaError_t ce = cudaMemsetAsync(grad, 0, (size_t)L.total * sizeof(float), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_ppo_actor_grad(memset)");
   const int64_t rows = b->rows;
@@ -429,6 +457,20 @@ int hb_value_grad(const hb_net_desc* d, const float* params, const float* prepar
   int rc = check_net(d, &P, &Q, &L, 0);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (Q.fz_ok && fused_enabled() && b->rows > 0) {
+    const size_t need = (size_t)fused_max_slots() * L.total * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) { set_error("hb_value_grad: workspace too small: need %zu bytes, have %zu", need, ws_bytes); return HB_ERR_WORKSPACE; }
+    fz::Args fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.obs = b->share_obs; fa.index = b->index; fa.rows = b->rows;
+    fa.value_preds = b->value_preds; fa.returns = b->returns; fa.vn_state = vn_state;
+    fa.clip = h->clip_param; fa.huber_delta = h->huber_delta; fa.vcoef = h->value_loss_coef;
+    fa.use_huber = h->use_huber_loss; fa.use_clipped = h->use_clipped_value_loss;
+    fa.part = (float*)ws; fa.part_stride = L.total; fa.scalars = scalars;
+    int slots = 0;
+    if ((rc = launch_fused_update(d, Q, P, prepared, fa, 0, &slots, st))) return rc;
+    return launch_fused_finish(d, P, params, grad, (const float*)ws, slots, L.total, nullptr, inv_count, st);
+  }
   cudaError_t ce = cudaMemsetAsync(grad, 0, (size_t)L.total * sizeof(float), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_value_grad(memset)");
   const int64_t rows = b->rows;
@@ -740,6 +782,12 @@ int hb_set_trpo_jvp_impl(int impl) {
   return HB_OK;
 }
 int hb_get_trpo_jvp_impl(void) { return g_trpo_jvp_impl.load(); }
+
+int hb_set_fused_update(int on) {
+  hb::set_fused_enabled(on);
+  return HB_OK;
+}
+int hb_get_fused_update(void) { return hb::fused_enabled() ? 1 : 0; }
 
 int hb_set_rnn_impl(int impl) {
   HB_CHECK_ARG(impl == 0 || impl == 1, "impl must be 0 (launch per step) or 1 (experimental persistent recurrence)");

@@ -54,6 +54,13 @@ struct PrepLayout {
   int tk[HB_MAX_LAYERS], tk_chunks[HB_MAX_LAYERS], tk_nt[HB_MAX_LAYERS];
   // images of W^T for the backward dX GEMM (layers >= 1)
   int tkt[HB_MAX_LAYERS], tkt_chunks[HB_MAX_LAYERS], tkt_nt[HB_MAX_LAYERS];
+  // fused update kernel (fused_update.cu): fp16 hi/lo operand images of the LayerNorm-affine-folded weights
+  //   W'_l = W_l diag(gamma_{l-1}),  b'_l = b_l + W_l beta_{l-1}   (gamma_{-1}, beta_{-1} = the feature-norm affine)
+  // per layer, per 32-wide k-chunk (the last may be 16 wide): hi image [n_l][kc] then lo image, K-major no-swizzle core
+  // matrices; the head likewise as one [16][h] image pair.  fz_ok = 0: shape outside the fused kernel (layer-wise path).
+  int fz_ok, fz_k0p;
+  int fz_w[2], fz_chunks[2], fz_bias[2];
+  int fz_hw, fz_hbias, fz_scale;
   int total;
 };
 

@@ -1,0 +1,874 @@
+// Fused actor / critic update kernel (SURVEY.md section 7 step 4, section 8(d) "fused actor update"):
+//   ONE persistent launch per (agent, epoch, minibatch) does, per 128-row tile, entirely on chip,
+//     obs rows -> feature LayerNorm -> [Linear -> act -> LayerNorm] x 2 -> head -> PPO-clip / value loss
+//     -> d logits -> head backward -> LayerNorm/act backward x 2 -> weight-gradient accumulation,
+//   so per row and epoch the kernel reads the algorithmic bytes only (obs + a handful of scalars) and no activation ever
+//   touches HBM.  Replaces HAPPO.update's forward / loss / backward (harl/algorithms/actors/happo.py:28-91 over
+//   harl/models/base/mlp.py:25-36, act.py, distributions.py) and VCritic.update's (v_critic.py:75-146).
+//
+// Arithmetic: every GEMM runs on tcgen05 (kind::f16, fp32 accumulators in TMEM) with the error-compensated split
+//   x = hi + lo (hi = fp16(x), lo = fp16(x - hi), operands pre-scaled by powers of two into the fp16 range):
+//   D += A_hi B_hi + A_lo B_hi + A_hi B_lo -- 22-bit operands, the accuracy class of the 3xTF32 path (measured on a B200:
+//   profiles/probe_umma_layouts_r02.log) at twice its MMA rate and half its shared-memory footprint.
+//
+// LayerNorm affines are folded into the NEXT layer's weights (W' = W diag(gamma), b' = b + W beta; hb_net_prepare packs
+// the images), so the on-chip activations are the plain normalised rows xhat, the LayerNorm backward needs no per-row
+// affine work, and all affine gradients fall out of the weight gradients afterwards (optim.cu featnorm_grad_fold_kernel,
+// applied per layer).
+//
+// Layout trick: a tile image written by "thread = row" as  IMG[row/8][feature/8][row%8][8 x fp16]  is at the same time a
+//   K-major operand (rows x features: the forward / dX GEMMs) and an MN-major operand (features x rows: the weight-gradient
+//   GEMMs, whose reduction index is the row) -- no transposition anywhere (umma.cuh).  dZ overwrites xhat in place.
+//
+// CTA = 6 warps: warp 0 streams weight chunks through a TMA ring, warp 1 issues the MMAs, warps 2-5 (thread = row, TMEM
+// lane quarter = warp % 4) run the epilogues.  The phases of a tile alternate strictly between the MMA warp and the
+// epilogue warps (two mbarriers); weight gradients accumulate in TMEM across all tiles of the CTA and are written once,
+// to the CTA's slot of a split buffer (deterministic; summed by fused_slot_reduce_kernel).
+#include <cuda_fp16.h>
+
+#include <atomic>
+
+#include "common.cuh"
+#include "head_rows.cuh"
+#include "kernels.cuh"
+#include "row_helpers.cuh"
+#include "fused_args.cuh"
+#include "umma.cuh"
+
+namespace hb {
+
+int launch_featnorm_fold_at(const float* params, float* grad, int w0, int b0, int gw, int gb, int N, int K, cudaStream_t st);
+
+namespace fz {
+
+constexpr float XS = 16.f;          // activation images hold XS * xhat      (|xhat| <= sqrt(h))
+constexpr float DZS = 16.f;         // gradient images hold DZS * dZ (dZ is un-normalised: O(advantage))
+constexpr int TILE = 128;
+constexpr int NH = 16;              // padded head width (MMA N)
+constexpr int STAGES = 2;
+constexpr int STAGE_BYTES = 16384;  // one weight chunk: hi + lo images of [128][32] fp16
+constexpr int THREADS = 192;
+enum { M_GRAD = 0, M_EVAL = 1 };
+
+// TMEM columns (fp32 accumulators, 128 lanes each)
+constexpr uint32_t C_F = 0;         // forward pre-activations / backward dY      [rows][<= 128]
+constexpr uint32_t C_W1 = 128;      // dW'_1                                       [n][k <= 128]
+constexpr uint32_t C_W0 = 256;      // dW'_0                                       [n][k <= 64]
+constexpr uint32_t C_H = 320;       // head outputs                                [rows][16]
+constexpr uint32_t C_WH = 336;      // dW'_head transposed                         [feature][16]
+constexpr uint32_t C_B1 = 352;      // db'_1 in column 0                           [n][16]
+constexpr uint32_t C_B0 = 368;      // db'_0 in column 0
+constexpr uint32_t TMEM_COLS = 512;
+
+
+
+// ------------------------------------------------------------------------------------------------ image addressing
+// byte offset of (row r, 8-feature chunk ch) in a tile image with `wch` chunks per row
+__device__ __forceinline__ uint32_t img_off(int r, int ch, int wch) { return (uint32_t)(((r >> 3) * wch + ch) * 128 + (r & 7) * 16); }
+
+struct Op {  // one operand view for the MMA issuer
+  uint32_t hi, lo, lbo, sbo, adv;
+};
+__device__ __forceinline__ Op op_kmajor(uint32_t base, uint32_t img_bytes, int wch, int ch0) {  // rows x features, k offset = chunk ch0
+  return Op{base + (uint32_t)ch0 * 128u, base + img_bytes + (uint32_t)ch0 * 128u, 128u, (uint32_t)wch * 128u, 256u};
+}
+__device__ __forceinline__ Op op_mnmajor(uint32_t base, uint32_t img_bytes, int wch, int ch0) {  // features x rows, feature offset = chunk ch0
+  return Op{base + (uint32_t)ch0 * 128u, base + img_bytes + (uint32_t)ch0 * 128u, (uint32_t)wch * 128u, 128u, 2u * (uint32_t)wch * 128u};
+}
+// D (+)= A B^T over `ksteps` MMA k-steps, three passes per step (b_lo == 0: B is exact in fp16 -> two passes)
+__device__ __forceinline__ void gemm3(uint32_t d, const Op& A, const Op& B, int ksteps, uint32_t idesc, bool accumulate, bool b_has_lo = true) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t ah = um::desc(A.hi + ks * A.adv, A.lbo, A.sbo), al = um::desc(A.lo + ks * A.adv, A.lbo, A.sbo);
+    const uint64_t bh = um::desc(B.hi + ks * B.adv, B.lbo, B.sbo);
+    um::mma_f16(d, ah, bh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+    um::mma_f16(d, al, bh, idesc, 1u);
+    if (b_has_lo) {
+      const uint64_t bl = um::desc(B.lo + ks * B.adv, B.lbo, B.sbo);
+      um::mma_f16(d, ah, bl, idesc, 1u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue pieces
+// d act / dz from the post-activation value and the sign of z
+template <int ACT>
+__device__ __forceinline__ float act_prime(int act_rt, float a, bool zpos) {
+  const int A_ = ACT >= 0 ? ACT : act_rt;
+  switch (A_) {
+    case HB_ACT_RELU: return zpos ? 1.f : 0.f;
+    case HB_ACT_TANH: return 1.f - a * a;
+    case HB_ACT_SIGMOID: return a * (1.f - a);
+    case HB_ACT_LEAKY_RELU: return zpos ? 1.f : 0.01f;
+    case HB_ACT_SELU: {
+      const float al = 1.6732632423543772848170429916717f, s = 1.0507009873554804934193349852946f;
+      return zpos ? s : a + s * al;   // s * al * exp(z) = a + s * al for z <= 0
+    }
+    default: return 1.f;
+  }
+}
+template <int ACT>
+__device__ __forceinline__ float act_f(int act_rt, float z) {
+  if (ACT >= 0) return act_fwd<(ACT >= 0 ? ACT : 0)>(z);
+  return act_fwd_rt(act_rt, z);
+}
+
+// Linear -> act -> LayerNorm epilogue of one row: TMEM accumulator row -> xhat image row (hi, lo), statistics, sign mask.
+template <int ACT>
+__device__ __forceinline__ void fwd_epilogue(int act_rt, uint32_t tacc, int H, const float* __restrict__ sbias, float descale,
+                                             unsigned char* img, uint32_t img_bytes, int wch, int r, float& mu, float& rstd,
+                                             uint32_t (&mask)[4]) {
+  const float inv_n = 1.f / (float)H;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int c0 = 0; c0 < H; c0 += 32) {
+    float v[32];
+    um::tmem_ld32(tacc + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);
+      s0 += act_f<ACT>(act_rt, fmaf(v[j], descale, b4.x));
+      s1 += act_f<ACT>(act_rt, fmaf(v[j + 1], descale, b4.y));
+      s2 += act_f<ACT>(act_rt, fmaf(v[j + 2], descale, b4.z));
+      s3 += act_f<ACT>(act_rt, fmaf(v[j + 3], descale, b4.w));
+    }
+  }
+  mu = ((s0 + s1) + (s2 + s3)) * inv_n;
+  s0 = s1 = s2 = s3 = 0.f;
+  for (int c0 = 0; c0 < H; c0 += 32) {
+    float v[32];
+    um::tmem_ld32(tacc + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);
+      float d;
+      d = act_f<ACT>(act_rt, fmaf(v[j], descale, b4.x)) - mu; s0 = fmaf(d, d, s0);
+      d = act_f<ACT>(act_rt, fmaf(v[j + 1], descale, b4.y)) - mu; s1 = fmaf(d, d, s1);
+      d = act_f<ACT>(act_rt, fmaf(v[j + 2], descale, b4.z)) - mu; s2 = fmaf(d, d, s2);
+      d = act_f<ACT>(act_rt, fmaf(v[j + 3], descale, b4.w)) - mu; s3 = fmaf(d, d, s3);
+    }
+  }
+  rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * inv_n + 1e-5f);
+  const float rs = rstd * XS, sh = -mu * rstd * XS;
+  for (int c0 = 0; c0 < H; c0 += 32) {
+    float v[32];
+    um::tmem_ld32(tacc + c0, v);
+    uint32_t m = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float x[8];
+      const float4 ba = *reinterpret_cast<const float4*>(sbias + c0 + q * 8), bb = *reinterpret_cast<const float4*>(sbias + c0 + q * 8 + 4);
+      const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(v[q * 8 + j], descale, bq[j]);
+        m |= z > 0.f ? (1u << (q * 8 + j)) : 0u;
+        x[j] = fmaf(act_f<ACT>(act_rt, z), rs, sh);
+      }
+      uint4 hi, lo;
+      um::split8(x, hi, lo);
+      const uint32_t off = img_off(r, (c0 >> 3) + q, wch);
+      *reinterpret_cast<uint4*>(img + off) = hi;
+      *reinterpret_cast<uint4*>(img + img_bytes + off) = lo;
+    }
+    if (c0 == 0) mask[0] = m; else if (c0 == 32) mask[1] = m; else if (c0 == 64) mask[2] = m; else mask[3] = m;
+  }
+}
+
+// LayerNorm + activation backward of one row: g = dL/dxhat from TMEM, xhat from the image; writes DZS * dZ over xhat.
+template <int ACT>
+__device__ __forceinline__ void bwd_epilogue(int act_rt, uint32_t tacc, int H, float descale, unsigned char* img,
+                                             uint32_t img_bytes, int wch, int r, float mu, float rstd, const uint32_t (&mask)[4],
+                                             bool row_ok) {
+  const float inv_n = 1.f / (float)H, inv_xs = 1.f / XS;
+  float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+  for (int c0 = 0; c0 < H; c0 += 32) {
+    float g[32];
+    um::tmem_ld32(tacc + c0, g);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t off = img_off(r, (c0 >> 3) + q, wch);
+      float x[8];
+      um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float g0 = g[q * 8 + j] * descale, g1 = g[q * 8 + j + 1] * descale;
+        s1a += g0; s1b += g1;
+        s2a = fmaf(g0, x[j] * inv_xs, s2a); s2b = fmaf(g1, x[j + 1] * inv_xs, s2b);
+      }
+    }
+  }
+  const float m1 = (s1a + s1b) * inv_n, m2 = (s2a + s2b) * inv_n;
+  const float stdv = 1.f / rstd;
+  const float k = row_ok ? rstd * DZS : 0.f;
+  for (int c0 = 0; c0 < H; c0 += 32) {
+    float g[32];
+    um::tmem_ld32(tacc + c0, g);
+    const uint32_t m = c0 == 0 ? mask[0] : (c0 == 32 ? mask[1] : (c0 == 64 ? mask[2] : mask[3]));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t off = img_off(r, (c0 >> 3) + q, wch);
+      float x[8], dz[8];
+      um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = x[j] * inv_xs;
+        const float a = fmaf(xh, stdv, mu);
+        const float t = fmaf(-xh, m2, g[q * 8 + j] * descale - m1);
+        dz[j] = k * t * act_prime<ACT>(act_rt, a, (m >> (q * 8 + j)) & 1u);
+      }
+      uint4 hi, lo;
+      um::split8(dz, hi, lo);
+      *reinterpret_cast<uint4*>(img + off) = hi;
+      *reinterpret_cast<uint4*>(img + img_bytes + off) = lo;
+    }
+  }
+}
+
+__device__ __forceinline__ float huber_v(float e, float d, int use_huber, float* de) {
+  if (!use_huber) { *de = e; return e * e / 2.f; }
+  const float ae = fabsf(e);
+  if (ae <= d) { *de = e; return e * e / 2.f; }
+  *de = e > 0.f ? d : -d;
+  return d * (ae - d / 2.f);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int HEAD, int MODE, int ACT>
+__global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_constant__ Args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.H, K0p = a.K0p;
+  const int wch0 = K0p >> 3, wchx = 16, wchd = NH >> 3, wchh = H >> 3;   // 8-feature chunks per image row
+  const uint32_t x0_bytes = TILE * K0p * 2, x_bytes = TILE * 128 * 2, dl_bytes = TILE * NH * 2, wh_bytes = NH * H * 2;
+  unsigned char* p = smem;
+  unsigned char* X0 = p; p += 2 * x0_bytes;
+  unsigned char* X1 = p; p += 2 * x_bytes;
+  unsigned char* X2 = p; p += 2 * x_bytes;
+  unsigned char* DL = p; p += 2 * dl_bytes;
+  unsigned char* ONES = p; p += dl_bytes;
+  unsigned char* WH = p; p += 2 * wh_bytes;
+  unsigned char* ring = p; p += STAGES * STAGE_BYTES;
+  float* sb0 = reinterpret_cast<float*>(p); p += 128 * 4;
+  float* sb1 = reinterpret_cast<float*>(p); p += 128 * 4;
+  float* sbh = reinterpret_cast<float*>(p); p += NH * 4;
+  float* sstd = reinterpret_cast<float*>(p); p += 4 * NH * 4;       // Box: std, log std, d std / d log_std param, 1 / var
+  float* sacc = reinterpret_cast<float*>(p); p += 2 * NH * 4;       // end-of-kernel sums: head bias grads, log_std grads
+  double* sred = reinterpret_cast<double*>(p); p += 4 * 4 * 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p); p += 8 * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p);
+  uint64_t* w_full = bars;            // [STAGES] weight chunk landed
+  uint64_t* w_empty = bars + STAGES;  // [STAGES] MMAs reading the chunk retired
+  uint64_t* e2m = bars + 2 * STAGES;  // epilogue warps -> MMA warp (128 arrivals)
+  uint64_t* m2e = e2m + 1;            // MMA warp -> epilogue warps (tcgen05.commit)
+
+  const long long ntiles = (a.rows + TILE - 1) / TILE;
+  const int nch1 = H >> 5;
+  constexpr bool GRAD = MODE == M_GRAD;
+
+  // ---- one-time setup
+  for (int i = tid; i < (int)((2 * x_bytes) / 16); i += THREADS) {
+    reinterpret_cast<uint4*>(X1)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(X2)[i] = make_uint4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < (int)((2 * x0_bytes) / 16); i += THREADS) reinterpret_cast<uint4*>(X0)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)((2 * dl_bytes) / 16); i += THREADS) reinterpret_cast<uint4*>(DL)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < TILE * 2; i += THREADS)   // ONES[row][16]: column 0 = 1.0, 16-byte chunks [row/8][2][row%8]
+    reinterpret_cast<uint4*>(ONES)[i] = ((i >> 3) & 1) ? make_uint4(0, 0, 0, 0) : make_uint4(0x00003C00u, 0, 0, 0);
+  for (int i = tid; i < (int)((2 * wh_bytes) / 16); i += THREADS) reinterpret_cast<uint4*>(WH)[i] = reinterpret_cast<const uint4*>(a.imgh)[i];
+  for (int i = tid; i < 128; i += THREADS) { sb0[i] = i < H ? a.bias0[i] : 0.f; sb1[i] = i < H ? a.bias1[i] : 0.f; }
+  if (tid < NH) {
+    sbh[tid] = a.biash[tid];
+    sacc[tid] = sacc[NH + tid] = 0.f;
+    float sd = 1.f, ls = 0.f, dsd = 0.f;
+    if (HEAD == HB_HEAD_BOX && tid < a.out) {
+      const float sig = 1.f / (1.f + expf(-a.log_std[tid] / a.std_x));
+      sd = sig * a.std_y;
+      ls = logf(sd);
+      dsd = a.std_y * sig * (1.f - sig) / a.std_x;
+    }
+    sstd[tid] = sd; sstd[NH + tid] = ls; sstd[2 * NH + tid] = dsd; sstd[3 * NH + tid] = 1.f / (sd * sd);
+  }
+  if (tid < 16) sred[tid] = 0.0;
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { um::mbar_init(&w_full[i], 1); um::mbar_init(&w_empty[i], 1); }
+    um::mbar_init(e2m, 128);
+    um::mbar_init(m2e, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um::smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  um::fence_async_smem();
+  um::tc_fence_before();
+  __syncthreads();
+  um::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float ws0 = a.scales[0], ws1 = a.scales[1], wsh = a.scales[2];
+
+  if (warp == 0) {
+    // ================================================================ weight-chunk producer (one lane)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int pass = 0; pass < (GRAD ? 3 : 2); ++pass) {
+          const int layer = pass == 0 ? 0 : 1;
+          const int nch = layer == 0 ? a.nch0 : nch1, kp = layer == 0 ? K0p : H;
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(layer == 0 ? a.img0 : a.img1);
+          for (int c = 0; c < nch; ++c, ++it) {
+            const int kc = kp - 32 * c < 32 ? kp - 32 * c : 32;
+            const uint32_t bytes = 2u * (uint32_t)H * (uint32_t)kc * 2u;
+            const uint32_t st = it % STAGES, use = it / STAGES;
+            if (use > 0) um::mbar_wait(&w_empty[st], (use - 1) & 1);
+            um::mbar_expect_tx(&w_full[st], bytes);
+            um::tma_bulk_g2s(ring + st * STAGE_BYTES, src + (size_t)c * (2u * H * 32u * 2u), bytes, &w_full[st]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one lane)
+    if (lane == 0) {
+      uint32_t it = 0, pe = 0;
+      bool first = true;
+      const uint32_t X0a = um::smem_u32(X0), X1a = um::smem_u32(X1), X2a = um::smem_u32(X2), DLa = um::smem_u32(DL);
+      const uint32_t ONa = um::smem_u32(ONES), WHa = um::smem_u32(WH), RGa = um::smem_u32(ring);
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        auto wait_e = [&]() { um::mbar_wait(e2m, pe); pe ^= 1; um::tc_fence_after(); };
+        auto chunk = [&](int kc, auto&& body) {   // consume the next ring stage
+          const uint32_t st = it % STAGES, use = it / STAGES;
+          um::mbar_wait(&w_full[st], use & 1);
+          um::tc_fence_after();
+          body(RGa + st * STAGE_BYTES, (uint32_t)H * (uint32_t)kc * 2u);
+          um::commit(&w_empty[st]);
+          ++it;
+        };
+        // -- layer 0: C_F = X0 W0'^T
+        wait_e();
+        for (int c = 0; c < a.nch0; ++c) {
+          const int kc = K0p - 32 * c < 32 ? K0p - 32 * c : 32;
+          chunk(kc, [&](uint32_t wb, uint32_t wimg) {
+            gemm3(tmem + C_F, op_kmajor(X0a, x0_bytes, wch0, 4 * c), op_kmajor(wb, wimg, kc >> 3, 0), kc >> 4,
+                  um::idesc_f16(H, 0, 0), c > 0);
+          });
+        }
+        um::commit(m2e);
+        // -- layer 1: C_F = X1 W1'^T
+        wait_e();
+        for (int c = 0; c < nch1; ++c)
+          chunk(32, [&](uint32_t wb, uint32_t wimg) {
+            gemm3(tmem + C_F, op_kmajor(X1a, x_bytes, wchx, 4 * c), op_kmajor(wb, wimg, 4, 0), 2, um::idesc_f16(H, 0, 0), c > 0);
+          });
+        um::commit(m2e);
+        // -- head: C_H = X2 Wh'^T
+        wait_e();
+        gemm3(tmem + C_H, op_kmajor(X2a, x_bytes, wchx, 0), op_kmajor(WHa, wh_bytes, wchh, 0), H >> 4, um::idesc_f16(NH, 0, 0), false);
+        um::commit(m2e);
+        if (GRAD) {
+          // -- head backward: C_F = DL Wh' (dL/dxhat_1);  C_WH += X2^T DL
+          wait_e();
+          gemm3(tmem + C_F, op_kmajor(DLa, dl_bytes, wchd, 0), op_mnmajor(WHa, wh_bytes, wchh, 0), 1, um::idesc_f16(H, 0, 1), false);
+          gemm3(tmem + C_WH, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(DLa, dl_bytes, wchd, 0), TILE >> 4,
+                um::idesc_f16(NH, 1, 1), !first);
+          um::commit(m2e);
+          // -- layer 1 backward: C_W1 += dZ1^T X1;  C_B1 += dZ1^T 1;  C_F = dZ1 W1' (dL/dxhat_0), one weight chunk at a time
+          wait_e();
+          gemm3(tmem + C_W1, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(X1a, x_bytes, wchx, 0), TILE >> 4,
+                um::idesc_f16(H, 1, 1), !first);
+          gemm3(tmem + C_B1, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(ONa, dl_bytes, wchd, 0), TILE >> 4,
+                um::idesc_f16(NH, 1, 1), !first, false);
+          for (int c = 0; c < nch1; ++c)
+            chunk(32, [&](uint32_t wb, uint32_t wimg) {
+              gemm3(tmem + C_F + 32 * c, op_kmajor(X2a, x_bytes, wchx, 0), op_mnmajor(wb, wimg, 4, 0), H >> 4,
+                    um::idesc_f16(32, 0, 1), false);
+            });
+          um::commit(m2e);
+          // -- layer 0 backward: C_W0 += dZ0^T X0;  C_B0 += dZ0^T 1
+          wait_e();
+          gemm3(tmem + C_W0, op_mnmajor(X1a, x_bytes, wchx, 0), op_mnmajor(X0a, x0_bytes, wch0, 0), TILE >> 4,
+                um::idesc_f16(K0p, 1, 1), !first);
+          gemm3(tmem + C_B0, op_mnmajor(X1a, x_bytes, wchx, 0), op_mnmajor(ONa, dl_bytes, wchd, 0), TILE >> 4,
+                um::idesc_f16(NH, 1, 1), !first, false);
+          um::commit(m2e);
+          first = false;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ epilogue warps: thread = row
+    const int q = warp & 3, r = q * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t pm = 0;
+    auto wait_m = [&]() { um::mbar_wait(m2e, pm); pm ^= 1; um::tc_fence_after(); };
+    auto signal = [&]() { um::fence_async_smem(); um::tc_fence_before(); um::mbar_arrive(e2m); };
+    const int na = a.out;
+    float gb[NH], gs[HEAD == HB_HEAD_BOX ? NH : 1];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) gb[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < (HEAD == HB_HEAD_BOX ? NH : 1); ++j) gs[j] = 0.f;
+    float s_loss = 0.f, s_ent = 0.f, s_ratio = 0.f, s_rows = 0.f;
+    float vmean = 0.f, vstd = 1.f;
+    if (HEAD == HB_HEAD_VALUE && a.vn_state != nullptr) {  // valuenorm.py:38-45
+      const float d = fmaxf(a.vn_state[2], 1e-5f);
+      const float mu = a.vn_state[0] / d, msq = a.vn_state[1] / d;
+      vmean = mu;
+      vstd = sqrtf(fmaxf(msq - mu * mu, 1e-2f));
+    }
+    bool pending = false;   // a backward MMA group of the previous tile may still read X0 / X1
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const long long row = t * TILE + r;
+      const bool ok = row < a.rows;
+      const long long src = ok ? (a.index ? (long long)a.index[row] : row) : 0;
+      // ---- feature LayerNorm of the observation row (mlp.py:57-66), exact two-pass statistics
+      const float* o = a.obs + src * a.in_dim;
+      float mean = 0.f, rs = 0.f;
+      {
+        float s = 0.f;
+        for (int k = 0; k < a.in_dim; ++k) s += ok ? __ldg(o + k) : 0.f;
+        mean = s / (float)a.in_dim;
+        float qv = 0.f;
+        for (int k = 0; k < a.in_dim; ++k) { const float d = (ok ? __ldg(o + k) : 0.f) - mean; qv = fmaf(d, d, qv); }
+        rs = rsqrtf(qv / (float)a.in_dim + 1e-5f);
+      }
+      if (pending) { wait_m(); pending = false; }
+      for (int ch = 0; ch < wch0; ++ch) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = ch * 8 + j;
+          x[j] = (ok && k < a.in_dim) ? (__ldg(o + k) - mean) * rs * XS : 0.f;
+        }
+        uint4 hi, lo;
+        um::split8(x, hi, lo);
+        const uint32_t off = img_off(r, ch, wch0);
+        *reinterpret_cast<uint4*>(X0 + off) = hi;
+        *reinterpret_cast<uint4*>(X0 + x0_bytes + off) = lo;
+      }
+      signal();
+      // ---- layer 0
+      float mu0, rstd0, mu1, rstd1;
+      uint32_t mask0[4] = {0, 0, 0, 0}, mask1[4] = {0, 0, 0, 0};
+      wait_m();
+      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb0, 1.f / (XS * ws0), X1, x_bytes, wchx, r, mu0, rstd0, mask0);
+      signal();
+      // ---- layer 1
+      wait_m();
+      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb1, 1.f / (XS * ws1), X2, x_bytes, wchx, r, mu1, rstd1, mask1);
+      signal();
+      // ---- head
+      wait_m();
+      float hv[NH];
+      um::tmem_ld16(tl + C_H, hv);
+      const float hdesc = 1.f / (XS * wsh);
+      float dl[NH];
+#pragma unroll
+      for (int j = 0; j < NH; ++j) dl[j] = 0.f;
+      if (HEAD == HB_HEAD_DISCRETE) {
+        float lg[NH], lp[NH], pj[NH];
+#pragma unroll
+        for (int j = 0; j < NH; ++j) lg[j] = hv[j] * hdesc;
+        unsigned avm = 0xffffu;
+        if (a.avail != nullptr && ok) {
+          avm = 0u;
+          for (int j = 0; j < na; ++j) avm |= a.avail[src * na + j] != 0.f ? (1u << j) : 0u;
+        }
+        const float ent = rows::categorical<NH>(lg, sbh, na, avm, lp, pj);
+        const int act = ok ? (int)a.actions[src] : 0;
+        const float lpa = rows::select<NH>(lp, act);
+        if (MODE == M_EVAL) {
+          if (ok) {
+            if (a.logp_out) a.logp_out[row] = lpa;
+            if (a.factor_inout) a.factor_inout[src] = a.factor_inout[src] * expf(lpa - a.logp_ref[src]);
+          }
+        } else {
+          // happo.py:66-91 (the 1 / sum(active) normaliser is applied when the slots are reduced)
+          float w = 1.f, fac = 1.f, adv = 0.f, old = 0.f;
+          if (ok) {
+            if (a.use_active) w = a.active[src];
+            if (a.factor) fac = a.factor[src];
+            adv = a.adv[src];
+            old = a.old_logp[src];
+          }
+          const float ratio = expf(lpa - old);
+          float m;
+          const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
+          const float okf = ok ? 1.f : 0.f;
+          const float c_lp = -fac * w * dm * ratio * okf;
+          const float c_h = a.entropy_coef * w * okf;
+          if (ok) { s_loss += -fac * m * w; s_ent += ent * w; s_ratio += ratio; s_rows += 1.f; }
+#pragma unroll
+          for (int j = 0; j < NH; ++j) {
+            const bool live = j < na && ((avm >> j) & 1u);
+            dl[j] = live ? c_lp * ((j == act ? 1.f : 0.f) - pj[j]) + c_h * pj[j] * (lp[j] + ent) : 0.f;
+            gb[j] += dl[j];
+          }
+        }
+      } else if (HEAD == HB_HEAD_BOX) {
+        // DiagGaussian (distributions.py:24-34,58-89)
+        float lpj[NH], dlt[NH];
+        float ent_row = 0.f;
+#pragma unroll
+        for (int j = 0; j < NH; ++j) {
+          lpj[j] = 0.f; dlt[j] = 0.f;
+          if (j < na) {
+            const float mean_j = fmaf(hv[j], hdesc, sbh[j]);
+            dlt[j] = (ok ? a.actions[src * na + j] : 0.f) - mean_j;
+            lpj[j] = -(dlt[j] * dlt[j]) * 0.5f * sstd[3 * NH + j] - sstd[NH + j] - 0.5f * HB_LOG_2PI_F;
+            ent_row += 0.5f + 0.5f * HB_LOG_2PI_F + sstd[NH + j];
+          }
+        }
+        if (MODE == M_EVAL) {
+          if (ok) {
+            float agg = a.agg_prod ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              if (j < na) {
+                if (a.logp_out) a.logp_out[row * na + j] = lpj[j];
+                if (a.factor_inout) {
+                  const float e = expf(lpj[j] - a.logp_ref[src * na + j]);
+                  agg = a.agg_prod ? agg * e : agg + e;
+                }
+              }
+            }
+            if (a.factor_inout) a.factor_inout[src] = a.factor_inout[src] * (a.agg_prod ? agg : agg / (float)na);
+          }
+        } else {
+          float w = 1.f, fac = 1.f, adv = 0.f;
+          if (ok) {
+            if (a.use_active) w = a.active[src];
+            if (a.factor) fac = a.factor[src];
+            adv = a.adv[src];
+          }
+          float e[NH];
+          float ratio = a.agg_prod ? 1.f : 0.f;
+#pragma unroll
+          for (int j = 0; j < NH; ++j) {
+            e[j] = 0.f;
+            if (j < na) {
+              e[j] = expf(lpj[j] - (ok ? a.old_logp[src * na + j] : 0.f));
+              ratio = a.agg_prod ? ratio * e[j] : ratio + e[j];
+            }
+          }
+          if (!a.agg_prod) ratio /= (float)na;
+          float m;
+          const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
+          const float okf = ok ? 1.f : 0.f;
+          const float c_r = -fac * w * dm * okf;
+          if (ok) { s_loss += -fac * m * w; s_ent += ent_row * w; s_ratio += ratio; s_rows += 1.f; }
+#pragma unroll
+          for (int j = 0; j < NH; ++j) {
+            if (j < na) {
+              const float sd = sstd[j], ivar = sstd[3 * NH + j];
+              const float c_lp = c_r * (a.agg_prod ? ratio : e[j] / (float)na);
+              const float dmean = c_lp * dlt[j] * ivar;
+              const float dstd = c_lp * (dlt[j] * dlt[j] * ivar / sd - 1.f / sd) - a.entropy_coef * w * okf / sd;
+              gs[HEAD == HB_HEAD_BOX ? j : 0] += dstd * sstd[2 * NH + j];
+              gb[j] += dmean;
+              dl[j] = dmean;
+            }
+          }
+        }
+      } else {
+        // value head + cal_value_loss (v_critic.py:75-114); the 1 / rows normaliser is applied at the slot reduction
+        const float v = fmaf(hv[0], hdesc, sbh[0]);
+        if (MODE == M_EVAL) {
+          if (ok && a.logp_out) a.logp_out[row] = v;
+        } else {
+          const float vp = ok ? a.value_preds[src] : 0.f;
+          float ret = ok ? a.returns[src] : 0.f;
+          if (a.vn_state != nullptr) ret = (ret - vmean) / vstd;
+          const float dv = v - vp;
+          const float dc = fminf(fmaxf(dv, -a.clip), a.clip);
+          const float vclip = vp + dc;
+          const bool pass = dv >= -a.clip && dv <= a.clip;
+          float de_c, de_o;
+          const float l_c = huber_v(ret - vclip, a.huber_delta, a.use_huber, &de_c);
+          const float l_o = huber_v(ret - v, a.huber_delta, a.use_huber, &de_o);
+          const float g_o = -de_o, g_c = pass ? -de_c : 0.f;
+          float loss = l_o, g = g_o;
+          if (a.use_clipped) {
+            if (l_c > l_o) { loss = l_c; g = g_c; }
+            else if (l_c == l_o) { loss = l_o; g = 0.5f * (g_o + g_c); }
+          }
+          g = ok ? g * a.vcoef : 0.f;
+          if (ok) { s_loss += loss; s_rows += 1.f; }
+          gb[0] += g;
+          dl[0] = g;
+        }
+      }
+      if (!GRAD) continue;   // evaluate: nothing of this tile is read by a later MMA group
+      {
+        float x[8];
+        uint4 hi, lo;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = dl[ch * 8 + j] * DZS;
+          um::split8(x, hi, lo);
+          const uint32_t off = img_off(r, ch, wchd);
+          *reinterpret_cast<uint4*>(DL + off) = hi;
+          *reinterpret_cast<uint4*>(DL + dl_bytes + off) = lo;
+        }
+      }
+      signal();
+      // ---- layer 1 backward (dL/dxhat_1 in C_F), dZ_1 over xhat_1 in X2
+      wait_m();
+      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * wsh), X2, x_bytes, wchx, r, mu1, rstd1, mask1, ok);
+      signal();
+      // ---- layer 0 backward (dL/dxhat_0 in C_F), dZ_0 over xhat_0 in X1
+      wait_m();
+      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * ws1), X1, x_bytes, wchx, r, mu0, rstd0, mask0, ok);
+      signal();
+      pending = true;
+    }
+    if (GRAD) {
+      if (pending) wait_m();
+      // ---- flush: this CTA's weight-gradient sums -> its slot of the split buffer (lane = output feature n)
+      float* slot = a.part + (long long)blockIdx.x * a.part_stride;
+      const int n = r;
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        float v[32];
+        um::tmem_ld32(tl + C_W1 + c0, v);
+        if (n < H) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(slot + a.pw1 + n * H + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      for (int c0 = 0; c0 < K0p; c0 += 16) {
+        float v[16];
+        um::tmem_ld16(tl + C_W0 + c0, v);
+        if (n < H) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < a.in_dim) slot[a.pw0 + n * a.in_dim + c0 + j] = v[j];
+        }
+      }
+      {
+        float v[16];
+        um::tmem_ld16(tl + C_B1, v);
+        if (n < H) slot[a.pb1 + n] = v[0];
+        um::tmem_ld16(tl + C_B0, v);
+        if (n < H) slot[a.pb0 + n] = v[0];
+        um::tmem_ld16(tl + C_WH, v);
+        if (n < H) {
+#pragma unroll
+          for (int j = 0; j < NH; ++j)
+            if (j < na) slot[a.phw + j * H + n] = v[j];
+        }
+      }
+      // head bias / log_std gradients and the loss scalars: sums over this CTA's rows
+#pragma unroll
+      for (int j = 0; j < NH; ++j) {
+        const float s = warp_sum(gb[j]);
+        if (lane == 0 && j < na) atomicAdd(&sacc[j], s);
+      }
+      if (HEAD == HB_HEAD_BOX) {
+#pragma unroll
+        for (int j = 0; j < (HEAD == HB_HEAD_BOX ? NH : 1); ++j) {
+          const float s = warp_sum(gs[j]);
+          if (lane == 0 && j < na) atomicAdd(&sacc[NH + j], s);
+        }
+      }
+      const double d0 = warp_sum_d((double)s_loss), d1 = warp_sum_d((double)s_ent), d2 = warp_sum_d((double)s_ratio), d3 = warp_sum_d((double)s_rows);
+      if (lane == 0) { sred[q * 4 + 0] = d0; sred[q * 4 + 1] = d1; sred[q * 4 + 2] = d2; sred[q * 4 + 3] = d3; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (r < na) {
+        slot[a.phb + r] = sacc[r];
+        if (HEAD == HB_HEAD_BOX) slot[a.plogstd + r] = sacc[NH + r];
+      }
+      if (r < 4) {
+        const double s = sred[r] + sred[4 + r] + sred[8 + r] + sred[12 + r];
+        if (HEAD == HB_HEAD_VALUE) { if (r == 0) atomicAdd(a.scalars, s); if (r == 3) atomicAdd(a.scalars + 1, s); }
+        else atomicAdd(a.scalars + r, s);
+      }
+    }
+  }
+  um::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ weight images
+// One launch per weight matrix: W'[n][k] = W[n][k] * gamma[k], scaled by a power of two so that max |W'| lands in
+// [128, 256), split into fp16 hi / lo, written as KC-wide k-chunks of K-major core matrices; folded bias b' = b + W beta.
+__global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, const float* __restrict__ b, int N, int K,
+                                                         int Nimg, int Kp, int KC, __half* __restrict__ img,
+                                                         float* __restrict__ bias_out, float* __restrict__ scale_out) {
+  __shared__ float smax[8];
+  __shared__ float sscale;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < N * K; i += 256) mx = fmaxf(mx, fabsf(W[i] * (gamma ? gamma[i % K] : 1.f)));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, smax[i]);
+    int ex = 0;
+    if (m > 0.f) frexpf(m, &ex);                     // m = f * 2^ex, f in [0.5, 1)
+    ex = ex < -20 ? -20 : (ex > 20 ? 20 : ex);
+    sscale = m > 0.f ? exp2f((float)(8 - ex)) : 1.f;
+    if (blockIdx.x == 0) *scale_out = sscale;
+  }
+  __syncthreads();
+  const float sc = sscale;
+  const int total = Nimg * Kp;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int n = i / Kp, k = i % Kp;
+    const float v = (n < N && k < K) ? W[n * K + k] * (gamma ? gamma[k] : 1.f) * sc : 0.f;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const int c = k / KC, kl = k % KC;                                          // KC-wide k-chunks (the last may be narrower)
+    const int kc = Kp - KC * c < KC ? Kp - KC * c : KC;
+    const size_t chunk0 = (size_t)c * (2u * Nimg * KC);                        // halves before this chunk
+    const size_t e = (size_t)((n >> 3) * (kc >> 3) + (kl >> 3)) * 64 + (n & 7) * 8 + (kl & 7);
+    img[chunk0 + e] = hi;
+    img[chunk0 + (size_t)Nimg * kc + e] = lo;
+  }
+  if (blockIdx.x == 0) {
+    for (int n = threadIdx.x; n < Nimg; n += 256) {
+      float v = 0.f;
+      if (n < N) {
+        v = b[n];
+        if (beta)
+          for (int k = 0; k < K; ++k) v += W[n * K + k] * beta[k];
+      }
+      bias_out[n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ slot reduction
+struct Regions { int n; int off[8]; int len[8]; float scale[8]; };
+__global__ void fused_slot_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int slots, long long stride,
+                                         int total, Regions R, const double* __restrict__ norm3, double host_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float sc = 0.f;
+  bool in = false;
+  for (int q = 0; q < R.n; ++q)
+    if (i >= R.off[q] && i < R.off[q] + R.len[q]) { sc = R.scale[q]; in = true; }
+  if (!in) { grad[i] = 0.f; return; }
+  float acc = 0.f;
+#pragma unroll 4
+  for (int s = 0; s < slots; ++s) acc += part[(long long)s * stride + i];
+  const double nrm = host_scale * (norm3 ? 1.0 / norm3[2] : 1.0);
+  grad[i] = (float)((double)acc * (double)sc * nrm);
+}
+
+static std::atomic<int> g_enabled{-1};
+
+}  // namespace fz
+
+bool fused_enabled() {
+  int v = fz::g_enabled.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HB_FUSED");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    fz::g_enabled.store(v);
+  }
+  return v != 0 && gemm_impl() != 0;   // HB_GEMM_IMPL=fp32 keeps every GEMM on the FP32 SIMT parity anchor
+}
+void set_fused_enabled(int v) { fz::g_enabled.store(v ? 1 : 0); }
+
+bool fused_shape_ok(const hb_net_desc* d) {
+  if (d->rnn_layers != 0 || d->n_layers != 2 || d->hidden[0] != d->hidden[1]) return false;
+  const int H = d->hidden[0];
+  if (H != 32 && H != 64 && H != 128) return false;
+  if (!d->feature_norm || d->in_dim < 1 || d->in_dim > 64) return false;
+  if (d->activation == HB_ACT_HARDSWISH) return false;
+  if (d->out_dim < 1 || d->out_dim > fz::NH) return false;
+  return true;
+}
+
+int launch_fused_pack(const hb_net_desc* d, const ParamLayout& P, const PrepLayout& Q, const float* params, float* prepared,
+                      cudaStream_t st) {
+  const int H = d->hidden[0];
+  float* sc = prepared + Q.fz_scale;
+  fz::fused_pack_kernel<<<8, 256, 0, st>>>(params + P.w[0], params + P.fn_w, params + P.fn_b, params + P.b[0], H, d->in_dim, H,
+                                           Q.fz_k0p, 32, reinterpret_cast<__half*>(prepared + Q.fz_w[0]), prepared + Q.fz_bias[0], sc + 0);
+  HB_LAUNCH_DONE(st, "fused_pack");
+  fz::fused_pack_kernel<<<16, 256, 0, st>>>(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32,
+                                            reinterpret_cast<__half*>(prepared + Q.fz_w[1]), prepared + Q.fz_bias[1], sc + 1);
+  HB_LAUNCH_DONE(st, "fused_pack");
+  fz::fused_pack_kernel<<<4, 256, 0, st>>>(params + P.hw, params + P.lnw[1], params + P.lnb[1], params + P.hbias, d->out_dim, H,
+                                           fz::NH, H, H, reinterpret_cast<__half*>(prepared + Q.fz_hw), prepared + Q.fz_hbias, sc + 2);
+  HB_LAUNCH_DONE(st, "fused_pack");
+  return HB_OK;
+}
+
+size_t fused_smem_bytes(int H, int K0p) {
+  size_t b = 2 * (size_t)fz::TILE * K0p * 2 + 2 * 2 * (size_t)fz::TILE * 128 * 2 + 3 * (size_t)fz::TILE * fz::NH * 2 +
+             2 * (size_t)fz::NH * H * 2 + (size_t)fz::STAGES * fz::STAGE_BYTES;
+  b += 2 * 128 * 4 + fz::NH * 4 + 4 * fz::NH * 4 + 2 * fz::NH * 4 + 16 * 8 + 8 * 8 + 16;
+  return b + 1024;
+}
+
+template <int HEAD, int MODE>
+static int launch_fused_act(const fz::Args& a, int grid, size_t smem, cudaStream_t st) {
+#define HB_FZ(ACTV)                                                                                   \
+  {                                                                                                   \
+    auto kern = fz::fused_update_kernel<HEAD, MODE, ACTV>;                                            \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    kern<<<grid, fz::THREADS, smem, st>>>(a);                                                         \
+  }
+  if (a.act == HB_ACT_RELU) HB_FZ(HB_ACT_RELU)
+  else if (a.act == HB_ACT_TANH) HB_FZ(HB_ACT_TANH)
+  else HB_FZ(-1)
+#undef HB_FZ
+  return HB_OK;
+}
+
+// mode 0 = gradient, 1 = evaluate.  Caller guarantees fused_shape_ok(d) and a packed `prepared` buffer.
+int launch_fused_update(const hb_net_desc* d, const PrepLayout& Q, const ParamLayout& P, const float* prepared, fz::Args a, int mode,
+                        int* grid_out, cudaStream_t st) {
+  const int H = d->hidden[0];
+  a.H = H; a.K0p = Q.fz_k0p; a.in_dim = d->in_dim; a.out = d->out_dim; a.act = d->activation; a.nch0 = Q.fz_chunks[0];
+  a.img0 = reinterpret_cast<const __half*>(prepared + Q.fz_w[0]);
+  a.img1 = reinterpret_cast<const __half*>(prepared + Q.fz_w[1]);
+  a.imgh = reinterpret_cast<const __half*>(prepared + Q.fz_hw);
+  a.bias0 = prepared + Q.fz_bias[0]; a.bias1 = prepared + Q.fz_bias[1]; a.biash = prepared + Q.fz_hbias;
+  a.scales = prepared + Q.fz_scale;
+  a.log_std = prepared + Q.log_std; a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;
+  a.pw0 = P.w[0]; a.pb0 = P.b[0]; a.pw1 = P.w[1]; a.pb1 = P.b[1]; a.phw = P.hw; a.phb = P.hbias; a.plogstd = P.log_std;
+  const long long ntiles = (a.rows + fz::TILE - 1) / fz::TILE;
+  const int grid = (int)(ntiles < 148 ? ntiles : 148);
+  if (grid_out) *grid_out = grid;
+  const size_t smem = fused_smem_bytes(H, Q.fz_k0p);
+  int rc;
+  if (d->head == HB_HEAD_DISCRETE) rc = mode == 0 ? launch_fused_act<HB_HEAD_DISCRETE, fz::M_GRAD>(a, grid, smem, st) : launch_fused_act<HB_HEAD_DISCRETE, fz::M_EVAL>(a, grid, smem, st);
+  else if (d->head == HB_HEAD_BOX) rc = mode == 0 ? launch_fused_act<HB_HEAD_BOX, fz::M_GRAD>(a, grid, smem, st) : launch_fused_act<HB_HEAD_BOX, fz::M_EVAL>(a, grid, smem, st);
+  else rc = mode == 0 ? launch_fused_act<HB_HEAD_VALUE, fz::M_GRAD>(a, grid, smem, st) : launch_fused_act<HB_HEAD_VALUE, fz::M_EVAL>(a, grid, smem, st);
+  if (rc) return rc;
+  HB_LAUNCH_DONE(st, shape_label(mode == 0 ? (d->head == HB_HEAD_VALUE ? "fused_critic_update" : "fused_actor_update") : "fused_evaluate",
+                                 a.rows, H, d->in_dim));
+  return HB_OK;
+}
+
+// slot sums -> grad (scaled), then the LayerNorm-affine unfolding per consumer (layer 0 / layer 1 / head)
+int launch_fused_finish(const hb_net_desc* d, const ParamLayout& P, const float* params, float* grad, const float* part, int slots,
+                        long long stride, const double* norm3, double host_scale, cudaStream_t st) {
+  const int H = d->hidden[0];
+  fz::Regions R;
+  memset(&R, 0, sizeof(R));
+  const float sw = 1.f / (fz::DZS * fz::XS), sb = 1.f / fz::DZS;
+  int n = 0;
+  auto add = [&](int off, int len, float s) { R.off[n] = off; R.len[n] = len; R.scale[n] = s; ++n; };
+  add(P.w[0], H * d->in_dim, sw); add(P.b[0], H, sb);
+  add(P.w[1], H * H, sw);         add(P.b[1], H, sb);
+  add(P.hw, d->out_dim * H, sw);  add(P.hbias, d->out_dim, 1.f);
+  if (d->head == HB_HEAD_BOX) add(P.log_std, d->out_dim, 1.f);
+  R.n = n;
+  fz::fused_slot_reduce_kernel<<<(P.total + 127) / 128, 128, 0, st>>>(grad, part, slots, stride, P.total, R, norm3, host_scale);
+  HB_LAUNCH_DONE(st, "fused_slot_reduce");
+  int rc = launch_featnorm_fold_at(params, grad, P.hw, P.hbias, P.lnw[1], P.lnb[1], d->out_dim, H, st);
+  if (rc) return rc;
+  if ((rc = launch_featnorm_fold_at(params, grad, P.w[1], P.b[1], P.lnw[0], P.lnb[0], H, H, st))) return rc;
+  return launch_featnorm_fold_at(params, grad, P.w[0], P.b[0], P.fn_w, P.fn_b, H, d->in_dim, st);
+}
+
+}  // namespace hb

@@ -44,6 +44,10 @@ int tc_nt_of(int n);
 int launch_pack_umma_tiles(const float* W, int ldn, int ldk, const float* scale, int N, int K, int NT, int nchunks,
                            float* dst, cudaStream_t st);
 
+bool fused_shape_ok(const hb_net_desc* d);   // fused_update.cu
+int launch_fused_pack(const hb_net_desc* d, const ParamLayout& P, const PrepLayout& Q, const float* params, float* prepared,
+                      cudaStream_t st);
+
 static std::atomic<int> g_gemm_impl{1};  // default: tcgen05 with the fp32-accurate 3xTF32 split
 int gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 
@@ -137,6 +141,21 @@ int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_l
     Q.tkt[l] = c;
     c += Q.tkt_chunks[l] * 2 * Q.tkt_nt[l] * 32;
   }
+  Q.fz_ok = fused_shape_ok(d) ? 1 : 0;
+  if (Q.fz_ok) {
+    const int H = d->hidden[0];
+    c = round_up(c, 4);                          // TMA bulk copies read the images: 16-byte aligned starts
+    Q.fz_k0p = round_up(d->in_dim, 16);
+    const int kp[2] = {Q.fz_k0p, H};
+    for (int l = 0; l < 2; ++l) {
+      Q.fz_chunks[l] = (kp[l] + 31) / 32;
+      Q.fz_w[l] = c;    c += H * kp[l];          // 2 images x H x kp halves = H * kp floats
+      Q.fz_bias[l] = c; c += H;
+    }
+    Q.fz_hw = c;    c += 16 * H;                 // 2 images x 16 x H halves
+    Q.fz_hbias = c; c += 16;
+    Q.fz_scale = c; c += 4;
+  }
   Q.total = c;
   if (pl) *pl = P;
   if (pp) *pp = Q;
@@ -217,6 +236,7 @@ int prepare_launch(const hb_net_desc* d, const float* params, float* prepared, c
       }
     }
   }
+  if (Q.fz_ok) return launch_fused_pack(d, P, Q, params, prepared, st);
   return HB_OK;
 }
 

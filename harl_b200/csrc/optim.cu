@@ -39,6 +39,13 @@ int launch_featnorm_fold(const hb_net_desc* d, const float* params, float* grad,
   return HB_OK;
 }
 
+// the same fold for any consumer of a LayerNorm affine (fused_update.cu: W' = W diag(gamma), b' = b + W beta per layer / head)
+int launch_featnorm_fold_at(const float* params, float* grad, int w0, int b0, int gw, int gb, int N, int K, cudaStream_t st) {
+  featnorm_grad_fold_kernel<<<(K + 127) / 128, 128, 0, st>>>(params, grad, w0, b0, gw, gb, N, K);
+  HB_LAUNCH_DONE(st, "ln_affine_grad_fold");
+  return HB_OK;
+}
+
 // One CTA: total L2 norm, clip coefficient, Adam (torch single-tensor form).
 __global__ void __launch_bounds__(1024) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v, int n,

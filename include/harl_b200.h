@@ -105,6 +105,13 @@ int hb_profile_end(char* out, int out_size);
 int hb_set_gemm_impl(int impl);
 int hb_get_gemm_impl(void);
 
+/* Fused update kernel (one persistent tcgen05 launch per update: feature norm -> MLP -> head -> loss -> backward, activations
+ * never leave the SM; fp16 hi/lo split operands with fp32 accumulation): 1 = use it for the shapes it covers (MLP nets with
+ * two equal hidden layers of 32 / 64 / 128 units, feature normalisation, in_dim <= 64, out_dim <= 16; default), 0 = always the
+ * layer-wise kernels.  Env HB_FUSED=0 selects 0.  hb_set_gemm_impl(0) (FP32 SIMT) also disables it. */
+int hb_set_fused_update(int on);
+int hb_get_fused_update(void);
+
 /* ---- network parameter plumbing ------------------------------------------------------ */
 int hb_net_layout_of(const hb_net_desc* d, hb_net_layout* out);
 /* Derived weights the kernels read (transposed Linear weights, feature-norm affine folded
