@@ -116,6 +116,8 @@ SIGNATURES = {
     "hb_get_gemm_impl": (C.c_int, []),
     "hb_set_fused_update": (C.c_int, [C.c_int]),
     "hb_get_fused_update": (C.c_int, []),
+    "hb_fused_timing_enable": (C.c_int, [C.c_int]),
+    "hb_fused_timing_read": (C.c_int, [P]),
     "hb_net_layout_of": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetLayout)]),
     "hb_net_prepare": (C.c_int, [C.POINTER(NetDesc), P, P, P]),
     "hb_workspace_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64, C.c_int]),

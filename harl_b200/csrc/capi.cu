@@ -788,6 +788,11 @@ int hb_set_fused_update(int on) {
   return HB_OK;
 }
 int hb_get_fused_update(void) { return hb::fused_enabled() ? 1 : 0; }
+int hb_fused_timing_enable(int on) { return hb::fused_timing_enable(on); }
+int hb_fused_timing_read(unsigned long long* out) {
+  HB_CHECK_ARG(out != nullptr, "NULL");
+  return hb::fused_timing_read(out);
+}
 
 int hb_set_rnn_impl(int impl) {
   HB_CHECK_ARG(impl == 0 || impl == 1, "impl must be 0 (launch per step) or 1 (experimental persistent recurrence)");

@@ -60,6 +60,7 @@ struct PrepLayout {
   // matrices; the head likewise as one [16][h] image pair.  fz_ok = 0: shape outside the fused kernel (layer-wise path).
   int fz_ok, fz_k0p;
   int fz_w[2], fz_chunks[2], fz_bias[2];
+  int fz_w1b;                        // layer 1 again, chunked by 32 OUTPUT rows ([32][h] images): the dX GEMM's B operand
   int fz_hw, fz_hbias, fz_scale;
   int total;
 };

@@ -10,12 +10,13 @@ namespace fz {
 struct Args {
   // network
   int H, K0p, in_dim, out, act, nch0;
-  const __half* img0; const __half* img1; const __half* imgh;
+  const __half* img0; const __half* img1; const __half* img1b; const __half* imgh;
   const float* bias0; const float* bias1; const float* biash;
   const float* scales;                      // [3] power-of-two operand scales of W'_0, W'_1, W'_head
   const float* log_std; float std_x, std_y;
   // batch (buffer-row indexed through `index`)
   const float* obs; const int32_t* index; long long rows;
+  int stage_obs;                            // full tiles' observation blocks arrive by TMA bulk copy (identity index, 16-byte aligned)
   const float* actions; const float* avail; const float* old_logp; const float* adv; const float* factor; const float* active;
   const float* value_preds; const float* returns; const float* vn_state;
   // hyper-parameters
@@ -40,5 +41,8 @@ int launch_fused_update(const hb_net_desc* d, const PrepLayout& Q, const ParamLa
 // slot sums -> grad with the loss normaliser, then the LayerNorm-affine unfolding
 int launch_fused_finish(const hb_net_desc* d, const ParamLayout& P, const float* params, float* grad, const float* part, int slots,
                         long long stride, const double* norm3, double host_scale, cudaStream_t st);
+
+int fused_timing_enable(int on);
+int fused_timing_read(unsigned long long* out);
 
 }  // namespace hb

@@ -45,9 +45,9 @@ constexpr float XS = 16.f;          // activation images hold XS * xhat      (|x
 constexpr float DZS = 16.f;         // gradient images hold DZS * dZ (dZ is un-normalised: O(advantage))
 constexpr int TILE = 128;
 constexpr int NH = 16;              // padded head width (MMA N)
-constexpr int STAGES = 2;
+constexpr int MAX_STAGES = 3;          // weight-chunk ring: 3 stages when the images leave room (in_dim <= 32), else 2
 constexpr int STAGE_BYTES = 16384;  // one weight chunk: hi + lo images of [128][32] fp16
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;           // producer warp, MMA warp, 8 epilogue warps (two threads per row)
 enum { M_GRAD = 0, M_EVAL = 1 };
 
 // TMEM columns (fp32 accumulators, 128 lanes each)
@@ -58,6 +58,7 @@ constexpr uint32_t C_H = 320;       // head outputs                             
 constexpr uint32_t C_WH = 336;      // dW'_head transposed                         [feature][16]
 constexpr uint32_t C_B1 = 352;      // db'_1 in column 0                           [n][16]
 constexpr uint32_t C_B0 = 368;      // db'_0 in column 0
+constexpr uint32_t C_BH = 384;      // column sums of the d-logits image: lane j = db'_head[j]; Box: lane 8 + j = d log_std[j]
 constexpr uint32_t TMEM_COLS = 512;
 
 
@@ -112,108 +113,152 @@ __device__ __forceinline__ float act_f(int act_rt, float z) {
   return act_fwd_rt(act_rt, z);
 }
 
-// Linear -> act -> LayerNorm epilogue of one row: TMEM accumulator row -> xhat image row (hi, lo), statistics, sign mask.
+// Two threads share a row (column halves): partial row sums meet through shared memory and a 64-thread named barrier of
+// the two warps that own the same TMEM lane quarter.  Both threads form a + b in the same order (bit-identical results).
+struct RowPair {
+  float* xch;     // [2 halves][128 rows][2 slots]
+  int half, r, bar_id;
+  __device__ __forceinline__ void put(int slot, float v) const { xch[(half * TILE + r) * 2 + slot] = v; }
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
+  __device__ __forceinline__ float total(int slot, float mine) const {
+    const float other = xch[((half ^ 1) * TILE + r) * 2 + slot];
+    return half == 0 ? mine + other : other + mine;
+  }
+};
+
+// ---- single-pass epilogues.  TMEM reads are the scarce resource here (measured: ~64 B / cycle / SM, so every extra pass over
+// a 128 x 128 accumulator costs ~1000 cycles per tile): each accumulator element is read ONCE, the thread's <= 64 columns stay
+// in registers for the statistics and the write-back.  The next 16-column chunk's tcgen05.ld is in flight while the current
+// one is consumed (two alternating register buffers; the loops are fully unrolled so that every index is static).
+
+// Linear -> act -> LayerNorm epilogue of the columns [cb, cb + H/2) of one row.  ONE pass over TMEM: a = act(z) goes to
+// the image as fp16 hi / lo (22 bits); the two statistics passes and the normalisation then run over the thread's own image
+// row in shared memory (cheap) instead of over TMEM, and xhat * XS overwrites a in place.
 template <int ACT>
 __device__ __forceinline__ void fwd_epilogue(int act_rt, uint32_t tacc, int H, const float* __restrict__ sbias, float descale,
-                                             unsigned char* img, uint32_t img_bytes, int wch, int r, float& mu, float& rstd,
-                                             uint32_t (&mask)[4]) {
+                                             unsigned char* img, uint32_t img_bytes, int wch, const RowPair& P, float& mu, float& rstd,
+                                             uint32_t (&mask)[2]) {
+  const int r = P.r, nc = H >> 1, cb = P.half * nc;
   const float inv_n = 1.f / (float)H;
+  uint32_t va[16], vb[16];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  for (int c0 = 0; c0 < H; c0 += 32) {
-    float v[32];
-    um::tmem_ld32(tacc + c0, v);
+  uint32_t mk0 = 0u, mk1 = 0u;
+  um::tmem_ld16_issue(tacc + cb, va);
+#define HB_STEP(CC, CUR, NXT)                                                                              \
+  if ((CC) * 16 < nc) {                                                                                    \
+    um::tmem_ld_wait16(CUR);                                                                               \
+    if (((CC) + 1) * 16 < nc) um::tmem_ld16_issue(tacc + cb + ((CC) + 1) * 16, NXT);                      \
+    uint32_t m_ = 0u;                                                                                      \
+    _Pragma("unroll") for (int q = 0; q < 2; ++q) {                                                        \
+      const float4 ba = *reinterpret_cast<const float4*>(sbias + cb + (CC) * 16 + q * 8);                  \
+      const float4 bb = *reinterpret_cast<const float4*>(sbias + cb + (CC) * 16 + q * 8 + 4);              \
+      const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};                                \
+      float x[8];                                                                                          \
+      _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                                      \
+        const float z = fmaf(__uint_as_float(CUR[q * 8 + j]), descale, bq[j]);                             \
+        m_ |= z > 0.f ? (1u << (q * 8 + j)) : 0u;                                                          \
+        x[j] = act_f<ACT>(act_rt, z);                                                                      \
+      }                                                                                                    \
+      s0 += (x[0] + x[1]); s1 += (x[2] + x[3]); s2 += (x[4] + x[5]); s3 += (x[6] + x[7]);                  \
+      uint4 hi, lo;                                                                                        \
+      um::split8(x, hi, lo);                                                                               \
+      const uint32_t off = img_off(r, (cb >> 3) + (CC) * 2 + q, wch);                                      \
+      *reinterpret_cast<uint4*>(img + off) = hi;                                                           \
+      *reinterpret_cast<uint4*>(img + img_bytes + off) = lo;                                               \
+    }                                                                                                      \
+    if ((CC) < 2) mk0 |= m_ << (16 * ((CC) & 1)); else mk1 |= m_ << (16 * ((CC) & 1));                     \
+  }
+  HB_STEP(0, va, vb) HB_STEP(1, vb, va) HB_STEP(2, va, vb) HB_STEP(3, vb, va)
+#undef HB_STEP
+  mask[0] = mk0; mask[1] = mk1;
+  float part = (s0 + s1) + (s2 + s3);
+  P.put(0, part);
+  P.sync();
+  mu = P.total(0, part) * inv_n;
+  s0 = s1 = 0.f;
+  for (int c8 = 0; c8 < (nc >> 3); ++c8) {
+    const uint32_t off = img_off(r, (cb >> 3) + c8, wch);
+    float x[8];
+    um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);
-      s0 += act_f<ACT>(act_rt, fmaf(v[j], descale, b4.x));
-      s1 += act_f<ACT>(act_rt, fmaf(v[j + 1], descale, b4.y));
-      s2 += act_f<ACT>(act_rt, fmaf(v[j + 2], descale, b4.z));
-      s3 += act_f<ACT>(act_rt, fmaf(v[j + 3], descale, b4.w));
+    for (int j = 0; j < 8; j += 2) {
+      const float d0 = x[j] - mu, d1 = x[j + 1] - mu;
+      s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1);
     }
   }
-  mu = ((s0 + s1) + (s2 + s3)) * inv_n;
-  s0 = s1 = s2 = s3 = 0.f;
-  for (int c0 = 0; c0 < H; c0 += 32) {
-    float v[32];
-    um::tmem_ld32(tacc + c0, v);
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + j);
-      float d;
-      d = act_f<ACT>(act_rt, fmaf(v[j], descale, b4.x)) - mu; s0 = fmaf(d, d, s0);
-      d = act_f<ACT>(act_rt, fmaf(v[j + 1], descale, b4.y)) - mu; s1 = fmaf(d, d, s1);
-      d = act_f<ACT>(act_rt, fmaf(v[j + 2], descale, b4.z)) - mu; s2 = fmaf(d, d, s2);
-      d = act_f<ACT>(act_rt, fmaf(v[j + 3], descale, b4.w)) - mu; s3 = fmaf(d, d, s3);
-    }
-  }
-  rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * inv_n + 1e-5f);
+  part = s0 + s1;
+  P.put(1, part);
+  P.sync();
+  rstd = rsqrtf(P.total(1, part) * inv_n + 1e-5f);
   const float rs = rstd * XS, sh = -mu * rstd * XS;
-  for (int c0 = 0; c0 < H; c0 += 32) {
-    float v[32];
-    um::tmem_ld32(tacc + c0, v);
-    uint32_t m = 0u;
+  for (int c8 = 0; c8 < (nc >> 3); ++c8) {
+    const uint32_t off = img_off(r, (cb >> 3) + c8, wch);
+    float x[8];
+    um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float x[8];
-      const float4 ba = *reinterpret_cast<const float4*>(sbias + c0 + q * 8), bb = *reinterpret_cast<const float4*>(sbias + c0 + q * 8 + 4);
-      const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v[q * 8 + j], descale, bq[j]);
-        m |= z > 0.f ? (1u << (q * 8 + j)) : 0u;
-        x[j] = fmaf(act_f<ACT>(act_rt, z), rs, sh);
-      }
-      uint4 hi, lo;
-      um::split8(x, hi, lo);
-      const uint32_t off = img_off(r, (c0 >> 3) + q, wch);
-      *reinterpret_cast<uint4*>(img + off) = hi;
-      *reinterpret_cast<uint4*>(img + img_bytes + off) = lo;
-    }
-    if (c0 == 0) mask[0] = m; else if (c0 == 32) mask[1] = m; else if (c0 == 64) mask[2] = m; else mask[3] = m;
+    for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], rs, sh);
+    uint4 hi, lo;
+    um::split8(x, hi, lo);
+    *reinterpret_cast<uint4*>(img + off) = hi;
+    *reinterpret_cast<uint4*>(img + img_bytes + off) = lo;
   }
 }
 
-// LayerNorm + activation backward of one row: g = dL/dxhat from TMEM, xhat from the image; writes DZS * dZ over xhat.
+// LayerNorm + activation backward of this thread's columns of one row: G = accumulator (= g / descale, g = dL/dxhat), x = XS * xhat
+// from the image; writes DZS * dZ over xhat.  With s1 = sum G, s2 = sum G x:
+//   dZ = rstd (g - mean(g) - xhat mean(g xhat)) act'   =   [rstd descale] (G - s1 / H - x s2 / (H XS^2)) act'
 template <int ACT>
 __device__ __forceinline__ void bwd_epilogue(int act_rt, uint32_t tacc, int H, float descale, unsigned char* img,
-                                             uint32_t img_bytes, int wch, int r, float mu, float rstd, const uint32_t (&mask)[4],
-                                             bool row_ok) {
-  const float inv_n = 1.f / (float)H, inv_xs = 1.f / XS;
+                                             uint32_t img_bytes, int wch, const RowPair& P, float mu, float rstd,
+                                             const uint32_t (&mask)[2], bool row_ok) {
+  const int r = P.r, nc = H >> 1, cb = P.half * nc;
+  const float inv_n = 1.f / (float)H;
+  // two passes over TMEM (sums, then the write-back): keeping the 64 accumulator values of a thread in registers across the
+  // statistics exchange does not fit the 168-register cap of the 320-thread CTA next to the rest of the epilogue state
   float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-  for (int c0 = 0; c0 < H; c0 += 32) {
-    float g[32];
-    um::tmem_ld32(tacc + c0, g);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t off = img_off(r, (c0 >> 3) + q, wch);
-      float x[8];
-      um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x);
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        const float g0 = g[q * 8 + j] * descale, g1 = g[q * 8 + j + 1] * descale;
-        s1a += g0; s1b += g1;
-        s2a = fmaf(g0, x[j] * inv_xs, s2a); s2b = fmaf(g1, x[j + 1] * inv_xs, s2b);
-      }
+  {
+    uint32_t va[16], vb[16];
+    um::tmem_ld16_issue(tacc + cb, va);
+#define HB_STEP(CC, CUR, NXT)                                                                              \
+    if ((CC) * 16 < nc) {                                                                                  \
+      um::tmem_ld_wait16(CUR);                                                                             \
+      if (((CC) + 1) * 16 < nc) um::tmem_ld16_issue(tacc + cb + ((CC) + 1) * 16, NXT);                    \
+      _Pragma("unroll") for (int q = 0; q < 2; ++q) {                                                      \
+        const uint32_t off = img_off(r, (cb >> 3) + (CC) * 2 + q, wch);                                    \
+        float x[8];                                                                                        \
+        um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x); \
+        _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                                 \
+          const float g0 = __uint_as_float(CUR[q * 8 + j]), g1 = __uint_as_float(CUR[q * 8 + j + 1]);      \
+          s1a += g0; s1b += g1;                                                                            \
+          s2a = fmaf(g0, x[j], s2a); s2b = fmaf(g1, x[j + 1], s2b);                                        \
+        }                                                                                                  \
+      }                                                                                                    \
     }
+    HB_STEP(0, va, vb) HB_STEP(1, vb, va) HB_STEP(2, va, vb) HB_STEP(3, vb, va)
+#undef HB_STEP
   }
-  const float m1 = (s1a + s1b) * inv_n, m2 = (s2a + s2b) * inv_n;
-  const float stdv = 1.f / rstd;
-  const float k = row_ok ? rstd * DZS : 0.f;
-  for (int c0 = 0; c0 < H; c0 += 32) {
-    float g[32];
-    um::tmem_ld32(tacc + c0, g);
-    const uint32_t m = c0 == 0 ? mask[0] : (c0 == 32 ? mask[1] : (c0 == 64 ? mask[2] : mask[3]));
+  const float p1 = s1a + s1b, p2 = s2a + s2b;
+  P.put(0, p1);
+  P.put(1, p2);
+  P.sync();
+  const float m1 = P.total(0, p1) * inv_n, m2 = P.total(1, p2) * inv_n * (1.f / (XS * XS));
+  const float stdx = 1.f / (rstd * XS);
+  const float k = row_ok ? rstd * descale * DZS : 0.f;
+  for (int cc = 0; cc * 16 < nc; ++cc) {
+    uint32_t v[16];
+    um::tmem_ld16_issue(tacc + cb + cc * 16, v);
+    um::tmem_ld_wait16(v);
+    const uint32_t mw = (cc < 2 ? mask[0] : mask[1]) >> (16 * (cc & 1));
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t off = img_off(r, (c0 >> 3) + q, wch);
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t off = img_off(r, (cb >> 3) + cc * 2 + q, wch);
       float x[8], dz[8];
       um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = x[j] * inv_xs;
-        const float a = fmaf(xh, stdv, mu);
-        const float t = fmaf(-xh, m2, g[q * 8 + j] * descale - m1);
-        dz[j] = k * t * act_prime<ACT>(act_rt, a, (m >> (q * 8 + j)) & 1u);
+        const float a = fmaf(x[j], stdx, mu);
+        const float t = fmaf(-x[j], m2, __uint_as_float(v[q * 8 + j]) - m1);
+        dz[j] = k * t * act_prime<ACT>(act_rt, a, (mw >> (q * 8 + j)) & 1u);
       }
       uint4 hi, lo;
       um::split8(dz, hi, lo);
@@ -231,6 +276,19 @@ __device__ __forceinline__ float huber_v(float e, float d, int use_huber, float*
   return d * (ae - d / 2.f);
 }
 
+// Phase clock (profiling aid, HB_FUSED_TIMING=1): thread 64 of every CTA adds the SM-clock cycles it spends in each
+// epilogue phase / each wait for the MMA warp to a global table, read back through hb_fused_timing_read.
+__device__ unsigned long long g_phase_cycles[148 * 16];
+__device__ int g_phase_on;
+struct PhaseClock {
+  unsigned long long t;
+  bool on;
+  __device__ __forceinline__ void start(bool enable) { on = enable; if (on) t = clock64(); }
+  __device__ __forceinline__ void lap(int slot) {
+    if (on) { const unsigned long long n = clock64(); g_phase_cycles[blockIdx.x * 16 + slot] += n - t; t = n; }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int HEAD, int MODE, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_constant__ Args a) {
@@ -246,6 +304,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   unsigned char* DL = p; p += 2 * dl_bytes;
   unsigned char* ONES = p; p += dl_bytes;
   unsigned char* WH = p; p += 2 * wh_bytes;
+  const int STAGES = K0p <= 32 ? 3 : 2;
   unsigned char* ring = p; p += STAGES * STAGE_BYTES;
   float* sb0 = reinterpret_cast<float*>(p); p += 128 * 4;
   float* sb1 = reinterpret_cast<float*>(p); p += 128 * 4;
@@ -253,24 +312,29 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   float* sstd = reinterpret_cast<float*>(p); p += 4 * NH * 4;       // Box: std, log std, d std / d log_std param, 1 / var
   float* sacc = reinterpret_cast<float*>(p); p += 2 * NH * 4;       // end-of-kernel sums: head bias grads, log_std grads
   double* sred = reinterpret_cast<double*>(p); p += 4 * 4 * 8;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p); p += 8 * 8;
+  float* xch = reinterpret_cast<float*>(p); p += 2 * TILE * 2 * 4;  // row-pair exchange of partial sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p); p += 10 * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p);
-  uint64_t* w_full = bars;            // [STAGES] weight chunk landed
-  uint64_t* w_empty = bars + STAGES;  // [STAGES] MMAs reading the chunk retired
-  uint64_t* e2m = bars + 2 * STAGES;  // epilogue warps -> MMA warp (128 arrivals)
+  uint64_t* w_full = bars;                // [STAGES] weight chunk landed
+  uint64_t* w_empty = bars + MAX_STAGES;  // [STAGES] MMAs reading the chunk retired
+  uint64_t* e2m = bars + 2 * MAX_STAGES;  // epilogue warps -> MMA warp (256 arrivals)
   uint64_t* m2e = e2m + 1;            // MMA warp -> epilogue warps (tcgen05.commit)
+  uint64_t* obs_free = e2m + 2;       // MMA warp -> producer: the staging image of the next tile's observations is dead
+  uint64_t* obs_full = e2m + 3;       // producer's bulk copy -> epilogue warps
+  unsigned char* OBS = MODE == M_GRAD ? X2 : X1;   // staging buffer = an activation image that is idle at that point
+  const uint32_t obs_bytes = (uint32_t)TILE * (uint32_t)a.in_dim * 4u;
 
   const long long ntiles = (a.rows + TILE - 1) / TILE;
   const int nch1 = H >> 5;
   constexpr bool GRAD = MODE == M_GRAD;
 
   // ---- one-time setup
-  for (int i = tid; i < (int)((2 * x_bytes) / 16); i += THREADS) {
-    reinterpret_cast<uint4*>(X1)[i] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4*>(X2)[i] = make_uint4(0, 0, 0, 0);
+  if (H < 128) {   // feature columns >= H of the activation images are read by the M = 128 weight-gradient MMAs, never written
+    for (int i = tid; i < (int)((2 * x_bytes) / 16); i += THREADS) {
+      reinterpret_cast<uint4*>(X1)[i] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(X2)[i] = make_uint4(0, 0, 0, 0);
+    }
   }
-  for (int i = tid; i < (int)((2 * x0_bytes) / 16); i += THREADS) reinterpret_cast<uint4*>(X0)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < (int)((2 * dl_bytes) / 16); i += THREADS) reinterpret_cast<uint4*>(DL)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < TILE * 2; i += THREADS)   // ONES[row][16]: column 0 = 1.0, 16-byte chunks [row/8][2][row%8]
     reinterpret_cast<uint4*>(ONES)[i] = ((i >> 3) & 1) ? make_uint4(0, 0, 0, 0) : make_uint4(0x00003C00u, 0, 0, 0);
   for (int i = tid; i < (int)((2 * wh_bytes) / 16); i += THREADS) reinterpret_cast<uint4*>(WH)[i] = reinterpret_cast<const uint4*>(a.imgh)[i];
@@ -290,8 +354,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   if (tid < 16) sred[tid] = 0.0;
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { um::mbar_init(&w_full[i], 1); um::mbar_init(&w_empty[i], 1); }
-    um::mbar_init(e2m, 128);
+    um::mbar_init(e2m, 256);
     um::mbar_init(m2e, 1);
+    um::mbar_init(obs_free, 1);
+    um::mbar_init(obs_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -308,12 +374,18 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   if (warp == 0) {
     // ================================================================ weight-chunk producer (one lane)
     if (lane == 0) {
-      uint32_t it = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      uint32_t it = 0, tl_ = 0;
+      auto staged = [&](long long t) { return a.stage_obs && t < ntiles && (t + 1) * TILE <= a.rows; };
+      auto load_obs = [&](long long t) {
+        um::mbar_expect_tx(obs_full, obs_bytes);
+        um::tma_bulk_g2s(OBS, a.obs + t * TILE * a.in_dim, obs_bytes, obs_full);
+      };
+      if (staged(blockIdx.x)) load_obs(blockIdx.x);
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl_) {
         for (int pass = 0; pass < (GRAD ? 3 : 2); ++pass) {
           const int layer = pass == 0 ? 0 : 1;
           const int nch = layer == 0 ? a.nch0 : nch1, kp = layer == 0 ? K0p : H;
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(layer == 0 ? a.img0 : a.img1);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(pass == 0 ? a.img0 : (pass == 1 ? a.img1 : a.img1b));
           for (int c = 0; c < nch; ++c, ++it) {
             const int kc = kp - 32 * c < 32 ? kp - 32 * c : 32;
             const uint32_t bytes = 2u * (uint32_t)H * (uint32_t)kc * 2u;
@@ -323,6 +395,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
             um::tma_bulk_g2s(ring + st * STAGE_BYTES, src + (size_t)c * (2u * H * 32u * 2u), bytes, &w_full[st]);
           }
         }
+        // the staging image is free once this tile's MMAs that read it have retired: fetch the next tile's observations
+        um::mbar_wait(obs_free, tl_ & 1);
+        if (staged(t + gridDim.x)) load_obs(t + gridDim.x);
       }
     }
     __syncwarp();
@@ -360,6 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
             gemm3(tmem + C_F, op_kmajor(X1a, x_bytes, wchx, 4 * c), op_kmajor(wb, wimg, 4, 0), 2, um::idesc_f16(H, 0, 0), c > 0);
           });
         um::commit(m2e);
+        if (!GRAD) um::commit(obs_free);   // evaluate: X1 (the staging image) is dead after these MMAs
         // -- head: C_H = X2 Wh'^T
         wait_e();
         gemm3(tmem + C_H, op_kmajor(X2a, x_bytes, wchx, 0), op_kmajor(WHa, wh_bytes, wchh, 0), H >> 4, um::idesc_f16(NH, 0, 0), false);
@@ -370,19 +446,31 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
           gemm3(tmem + C_F, op_kmajor(DLa, dl_bytes, wchd, 0), op_mnmajor(WHa, wh_bytes, wchh, 0), 1, um::idesc_f16(H, 0, 1), false);
           gemm3(tmem + C_WH, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(DLa, dl_bytes, wchd, 0), TILE >> 4,
                 um::idesc_f16(NH, 1, 1), !first);
+          // column sums of DL over the rows: M = 128 reads past the 16 real columns (finite garbage in lanes >= 16, unused)
+          gemm3(tmem + C_BH, op_mnmajor(DLa, dl_bytes, wchd, 0), op_mnmajor(ONa, dl_bytes, wchd, 0), TILE >> 4,
+                um::idesc_f16(NH, 1, 1), !first, false);
           um::commit(m2e);
           // -- layer 1 backward: C_W1 += dZ1^T X1;  C_B1 += dZ1^T 1;  C_F = dZ1 W1' (dL/dxhat_0), one weight chunk at a time
           wait_e();
+          // the chunks already sitting in the ring go first, so their stages are released (and refilled by the producer)
+          // while the weight-gradient MMAs, which need no streamed operand, run
+          // dX accumulates over chunks of 32 output features n: A = dZ1[:, 32c .. 32c+32) (K-major), B = W1'[32c .. 32c+32)[:]
+          // as an MN-major operand (N = h input features) -- full-width MMAs, every operand byte read once
+          auto dx_chunk = [&](int c) {
+            chunk(32, [&](uint32_t wb, uint32_t wimg) {
+              gemm3(tmem + C_F, op_kmajor(X2a, x_bytes, wchx, 4 * c), op_mnmajor(wb, wimg, H >> 3, 0), 2,
+                    um::idesc_f16(H, 0, 1), c > 0);
+            });
+          };
+          const int nres = nch1 < STAGES ? nch1 : STAGES;
+          for (int c = 0; c < nres; ++c) dx_chunk(c);
           gemm3(tmem + C_W1, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(X1a, x_bytes, wchx, 0), TILE >> 4,
                 um::idesc_f16(H, 1, 1), !first);
           gemm3(tmem + C_B1, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(ONa, dl_bytes, wchd, 0), TILE >> 4,
                 um::idesc_f16(NH, 1, 1), !first, false);
-          for (int c = 0; c < nch1; ++c)
-            chunk(32, [&](uint32_t wb, uint32_t wimg) {
-              gemm3(tmem + C_F + 32 * c, op_kmajor(X2a, x_bytes, wchx, 0), op_mnmajor(wb, wimg, 4, 0), H >> 4,
-                    um::idesc_f16(32, 0, 1), false);
-            });
+          for (int c = nres; c < nch1; ++c) dx_chunk(c);
           um::commit(m2e);
+          um::commit(obs_free);            // X2 (the staging image) is dead after these MMAs
           // -- layer 0 backward: C_W0 += dZ0^T X0;  C_B0 += dZ0^T 1
           wait_e();
           gemm3(tmem + C_W0, op_mnmajor(X1a, x_bytes, wchx, 0), op_mnmajor(X0a, x0_bytes, wch0, 0), TILE >> 4,
@@ -397,17 +485,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
     __syncwarp();
   } else {
     // ================================================================ epilogue warps: thread = row
-    const int q = warp & 3, r = q * 32 + lane;
+    // warps 2-5: column half 0, warps 6-9: column half 1 of the same rows (TMEM lane quarter = warp % 4)
+    const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t pm = 0;
+    const RowPair RP{xch, half, r, 2 + q};
+    uint32_t pm = 0, po = 0;
     auto wait_m = [&]() { um::mbar_wait(m2e, pm); pm ^= 1; um::tc_fence_after(); };
     auto signal = [&]() { um::fence_async_smem(); um::tc_fence_before(); um::mbar_arrive(e2m); };
     const int na = a.out;
-    float gb[NH], gs[HEAD == HB_HEAD_BOX ? NH : 1];
-#pragma unroll
-    for (int j = 0; j < NH; ++j) gb[j] = 0.f;
-#pragma unroll
-    for (int j = 0; j < (HEAD == HB_HEAD_BOX ? NH : 1); ++j) gs[j] = 0.f;
     float s_loss = 0.f, s_ent = 0.f, s_ratio = 0.f, s_rows = 0.f;
     float vmean = 0.f, vstd = 1.f;
     if (HEAD == HB_HEAD_VALUE && a.vn_state != nullptr) {  // valuenorm.py:38-45
@@ -417,189 +502,259 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
       vstd = sqrtf(fmaxf(msq - mu * mu, 1e-2f));
     }
     bool pending = false;   // a backward MMA group of the previous tile may still read X0 / X1
+    PhaseClock pc;
+    pc.start(g_phase_on != 0 && tid == 64);   // warp 2, lane 0: a half-0 thread
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const long long row = t * TILE + r;
       const bool ok = row < a.rows;
-      const long long src = ok ? (a.index ? (long long)a.index[row] : row) : 0;
-      // ---- feature LayerNorm of the observation row (mlp.py:57-66), exact two-pass statistics
-      const float* o = a.obs + src * a.in_dim;
-      float mean = 0.f, rs = 0.f;
+      const bool ld = ok && half == 0;   // the column-half-0 thread of a row owns its inputs, the head and the loss
+      const long long src = ld ? (a.index ? (long long)a.index[row] : row) : 0;
+      // ---- per-row scalars of the head phase: requested now, consumed ~a tile's worth of work later (latency hidden)
+      float in_act = 0.f, in_old = 0.f, in_adv = 0.f, in_fac = 1.f, in_w = 1.f, in_vp = 0.f, in_ret = 0.f;
+      unsigned in_avm = 0xffffu;
+      float in_av[NH];
+      if (HEAD == HB_HEAD_DISCRETE) {
+        if (ld) {
+          in_act = __ldg(a.actions + src);
+          if (GRAD) {
+            in_old = __ldg(a.old_logp + src); in_adv = __ldg(a.adv + src);
+            if (a.factor) in_fac = __ldg(a.factor + src);
+            if (a.use_active) in_w = __ldg(a.active + src);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NH; ++j) in_av[j] = (a.avail != nullptr && ld && j < a.out) ? __ldg(a.avail + src * a.out + j) : 1.f;
+      } else if (HEAD == HB_HEAD_BOX) {
+        if (ld && GRAD) {
+          in_adv = __ldg(a.adv + src);
+          if (a.factor) in_fac = __ldg(a.factor + src);
+          if (a.use_active) in_w = __ldg(a.active + src);
+        }
+      } else if (ld && GRAD) {
+        in_vp = __ldg(a.value_preds + src); in_ret = __ldg(a.returns + src);
+      }
+      (void)in_vp; (void)in_ret; (void)in_act; (void)in_old;
+      // next tile's rows -> L2 (identity index only): the first touch of a tile then costs an L2 hit, not a DRAM round trip
       {
+        const long long tn = t + gridDim.x;
+        const long long rown = tn * TILE + r;
+        if (a.index == nullptr && rown < a.rows && half == 0) {
+          if (!a.stage_obs) {
+            const float* on = a.obs + rown * a.in_dim;
+            um::prefetch_l2(on);
+            um::prefetch_l2(on + a.in_dim - 1);
+          }
+          if (lane == 0) {
+            if (HEAD == HB_HEAD_VALUE) { if (GRAD) { um::prefetch_l2(a.value_preds + rown); um::prefetch_l2(a.returns + rown); } }
+            else {
+              if (HEAD == HB_HEAD_DISCRETE) um::prefetch_l2(a.actions + rown);
+              if (GRAD) {
+                um::prefetch_l2(a.adv + rown);
+                if (HEAD == HB_HEAD_DISCRETE) um::prefetch_l2(a.old_logp + rown);
+                if (a.factor) um::prefetch_l2(a.factor + rown);
+                if (a.use_active) um::prefetch_l2(a.active + rown);
+              }
+            }
+          }
+          if (HEAD == HB_HEAD_DISCRETE && a.avail != nullptr) um::prefetch_l2(a.avail + rown * a.out);
+          if (HEAD == HB_HEAD_BOX) { um::prefetch_l2(a.actions + rown * a.out); if (GRAD) um::prefetch_l2(a.old_logp + rown * a.out); }
+        }
+      }
+      // ---- feature LayerNorm of the observation row (mlp.py:57-66), exact two-pass statistics; the row sits in registers
+      // full tiles: the producer's bulk copy put the 128 x in_dim block into the (idle) staging image; else direct loads
+      const bool st_obs = a.stage_obs && (t + 1) * TILE <= a.rows;
+      const float* o = st_obs ? reinterpret_cast<const float*>(OBS) + r * a.in_dim : a.obs + src * a.in_dim;
+      float mean = 0.f, rs = 0.f;
+      if (half == 0) {
+        if (st_obs) { um::mbar_wait(obs_full, po); po ^= 1; }
         float s = 0.f;
-        for (int k = 0; k < a.in_dim; ++k) s += ok ? __ldg(o + k) : 0.f;
+        for (int k0 = 0; k0 < a.in_dim; k0 += 16) {
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = (ld && k0 + j < a.in_dim) ? o[k0 + j] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s += x[j];
+        }
         mean = s / (float)a.in_dim;
         float qv = 0.f;
-        for (int k = 0; k < a.in_dim; ++k) { const float d = (ok ? __ldg(o + k) : 0.f) - mean; qv = fmaf(d, d, qv); }
+        for (int k0 = 0; k0 < a.in_dim; k0 += 16) {
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = (ld && k0 + j < a.in_dim) ? o[k0 + j] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { const float d = x[j] - mean; qv = k0 + j < a.in_dim ? fmaf(d, d, qv) : qv; }
+        }
         rs = rsqrtf(qv / (float)a.in_dim + 1e-5f);
       }
-      if (pending) { wait_m(); pending = false; }
-      for (int ch = 0; ch < wch0; ++ch) {
-        float x[8];
+      if (HEAD == HB_HEAD_DISCRETE && a.avail != nullptr && ld) {
+        in_avm = 0u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = ch * 8 + j;
-          x[j] = (ok && k < a.in_dim) ? (__ldg(o + k) - mean) * rs * XS : 0.f;
+        for (int j = 0; j < NH; ++j) in_avm |= (j < a.out && in_av[j] != 0.f) ? (1u << j) : 0u;
+      }
+      pc.lap(0);                                   // inputs + feature-norm statistics
+      if (pending) { wait_m(); pending = false; }
+      pc.lap(1);                                   // wait: last backward MMAs of the previous tile
+      const float rsx = rs * XS;
+      if (half == 0) {
+        for (int k0 = 0; k0 < K0p; k0 += 16) {
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = (ld && k0 + j < a.in_dim) ? (o[k0 + j] - mean) * rsx : 0.f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float xc[8] = {x[c * 8], x[c * 8 + 1], x[c * 8 + 2], x[c * 8 + 3], x[c * 8 + 4], x[c * 8 + 5], x[c * 8 + 6], x[c * 8 + 7]};
+            uint4 hi, lo;
+            um::split8(xc, hi, lo);
+            const uint32_t off = img_off(r, (k0 >> 3) + c, wch0);
+            *reinterpret_cast<uint4*>(X0 + off) = hi;
+            *reinterpret_cast<uint4*>(X0 + x0_bytes + off) = lo;
+          }
         }
-        uint4 hi, lo;
-        um::split8(x, hi, lo);
-        const uint32_t off = img_off(r, ch, wch0);
-        *reinterpret_cast<uint4*>(X0 + off) = hi;
-        *reinterpret_cast<uint4*>(X0 + x0_bytes + off) = lo;
       }
       signal();
+      pc.lap(2);                                   // X0 image written
       // ---- layer 0
       float mu0, rstd0, mu1, rstd1;
-      uint32_t mask0[4] = {0, 0, 0, 0}, mask1[4] = {0, 0, 0, 0};
+      uint32_t mask0[2] = {0, 0}, mask1[2] = {0, 0};
       wait_m();
-      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb0, 1.f / (XS * ws0), X1, x_bytes, wchx, r, mu0, rstd0, mask0);
+      pc.lap(3);                                   // wait: layer-0 MMAs
+      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb0, 1.f / (XS * ws0), X1, x_bytes, wchx, RP, mu0, rstd0, mask0);
       signal();
+      pc.lap(4);                                   // layer-0 epilogue
       // ---- layer 1
       wait_m();
-      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb1, 1.f / (XS * ws1), X2, x_bytes, wchx, r, mu1, rstd1, mask1);
+      pc.lap(5);                                   // wait: layer-1 MMAs
+      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb1, 1.f / (XS * ws1), X2, x_bytes, wchx, RP, mu1, rstd1, mask1);
       signal();
+      pc.lap(6);                                   // layer-1 epilogue
       // ---- head
       wait_m();
-      float hv[NH];
-      um::tmem_ld16(tl + C_H, hv);
-      const float hdesc = 1.f / (XS * wsh);
+      pc.lap(7);                                   // wait: head MMAs
       float dl[NH];
 #pragma unroll
       for (int j = 0; j < NH; ++j) dl[j] = 0.f;
-      if (HEAD == HB_HEAD_DISCRETE) {
-        float lg[NH], lp[NH], pj[NH];
+      if (half == 0) {
+        float hv[NH];
+        um::tmem_ld16(tl + C_H, hv);
+        const float hdesc = 1.f / (XS * wsh);
+        if (HEAD == HB_HEAD_DISCRETE) {
+          float lg[NH], lp[NH], pj[NH];
 #pragma unroll
-        for (int j = 0; j < NH; ++j) lg[j] = hv[j] * hdesc;
-        unsigned avm = 0xffffu;
-        if (a.avail != nullptr && ok) {
-          avm = 0u;
-          for (int j = 0; j < na; ++j) avm |= a.avail[src * na + j] != 0.f ? (1u << j) : 0u;
-        }
-        const float ent = rows::categorical<NH>(lg, sbh, na, avm, lp, pj);
-        const int act = ok ? (int)a.actions[src] : 0;
-        const float lpa = rows::select<NH>(lp, act);
-        if (MODE == M_EVAL) {
-          if (ok) {
-            if (a.logp_out) a.logp_out[row] = lpa;
-            if (a.factor_inout) a.factor_inout[src] = a.factor_inout[src] * expf(lpa - a.logp_ref[src]);
+          for (int j = 0; j < NH; ++j) lg[j] = hv[j] * hdesc;
+          const unsigned avm = in_avm;
+          const float ent = rows::categorical<NH>(lg, sbh, na, avm, lp, pj);
+          const int act = ld ? (int)in_act : 0;
+          const float lpa = rows::select<NH>(lp, act);
+          if (MODE == M_EVAL) {
+            if (ok) {
+              if (a.logp_out) a.logp_out[row] = lpa;
+              if (a.factor_inout) a.factor_inout[src] = a.factor_inout[src] * expf(lpa - a.logp_ref[src]);
+            }
+          } else {
+            // happo.py:66-91 (the 1 / sum(active) normaliser is applied when the slots are reduced)
+            const float w = in_w, fac = in_fac, adv = in_adv, old = in_old;
+            const float ratio = expf(lpa - old);
+            float m;
+            const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
+            const float okf = ok ? 1.f : 0.f;
+            const float c_lp = -fac * w * dm * ratio * okf;
+            const float c_h = a.entropy_coef * w * okf;
+            if (ok) { s_loss += -fac * m * w; s_ent += ent * w; s_ratio += ratio; s_rows += 1.f; }
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              const bool live = j < na && ((avm >> j) & 1u);
+              dl[j] = live ? c_lp * ((j == act ? 1.f : 0.f) - pj[j]) + c_h * pj[j] * (lp[j] + ent) : 0.f;
+            }
           }
-        } else {
-          // happo.py:66-91 (the 1 / sum(active) normaliser is applied when the slots are reduced)
-          float w = 1.f, fac = 1.f, adv = 0.f, old = 0.f;
-          if (ok) {
-            if (a.use_active) w = a.active[src];
-            if (a.factor) fac = a.factor[src];
-            adv = a.adv[src];
-            old = a.old_logp[src];
-          }
-          const float ratio = expf(lpa - old);
-          float m;
-          const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
-          const float okf = ok ? 1.f : 0.f;
-          const float c_lp = -fac * w * dm * ratio * okf;
-          const float c_h = a.entropy_coef * w * okf;
-          if (ok) { s_loss += -fac * m * w; s_ent += ent * w; s_ratio += ratio; s_rows += 1.f; }
+        } else if (HEAD == HB_HEAD_BOX) {
+          // DiagGaussian (distributions.py:24-34,58-89)
+          float lpj[NH], dlt[NH];
+          float ent_row = 0.f;
 #pragma unroll
           for (int j = 0; j < NH; ++j) {
-            const bool live = j < na && ((avm >> j) & 1u);
-            dl[j] = live ? c_lp * ((j == act ? 1.f : 0.f) - pj[j]) + c_h * pj[j] * (lp[j] + ent) : 0.f;
-            gb[j] += dl[j];
+            lpj[j] = 0.f; dlt[j] = 0.f;
+            if (j < na) {
+              const float mean_j = fmaf(hv[j], hdesc, sbh[j]);
+              dlt[j] = (ok ? a.actions[src * na + j] : 0.f) - mean_j;
+              lpj[j] = -(dlt[j] * dlt[j]) * 0.5f * sstd[3 * NH + j] - sstd[NH + j] - 0.5f * HB_LOG_2PI_F;
+              ent_row += 0.5f + 0.5f * HB_LOG_2PI_F + sstd[NH + j];
+            }
           }
-        }
-      } else if (HEAD == HB_HEAD_BOX) {
-        // DiagGaussian (distributions.py:24-34,58-89)
-        float lpj[NH], dlt[NH];
-        float ent_row = 0.f;
+          if (MODE == M_EVAL) {
+            if (ok) {
+              float agg = a.agg_prod ? 1.f : 0.f;
 #pragma unroll
-        for (int j = 0; j < NH; ++j) {
-          lpj[j] = 0.f; dlt[j] = 0.f;
-          if (j < na) {
-            const float mean_j = fmaf(hv[j], hdesc, sbh[j]);
-            dlt[j] = (ok ? a.actions[src * na + j] : 0.f) - mean_j;
-            lpj[j] = -(dlt[j] * dlt[j]) * 0.5f * sstd[3 * NH + j] - sstd[NH + j] - 0.5f * HB_LOG_2PI_F;
-            ent_row += 0.5f + 0.5f * HB_LOG_2PI_F + sstd[NH + j];
-          }
-        }
-        if (MODE == M_EVAL) {
-          if (ok) {
-            float agg = a.agg_prod ? 1.f : 0.f;
+              for (int j = 0; j < NH; ++j) {
+                if (j < na) {
+                  if (a.logp_out) a.logp_out[row * na + j] = lpj[j];
+                  if (a.factor_inout) {
+                    const float e = expf(lpj[j] - a.logp_ref[src * na + j]);
+                    agg = a.agg_prod ? agg * e : agg + e;
+                  }
+                }
+              }
+              if (a.factor_inout) a.factor_inout[src] = a.factor_inout[src] * (a.agg_prod ? agg : agg / (float)na);
+            }
+          } else {
+            const float w = in_w, fac = in_fac, adv = in_adv;
+            float e[NH];
+            float ratio = a.agg_prod ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              e[j] = 0.f;
+              if (j < na) {
+                e[j] = expf(lpj[j] - (ok ? a.old_logp[src * na + j] : 0.f));
+                ratio = a.agg_prod ? ratio * e[j] : ratio + e[j];
+              }
+            }
+            if (!a.agg_prod) ratio /= (float)na;
+            float m;
+            const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
+            const float okf = ok ? 1.f : 0.f;
+            const float c_r = -fac * w * dm * okf;
+            if (ok) { s_loss += -fac * m * w; s_ent += ent_row * w; s_ratio += ratio; s_rows += 1.f; }
 #pragma unroll
             for (int j = 0; j < NH; ++j) {
               if (j < na) {
-                if (a.logp_out) a.logp_out[row * na + j] = lpj[j];
-                if (a.factor_inout) {
-                  const float e = expf(lpj[j] - a.logp_ref[src * na + j]);
-                  agg = a.agg_prod ? agg * e : agg + e;
-                }
+                const float sd = sstd[j], ivar = sstd[3 * NH + j];
+                const float c_lp = c_r * (a.agg_prod ? ratio : e[j] / (float)na);
+                const float dmean = c_lp * dlt[j] * ivar;
+                const float dstd = c_lp * (dlt[j] * dlt[j] * ivar / sd - 1.f / sd) - a.entropy_coef * w * okf / sd;
+                dl[j] = dmean;
+                if (j < 8) dl[8 + j] = dstd * sstd[2 * NH + j];   // d loss / d log_std[j]: summed over rows by the C_BH MMAs
               }
             }
-            if (a.factor_inout) a.factor_inout[src] = a.factor_inout[src] * (a.agg_prod ? agg : agg / (float)na);
           }
         } else {
-          float w = 1.f, fac = 1.f, adv = 0.f;
-          if (ok) {
-            if (a.use_active) w = a.active[src];
-            if (a.factor) fac = a.factor[src];
-            adv = a.adv[src];
-          }
-          float e[NH];
-          float ratio = a.agg_prod ? 1.f : 0.f;
-#pragma unroll
-          for (int j = 0; j < NH; ++j) {
-            e[j] = 0.f;
-            if (j < na) {
-              e[j] = expf(lpj[j] - (ok ? a.old_logp[src * na + j] : 0.f));
-              ratio = a.agg_prod ? ratio * e[j] : ratio + e[j];
+          // value head + cal_value_loss (v_critic.py:75-114); the 1 / rows normaliser is applied at the slot reduction
+          const float v = fmaf(hv[0], hdesc, sbh[0]);
+          if (MODE == M_EVAL) {
+            if (ok && a.logp_out) a.logp_out[row] = v;
+          } else {
+            const float vp = in_vp;
+            float ret = in_ret;
+            if (a.vn_state != nullptr) ret = (ret - vmean) / vstd;
+            const float dv = v - vp;
+            const float dc = fminf(fmaxf(dv, -a.clip), a.clip);
+            const float vclip = vp + dc;
+            const bool pass = dv >= -a.clip && dv <= a.clip;
+            float de_c, de_o;
+            const float l_c = huber_v(ret - vclip, a.huber_delta, a.use_huber, &de_c);
+            const float l_o = huber_v(ret - v, a.huber_delta, a.use_huber, &de_o);
+            const float g_o = -de_o, g_c = pass ? -de_c : 0.f;
+            float loss = l_o, g = g_o;
+            if (a.use_clipped) {
+              if (l_c > l_o) { loss = l_c; g = g_c; }
+              else if (l_c == l_o) { loss = l_o; g = 0.5f * (g_o + g_c); }
             }
+            g = ok ? g * a.vcoef : 0.f;
+            if (ok) { s_loss += loss; s_rows += 1.f; }
+            dl[0] = g;
           }
-          if (!a.agg_prod) ratio /= (float)na;
-          float m;
-          const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
-          const float okf = ok ? 1.f : 0.f;
-          const float c_r = -fac * w * dm * okf;
-          if (ok) { s_loss += -fac * m * w; s_ent += ent_row * w; s_ratio += ratio; s_rows += 1.f; }
-#pragma unroll
-          for (int j = 0; j < NH; ++j) {
-            if (j < na) {
-              const float sd = sstd[j], ivar = sstd[3 * NH + j];
-              const float c_lp = c_r * (a.agg_prod ? ratio : e[j] / (float)na);
-              const float dmean = c_lp * dlt[j] * ivar;
-              const float dstd = c_lp * (dlt[j] * dlt[j] * ivar / sd - 1.f / sd) - a.entropy_coef * w * okf / sd;
-              gs[HEAD == HB_HEAD_BOX ? j : 0] += dstd * sstd[2 * NH + j];
-              gb[j] += dmean;
-              dl[j] = dmean;
-            }
-          }
-        }
-      } else {
-        // value head + cal_value_loss (v_critic.py:75-114); the 1 / rows normaliser is applied at the slot reduction
-        const float v = fmaf(hv[0], hdesc, sbh[0]);
-        if (MODE == M_EVAL) {
-          if (ok && a.logp_out) a.logp_out[row] = v;
-        } else {
-          const float vp = ok ? a.value_preds[src] : 0.f;
-          float ret = ok ? a.returns[src] : 0.f;
-          if (a.vn_state != nullptr) ret = (ret - vmean) / vstd;
-          const float dv = v - vp;
-          const float dc = fminf(fmaxf(dv, -a.clip), a.clip);
-          const float vclip = vp + dc;
-          const bool pass = dv >= -a.clip && dv <= a.clip;
-          float de_c, de_o;
-          const float l_c = huber_v(ret - vclip, a.huber_delta, a.use_huber, &de_c);
-          const float l_o = huber_v(ret - v, a.huber_delta, a.use_huber, &de_o);
-          const float g_o = -de_o, g_c = pass ? -de_c : 0.f;
-          float loss = l_o, g = g_o;
-          if (a.use_clipped) {
-            if (l_c > l_o) { loss = l_c; g = g_c; }
-            else if (l_c == l_o) { loss = l_o; g = 0.5f * (g_o + g_c); }
-          }
-          g = ok ? g * a.vcoef : 0.f;
-          if (ok) { s_loss += loss; s_rows += 1.f; }
-          gb[0] += g;
-          dl[0] = g;
         }
       }
       if (!GRAD) continue;   // evaluate: nothing of this tile is read by a later MMA group
-      {
+      if (half == 0) {
         float x[8];
         uint4 hi, lo;
 #pragma unroll
@@ -613,18 +768,23 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
         }
       }
       signal();
+      pc.lap(8);                                   // head epilogue (loss, d logits)
       // ---- layer 1 backward (dL/dxhat_1 in C_F), dZ_1 over xhat_1 in X2
       wait_m();
-      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * wsh), X2, x_bytes, wchx, r, mu1, rstd1, mask1, ok);
+      pc.lap(9);                                   // wait: head backward MMAs
+      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * wsh), X2, x_bytes, wchx, RP, mu1, rstd1, mask1, ok);
       signal();
+      pc.lap(10);                                  // layer-1 backward epilogue
       // ---- layer 0 backward (dL/dxhat_0 in C_F), dZ_0 over xhat_0 in X1
       wait_m();
-      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * ws1), X1, x_bytes, wchx, r, mu0, rstd0, mask0, ok);
+      pc.lap(11);                                  // wait: layer-1 backward MMAs (dW1, db1, dX through 4 weight chunks)
+      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * ws1), X1, x_bytes, wchx, RP, mu0, rstd0, mask0, ok);
       signal();
+      pc.lap(12);                                  // layer-0 backward epilogue
       pending = true;
     }
-    if (GRAD) {
-      if (pending) wait_m();
+    if (GRAD && pending) wait_m();
+    if (GRAD && half == 0) {
       // ---- flush: this CTA's weight-gradient sums -> its slot of the split buffer (lane = output feature n)
       float* slot = a.part + (long long)blockIdx.x * a.part_stride;
       const int n = r;
@@ -659,26 +819,16 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
             if (j < na) slot[a.phw + j * H + n] = v[j];
         }
       }
-      // head bias / log_std gradients and the loss scalars: sums over this CTA's rows
-#pragma unroll
-      for (int j = 0; j < NH; ++j) {
-        const float s = warp_sum(gb[j]);
-        if (lane == 0 && j < na) atomicAdd(&sacc[j], s);
+      {
+        float v[16];
+        um::tmem_ld16(tl + C_BH, v);
+        if (n < na) slot[a.phb + n] = v[0];
+        if (HEAD == HB_HEAD_BOX && n >= 8 && n < 8 + na) slot[a.plogstd + n - 8] = v[0];
       }
-      if (HEAD == HB_HEAD_BOX) {
-#pragma unroll
-        for (int j = 0; j < (HEAD == HB_HEAD_BOX ? NH : 1); ++j) {
-          const float s = warp_sum(gs[j]);
-          if (lane == 0 && j < na) atomicAdd(&sacc[NH + j], s);
-        }
-      }
+      // the loss scalars: sums over this CTA's rows
       const double d0 = warp_sum_d((double)s_loss), d1 = warp_sum_d((double)s_ent), d2 = warp_sum_d((double)s_ratio), d3 = warp_sum_d((double)s_rows);
       if (lane == 0) { sred[q * 4 + 0] = d0; sred[q * 4 + 1] = d1; sred[q * 4 + 2] = d2; sred[q * 4 + 3] = d3; }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (r < na) {
-        slot[a.phb + r] = sacc[r];
-        if (HEAD == HB_HEAD_BOX) slot[a.plogstd + r] = sacc[NH + r];
-      }
       if (r < 4) {
         const double s = sred[r] + sred[4 + r] + sred[8 + r] + sred[12 + r];
         if (HEAD == HB_HEAD_VALUE) { if (r == 0) atomicAdd(a.scalars, s); if (r == 3) atomicAdd(a.scalars + 1, s); }
@@ -696,7 +846,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
 // [128, 256), split into fp16 hi / lo, written as KC-wide k-chunks of K-major core matrices; folded bias b' = b + W beta.
 __global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, const float* __restrict__ b, int N, int K,
-                                                         int Nimg, int Kp, int KC, __half* __restrict__ img,
+                                                         int Nimg, int Kp, int KC, int RC, __half* __restrict__ img,
                                                          float* __restrict__ bias_out, float* __restrict__ scale_out) {
   __shared__ float smax[8];
   __shared__ float sscale;
@@ -712,7 +862,7 @@ __global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict
     if (m > 0.f) frexpf(m, &ex);                     // m = f * 2^ex, f in [0.5, 1)
     ex = ex < -20 ? -20 : (ex > 20 ? 20 : ex);
     sscale = m > 0.f ? exp2f((float)(8 - ex)) : 1.f;
-    if (blockIdx.x == 0) *scale_out = sscale;
+    if (blockIdx.x == 0 && scale_out != nullptr) *scale_out = sscale;
   }
   __syncthreads();
   const float sc = sscale;
@@ -722,6 +872,14 @@ __global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict
     const float v = (n < N && k < K) ? W[n * K + k] * (gamma ? gamma[k] : 1.f) * sc : 0.f;
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
+    if (RC > 0) {   // chunks of RC rows, each a [RC][Kp] K-major image pair (hi, lo)
+      const int c = n / RC, nl = n % RC;
+      const size_t chunk0 = (size_t)c * (2u * RC * Kp);
+      const size_t e = (size_t)((nl >> 3) * (Kp >> 3) + (k >> 3)) * 64 + (nl & 7) * 8 + (k & 7);
+      img[chunk0 + e] = hi;
+      img[chunk0 + (size_t)RC * Kp + e] = lo;
+      continue;
+    }
     const int c = k / KC, kl = k % KC;                                          // KC-wide k-chunks (the last may be narrower)
     const int kc = Kp - KC * c < KC ? Kp - KC * c : KC;
     const size_t chunk0 = (size_t)c * (2u * Nimg * KC);                        // halves before this chunk
@@ -729,7 +887,7 @@ __global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict
     img[chunk0 + e] = hi;
     img[chunk0 + (size_t)Nimg * kc + e] = lo;
   }
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && bias_out != nullptr) {
     for (int n = threadIdx.x; n < Nimg; n += 256) {
       float v = 0.f;
       if (n < N) {
@@ -764,6 +922,19 @@ static std::atomic<int> g_enabled{-1};
 
 }  // namespace fz
 
+// profiling aid: enable / read the per-phase cycle table of the fused kernel (out: [148][16] uint64)
+int fused_timing_enable(int on) {
+  static const unsigned long long zeros[148 * 16] = {0};
+  cudaError_t e = cudaMemcpyToSymbol(fz::g_phase_cycles, zeros, sizeof(zeros));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(fz::g_phase_on, &on, sizeof(int));
+  return e == cudaSuccess ? HB_OK : cuda_fail(e, "fused_timing_enable");
+}
+int fused_timing_read(unsigned long long* out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out, fz::g_phase_cycles, sizeof(unsigned long long) * 148 * 16);
+  return e == cudaSuccess ? HB_OK : cuda_fail(e, "fused_timing_read");
+}
+
 bool fused_enabled() {
   int v = fz::g_enabled.load(std::memory_order_relaxed);
   if (v < 0) {
@@ -781,7 +952,7 @@ bool fused_shape_ok(const hb_net_desc* d) {
   if (H != 32 && H != 64 && H != 128) return false;
   if (!d->feature_norm || d->in_dim < 1 || d->in_dim > 64) return false;
   if (d->activation == HB_ACT_HARDSWISH) return false;
-  if (d->out_dim < 1 || d->out_dim > fz::NH) return false;
+  if (d->out_dim < 1 || d->out_dim > (d->head == HB_HEAD_BOX ? 8 : fz::NH)) return false;
   return true;
 }
 
@@ -790,21 +961,24 @@ int launch_fused_pack(const hb_net_desc* d, const ParamLayout& P, const PrepLayo
   const int H = d->hidden[0];
   float* sc = prepared + Q.fz_scale;
   fz::fused_pack_kernel<<<8, 256, 0, st>>>(params + P.w[0], params + P.fn_w, params + P.fn_b, params + P.b[0], H, d->in_dim, H,
-                                           Q.fz_k0p, 32, reinterpret_cast<__half*>(prepared + Q.fz_w[0]), prepared + Q.fz_bias[0], sc + 0);
+                                           Q.fz_k0p, 32, 0, reinterpret_cast<__half*>(prepared + Q.fz_w[0]), prepared + Q.fz_bias[0], sc + 0);
   HB_LAUNCH_DONE(st, "fused_pack");
-  fz::fused_pack_kernel<<<16, 256, 0, st>>>(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32,
+  fz::fused_pack_kernel<<<16, 256, 0, st>>>(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32, 0,
                                             reinterpret_cast<__half*>(prepared + Q.fz_w[1]), prepared + Q.fz_bias[1], sc + 1);
   HB_LAUNCH_DONE(st, "fused_pack");
+  fz::fused_pack_kernel<<<16, 256, 0, st>>>(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32, 32,
+                                            reinterpret_cast<__half*>(prepared + Q.fz_w1b), nullptr, nullptr);
+  HB_LAUNCH_DONE(st, "fused_pack");
   fz::fused_pack_kernel<<<4, 256, 0, st>>>(params + P.hw, params + P.lnw[1], params + P.lnb[1], params + P.hbias, d->out_dim, H,
-                                           fz::NH, H, H, reinterpret_cast<__half*>(prepared + Q.fz_hw), prepared + Q.fz_hbias, sc + 2);
+                                           fz::NH, H, H, 0, reinterpret_cast<__half*>(prepared + Q.fz_hw), prepared + Q.fz_hbias, sc + 2);
   HB_LAUNCH_DONE(st, "fused_pack");
   return HB_OK;
 }
 
 size_t fused_smem_bytes(int H, int K0p) {
   size_t b = 2 * (size_t)fz::TILE * K0p * 2 + 2 * 2 * (size_t)fz::TILE * 128 * 2 + 3 * (size_t)fz::TILE * fz::NH * 2 +
-             2 * (size_t)fz::NH * H * 2 + (size_t)fz::STAGES * fz::STAGE_BYTES;
-  b += 2 * 128 * 4 + fz::NH * 4 + 4 * fz::NH * 4 + 2 * fz::NH * 4 + 16 * 8 + 8 * 8 + 16;
+             2 * (size_t)fz::NH * H * 2 + (size_t)(K0p <= 32 ? 3 : 2) * fz::STAGE_BYTES;
+  b += 2 * 128 * 4 + fz::NH * 4 + 4 * fz::NH * 4 + 2 * fz::NH * 4 + 16 * 8 + 2 * fz::TILE * 2 * 4 + 10 * 8 + 16;
   return b + 1024;
 }
 
@@ -830,11 +1004,13 @@ int launch_fused_update(const hb_net_desc* d, const PrepLayout& Q, const ParamLa
   a.H = H; a.K0p = Q.fz_k0p; a.in_dim = d->in_dim; a.out = d->out_dim; a.act = d->activation; a.nch0 = Q.fz_chunks[0];
   a.img0 = reinterpret_cast<const __half*>(prepared + Q.fz_w[0]);
   a.img1 = reinterpret_cast<const __half*>(prepared + Q.fz_w[1]);
+  a.img1b = reinterpret_cast<const __half*>(prepared + Q.fz_w1b);
   a.imgh = reinterpret_cast<const __half*>(prepared + Q.fz_hw);
   a.bias0 = prepared + Q.fz_bias[0]; a.bias1 = prepared + Q.fz_bias[1]; a.biash = prepared + Q.fz_hbias;
   a.scales = prepared + Q.fz_scale;
   a.log_std = prepared + Q.log_std; a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;
   a.pw0 = P.w[0]; a.pb0 = P.b[0]; a.pw1 = P.w[1]; a.pb1 = P.b[1]; a.phw = P.hw; a.phb = P.hbias; a.plogstd = P.log_std;
+  a.stage_obs = (a.index == nullptr && (reinterpret_cast<uintptr_t>(a.obs) & 15) == 0) ? 1 : 0;
   const long long ntiles = (a.rows + fz::TILE - 1) / fz::TILE;
   const int grid = (int)(ntiles < 148 ? ntiles : 148);
   if (grid_out) *grid_out = grid;
@@ -860,8 +1036,8 @@ int launch_fused_finish(const hb_net_desc* d, const ParamLayout& P, const float*
   auto add = [&](int off, int len, float s) { R.off[n] = off; R.len[n] = len; R.scale[n] = s; ++n; };
   add(P.w[0], H * d->in_dim, sw); add(P.b[0], H, sb);
   add(P.w[1], H * H, sw);         add(P.b[1], H, sb);
-  add(P.hw, d->out_dim * H, sw);  add(P.hbias, d->out_dim, 1.f);
-  if (d->head == HB_HEAD_BOX) add(P.log_std, d->out_dim, 1.f);
+  add(P.hw, d->out_dim * H, sw);  add(P.hbias, d->out_dim, sb);
+  if (d->head == HB_HEAD_BOX) add(P.log_std, d->out_dim, sb);
   R.n = n;
   fz::fused_slot_reduce_kernel<<<(P.total + 127) / 128, 128, 0, st>>>(grad, part, slots, stride, P.total, R, norm3, host_scale);
   HB_LAUNCH_DONE(st, "fused_slot_reduce");

@@ -152,6 +152,7 @@ int make_layouts(const hb_net_desc* d, ParamLayout* pl, PrepLayout* pp, hb_net_l
       Q.fz_w[l] = c;    c += H * kp[l];          // 2 images x H x kp halves = H * kp floats
       Q.fz_bias[l] = c; c += H;
     }
+    Q.fz_w1b = c;   c += H * H;
     Q.fz_hw = c;    c += 16 * H;                 // 2 images x 16 x H halves
     Q.fz_hbias = c; c += 16;
     Q.fz_scale = c; c += 4;

@@ -111,6 +111,10 @@ int hb_get_gemm_impl(void);
  * layer-wise kernels.  Env HB_FUSED=0 selects 0.  hb_set_gemm_impl(0) (FP32 SIMT) also disables it. */
 int hb_set_fused_update(int on);
 int hb_get_fused_update(void);
+/* Profiling aid: per-CTA, per-phase SM-clock cycle totals of the fused kernel (thread 64 of every CTA).  enable(1) clears and
+ * arms the table; read synchronises the device and copies [148][16] uint64 (slots: fused_update.cu PhaseClock laps). */
+int hb_fused_timing_enable(int on);
+int hb_fused_timing_read(unsigned long long* out);
 
 /* ---- network parameter plumbing ------------------------------------------------------ */
 int hb_net_layout_of(const hb_net_desc* d, hb_net_layout* out);

@@ -170,8 +170,14 @@ def test_evaluate_and_factor_update_fused_equals_layerwise(head, out):
         avail[torch.arange(rows), actions[:, 0].long().cpu()] = 1.0
         avail = cu(avail)
     else:
-        actions, avail = cu(0.5 * torch.randn(rows, out, generator=g)), None
-    ref = cu(-1.2 + 0.1 * torch.randn(rows, ad, generator=g))
+        actions, avail = cu(0.2 * torch.randn(rows, out, generator=g)), None
+    # reference log-probs near the net's own (a factor update multiplies by exp(logp - ref): keep it O(1))
+    from harl_b200 import _lib as L_
+    L_.call("hb_set_fused_update", 0)
+    lp0 = torch.empty(rows, ad, device="cuda")
+    net.evaluate(DeviceNet.actor_batch(obs, actions, avail=avail), logp_out=lp0)
+    L_.call("hb_set_fused_update", 1)
+    ref = (lp0 + 0.1 * torch.randn(rows, ad, generator=g).cuda()).contiguous()
     factor0 = cu(torch.exp(0.1 * torch.randn(rows, generator=g)))
     batch = DeviceNet.actor_batch(obs, actions, avail=avail)
 
