@@ -141,7 +141,7 @@ __device__ __forceinline__ void fwd_epilogue(int act_rt, uint32_t tacc, int H, c
   const int r = P.r, nc = H >> 1, cb = P.half * nc;
   const float inv_n = 1.f / (float)H;
   uint32_t va[16], vb[16];
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
   uint32_t mk0 = 0u, mk1 = 0u;
   um::tmem_ld16_issue(tacc + cb, va);
 #define HB_STEP(CC, CUR, NXT)                                                                              \
@@ -159,7 +159,10 @@ __device__ __forceinline__ void fwd_epilogue(int act_rt, uint32_t tacc, int H, c
         m_ |= z > 0.f ? (1u << (q * 8 + j)) : 0u;                                                          \
         x[j] = act_f<ACT>(act_rt, z);                                                                      \
       }                                                                                                    \
-      s0 += (x[0] + x[1]); s1 += (x[2] + x[3]); s2 += (x[4] + x[5]); s3 += (x[6] + x[7]);                  \
+      _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                                   \
+        s0 += x[j]; s1 += x[j + 1];                                                                        \
+        q0 = fmaf(x[j], x[j], q0); q1 = fmaf(x[j + 1], x[j + 1], q1);                                      \
+      }                                                                                                    \
       uint4 hi, lo;                                                                                        \
       um::split8(x, hi, lo);                                                                               \
       const uint32_t off = img_off(r, (cb >> 3) + (CC) * 2 + q, wch);                                      \
@@ -171,25 +174,14 @@ __device__ __forceinline__ void fwd_epilogue(int act_rt, uint32_t tacc, int H, c
   HB_STEP(0, va, vb) HB_STEP(1, vb, va) HB_STEP(2, va, vb) HB_STEP(3, vb, va)
 #undef HB_STEP
   mask[0] = mk0; mask[1] = mk1;
-  float part = (s0 + s1) + (s2 + s3);
-  P.put(0, part);
+  // statistics from one pass: var = E[a^2] - mean^2 (post-activation rows: var is the same order as E[a^2], the cancellation
+  // costs a few ulp; a second pass over the row would double the fp16 -> fp32 conversions, the busiest pipe of this kernel)
+  const float ps = s0 + s1, pq = q0 + q1;
+  P.put(0, ps);
+  P.put(1, pq);
   P.sync();
-  mu = P.total(0, part) * inv_n;
-  s0 = s1 = 0.f;
-  for (int c8 = 0; c8 < (nc >> 3); ++c8) {
-    const uint32_t off = img_off(r, (cb >> 3) + c8, wch);
-    float x[8];
-    um::join8(*reinterpret_cast<const uint4*>(img + off), *reinterpret_cast<const uint4*>(img + img_bytes + off), x);
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      const float d0 = x[j] - mu, d1 = x[j + 1] - mu;
-      s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1);
-    }
-  }
-  part = s0 + s1;
-  P.put(1, part);
-  P.sync();
-  rstd = rsqrtf(P.total(1, part) * inv_n + 1e-5f);
+  mu = P.total(0, ps) * inv_n;
+  rstd = rsqrtf(fmaxf(P.total(1, pq) * inv_n - mu * mu, 0.f) + 1e-5f);
   const float rs = rstd * XS, sh = -mu * rstd * XS;
   for (int c8 = 0; c8 < (nc >> 3); ++c8) {
     const uint32_t off = img_off(r, (cb >> 3) + c8, wch);
@@ -280,12 +272,19 @@ __device__ __forceinline__ float huber_v(float e, float d, int use_huber, float*
 // epilogue phase / each wait for the MMA warp to a global table, read back through hb_fused_timing_read.
 __device__ unsigned long long g_phase_cycles[148 * 16];
 __device__ int g_phase_on;
-struct PhaseClock {
+struct PhaseClock {   // accumulates in shared memory (a global read-modify-write per lap would itself cost ~600 cycles)
   unsigned long long t;
+  unsigned long long* acc;
   bool on;
-  __device__ __forceinline__ void start(bool enable) { on = enable; if (on) t = clock64(); }
+  __device__ __forceinline__ void start(bool enable, unsigned long long* smem_acc) {
+    on = enable; acc = smem_acc;
+    if (on) { for (int i = 0; i < 16; ++i) acc[i] = 0ull; t = clock64(); }
+  }
   __device__ __forceinline__ void lap(int slot) {
-    if (on) { const unsigned long long n = clock64(); g_phase_cycles[blockIdx.x * 16 + slot] += n - t; t = n; }
+    if (on) { const unsigned long long n = clock64(); acc[slot] += n - t; t = n; }
+  }
+  __device__ __forceinline__ void flush() {
+    if (on) for (int i = 0; i < 16; ++i) g_phase_cycles[blockIdx.x * 16 + i] += acc[i];
   }
 };
 
@@ -314,15 +313,33 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   double* sred = reinterpret_cast<double*>(p); p += 4 * 4 * 8;
   float* xch = reinterpret_cast<float*>(p); p += 2 * TILE * 2 * 4;  // row-pair exchange of partial sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(p); p += 10 * 8;
+  unsigned long long* sclk = reinterpret_cast<unsigned long long*>(p); p += 16 * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p);
   uint64_t* w_full = bars;                // [STAGES] weight chunk landed
   uint64_t* w_empty = bars + MAX_STAGES;  // [STAGES] MMAs reading the chunk retired
-  uint64_t* e2m = bars + 2 * MAX_STAGES;  // epilogue warps -> MMA warp (256 arrivals)
+  uint64_t* e2m = bars + 2 * MAX_STAGES;  // epilogue warps -> MMA warp (8 arrivals: lane 0 of every epilogue warp)
   uint64_t* m2e = e2m + 1;            // MMA warp -> epilogue warps (tcgen05.commit)
   uint64_t* obs_free = e2m + 2;       // MMA warp -> producer: the staging image of the next tile's observations is dead
   uint64_t* obs_full = e2m + 3;       // producer's bulk copy -> epilogue warps
   unsigned char* OBS = MODE == M_GRAD ? X2 : X1;   // staging buffer = an activation image that is idle at that point
   const uint32_t obs_bytes = (uint32_t)TILE * (uint32_t)a.in_dim * 4u;
+  // per-row inputs of the head phase ride along in the same staging image, behind the observation block (byte offsets; 0 = absent)
+  const int aw = HEAD == HB_HEAD_BOX ? a.out : 1;
+  uint32_t so = obs_bytes, o_act = 0, o_old = 0, o_adv = 0, o_fac = 0, o_w = 0, o_av = 0, o_vp = 0, o_ret = 0;
+  if (HEAD != HB_HEAD_VALUE) {
+    o_act = so; so += TILE * aw * 4;
+    if (MODE == M_GRAD) {
+      o_old = so; so += TILE * aw * 4;
+      o_adv = so; so += TILE * 4;
+      if (a.factor) { o_fac = so; so += TILE * 4; }
+      if (a.use_active) { o_w = so; so += TILE * 4; }
+    }
+    if (HEAD == HB_HEAD_DISCRETE && a.avail != nullptr) { o_av = so; so += TILE * a.out * 4; }
+  } else if (MODE == M_GRAD) {
+    o_vp = so; so += TILE * 4;
+    o_ret = so; so += TILE * 4;
+  }
+  const uint32_t stage_bytes = so;
 
   const long long ntiles = (a.rows + TILE - 1) / TILE;
   const int nch1 = H >> 5;
@@ -354,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   if (tid < 16) sred[tid] = 0.0;
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { um::mbar_init(&w_full[i], 1); um::mbar_init(&w_empty[i], 1); }
-    um::mbar_init(e2m, 256);
+    um::mbar_init(e2m, 8);             // one arrival per epilogue warp
     um::mbar_init(m2e, 1);
     um::mbar_init(obs_free, 1);
     um::mbar_init(obs_full, 1);
@@ -377,8 +394,17 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
       uint32_t it = 0, tl_ = 0;
       auto staged = [&](long long t) { return a.stage_obs && t < ntiles && (t + 1) * TILE <= a.rows; };
       auto load_obs = [&](long long t) {
-        um::mbar_expect_tx(obs_full, obs_bytes);
+        um::mbar_expect_tx(obs_full, stage_bytes);
         um::tma_bulk_g2s(OBS, a.obs + t * TILE * a.in_dim, obs_bytes, obs_full);
+        const long long r0 = t * TILE;
+        if (o_act) um::tma_bulk_g2s(OBS + o_act, a.actions + r0 * aw, TILE * aw * 4, obs_full);
+        if (o_old) um::tma_bulk_g2s(OBS + o_old, a.old_logp + r0 * aw, TILE * aw * 4, obs_full);
+        if (o_adv) um::tma_bulk_g2s(OBS + o_adv, a.adv + r0, TILE * 4, obs_full);
+        if (o_fac) um::tma_bulk_g2s(OBS + o_fac, a.factor + r0, TILE * 4, obs_full);
+        if (o_w) um::tma_bulk_g2s(OBS + o_w, a.active + r0, TILE * 4, obs_full);
+        if (o_av) um::tma_bulk_g2s(OBS + o_av, a.avail + r0 * a.out, TILE * a.out * 4, obs_full);
+        if (o_vp) um::tma_bulk_g2s(OBS + o_vp, a.value_preds + r0, TILE * 4, obs_full);
+        if (o_ret) um::tma_bulk_g2s(OBS + o_ret, a.returns + r0, TILE * 4, obs_full);
       };
       if (staged(blockIdx.x)) load_obs(blockIdx.x);
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl_) {
@@ -491,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
     const RowPair RP{xch, half, r, 2 + q};
     uint32_t pm = 0, po = 0;
     auto wait_m = [&]() { um::mbar_wait(m2e, pm); pm ^= 1; um::tc_fence_after(); };
-    auto signal = [&]() { um::fence_async_smem(); um::tc_fence_before(); um::mbar_arrive(e2m); };
+    auto signal = [&]() { um::fence_async_smem(); um::tc_fence_before(); __syncwarp(); if (lane == 0) um::mbar_arrive(e2m); };
     const int na = a.out;
     float s_loss = 0.f, s_ent = 0.f, s_ratio = 0.f, s_rows = 0.f;
     float vmean = 0.f, vstd = 1.f;
@@ -503,42 +529,58 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
     }
     bool pending = false;   // a backward MMA group of the previous tile may still read X0 / X1
     PhaseClock pc;
-    pc.start(g_phase_on != 0 && tid == 64);   // warp 2, lane 0: a half-0 thread
+    pc.start(g_phase_on != 0 && tid == 64, sclk);   // warp 2, lane 0: a half-0 thread
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const long long row = t * TILE + r;
       const bool ok = row < a.rows;
       const bool ld = ok && half == 0;   // the column-half-0 thread of a row owns its inputs, the head and the loss
       const long long src = ld ? (a.index ? (long long)a.index[row] : row) : 0;
-      // ---- per-row scalars of the head phase: requested now, consumed ~a tile's worth of work later (latency hidden)
+      // full tiles: the producer's bulk copies put the 128 x in_dim observation block and the per-row inputs of the head phase
+      // into the (idle) staging image; partial / gathered tiles read global memory directly
+      const bool st_obs = a.stage_obs && (t + 1) * TILE <= a.rows;
+      if (st_obs && half == 0) { um::mbar_wait(obs_full, po); po ^= 1; }
+      const float* stg = reinterpret_cast<const float*>(OBS);
+      const long long si = st_obs ? r : src;     // row index into the staged block / the global array
+      auto in = [&](const float* g, uint32_t off) -> const float* { return st_obs ? stg + (off >> 2) : g; };
+      // ---- per-row inputs of the head phase, read now (the staging image is rewritten by the layer epilogues)
       float in_act = 0.f, in_old = 0.f, in_adv = 0.f, in_fac = 1.f, in_w = 1.f, in_vp = 0.f, in_ret = 0.f;
+      float in_actv[HEAD == HB_HEAD_BOX ? 8 : 1], in_oldv[HEAD == HB_HEAD_BOX ? 8 : 1];
       unsigned in_avm = 0xffffu;
-      float in_av[NH];
       if (HEAD == HB_HEAD_DISCRETE) {
         if (ld) {
-          in_act = __ldg(a.actions + src);
+          in_act = in(a.actions, o_act)[si];
           if (GRAD) {
-            in_old = __ldg(a.old_logp + src); in_adv = __ldg(a.adv + src);
-            if (a.factor) in_fac = __ldg(a.factor + src);
-            if (a.use_active) in_w = __ldg(a.active + src);
+            in_old = in(a.old_logp, o_old)[si]; in_adv = in(a.adv, o_adv)[si];
+            if (a.factor) in_fac = in(a.factor, o_fac)[si];
+            if (a.use_active) in_w = in(a.active, o_w)[si];
+          }
+          if (a.avail != nullptr) {
+            const float* av = in(a.avail, o_av) + si * a.out;
+            in_avm = 0u;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) in_avm |= (j < a.out && av[j < a.out ? j : 0] != 0.f) ? (1u << j) : 0u;
           }
         }
-#pragma unroll
-        for (int j = 0; j < NH; ++j) in_av[j] = (a.avail != nullptr && ld && j < a.out) ? __ldg(a.avail + src * a.out + j) : 1.f;
       } else if (HEAD == HB_HEAD_BOX) {
+#pragma unroll
+        for (int j = 0; j < (HEAD == HB_HEAD_BOX ? 8 : 1); ++j) {
+          in_actv[j] = (ld && j < a.out) ? in(a.actions, o_act)[si * a.out + j] : 0.f;
+          in_oldv[j] = (ld && GRAD && j < a.out) ? in(a.old_logp, o_old)[si * a.out + j] : 0.f;
+        }
         if (ld && GRAD) {
-          in_adv = __ldg(a.adv + src);
-          if (a.factor) in_fac = __ldg(a.factor + src);
-          if (a.use_active) in_w = __ldg(a.active + src);
+          in_adv = in(a.adv, o_adv)[si];
+          if (a.factor) in_fac = in(a.factor, o_fac)[si];
+          if (a.use_active) in_w = in(a.active, o_w)[si];
         }
       } else if (ld && GRAD) {
-        in_vp = __ldg(a.value_preds + src); in_ret = __ldg(a.returns + src);
+        in_vp = in(a.value_preds, o_vp)[si]; in_ret = in(a.returns, o_ret)[si];
       }
-      (void)in_vp; (void)in_ret; (void)in_act; (void)in_old;
+      (void)in_vp; (void)in_ret; (void)in_act; (void)in_old; (void)in_actv; (void)in_oldv;
       // next tile's rows -> L2 (identity index only): the first touch of a tile then costs an L2 hit, not a DRAM round trip
       {
         const long long tn = t + gridDim.x;
         const long long rown = tn * TILE + r;
-        if (a.index == nullptr && rown < a.rows && half == 0) {
+        if (!a.stage_obs && a.index == nullptr && rown < a.rows && half == 0) {
           if (!a.stage_obs) {
             const float* on = a.obs + rown * a.in_dim;
             um::prefetch_l2(on);
@@ -561,12 +603,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
         }
       }
       // ---- feature LayerNorm of the observation row (mlp.py:57-66), exact two-pass statistics; the row sits in registers
-      // full tiles: the producer's bulk copy put the 128 x in_dim block into the (idle) staging image; else direct loads
-      const bool st_obs = a.stage_obs && (t + 1) * TILE <= a.rows;
-      const float* o = st_obs ? reinterpret_cast<const float*>(OBS) + r * a.in_dim : a.obs + src * a.in_dim;
+      const float* o = st_obs ? stg + r * a.in_dim : a.obs + src * a.in_dim;
       float mean = 0.f, rs = 0.f;
       if (half == 0) {
-        if (st_obs) { um::mbar_wait(obs_full, po); po ^= 1; }
         float s = 0.f;
         for (int k0 = 0; k0 < a.in_dim; k0 += 16) {
           float x[16];
@@ -585,11 +624,6 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
           for (int j = 0; j < 16; ++j) { const float d = x[j] - mean; qv = k0 + j < a.in_dim ? fmaf(d, d, qv) : qv; }
         }
         rs = rsqrtf(qv / (float)a.in_dim + 1e-5f);
-      }
-      if (HEAD == HB_HEAD_DISCRETE && a.avail != nullptr && ld) {
-        in_avm = 0u;
-#pragma unroll
-        for (int j = 0; j < NH; ++j) in_avm |= (j < a.out && in_av[j] != 0.f) ? (1u << j) : 0u;
       }
       pc.lap(0);                                   // inputs + feature-norm statistics
       if (pending) { wait_m(); pending = false; }
@@ -675,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
             lpj[j] = 0.f; dlt[j] = 0.f;
             if (j < na) {
               const float mean_j = fmaf(hv[j], hdesc, sbh[j]);
-              dlt[j] = (ok ? a.actions[src * na + j] : 0.f) - mean_j;
+              dlt[j] = (j < 8 ? in_actv[HEAD == HB_HEAD_BOX ? (j < 8 ? j : 0) : 0] : 0.f) - mean_j;
               lpj[j] = -(dlt[j] * dlt[j]) * 0.5f * sstd[3 * NH + j] - sstd[NH + j] - 0.5f * HB_LOG_2PI_F;
               ent_row += 0.5f + 0.5f * HB_LOG_2PI_F + sstd[NH + j];
             }
@@ -703,7 +737,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
             for (int j = 0; j < NH; ++j) {
               e[j] = 0.f;
               if (j < na) {
-                e[j] = expf(lpj[j] - (ok ? a.old_logp[src * na + j] : 0.f));
+                e[j] = expf(lpj[j] - (j < 8 ? in_oldv[HEAD == HB_HEAD_BOX ? (j < 8 ? j : 0) : 0] : 0.f));
                 ratio = a.agg_prod ? ratio * e[j] : ratio + e[j];
               }
             }
@@ -784,6 +818,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
       pending = true;
     }
     if (GRAD && pending) wait_m();
+    pc.flush();
     if (GRAD && half == 0) {
       // ---- flush: this CTA's weight-gradient sums -> its slot of the split buffer (lane = output feature n)
       float* slot = a.part + (long long)blockIdx.x * a.part_stride;
@@ -844,12 +879,25 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------ weight images
 // One launch per weight matrix: W'[n][k] = W[n][k] * gamma[k], scaled by a power of two so that max |W'| lands in
 // [128, 256), split into fp16 hi / lo, written as KC-wide k-chunks of K-major core matrices; folded bias b' = b + W beta.
-__global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, const float* __restrict__ b, int N, int K,
-                                                         int Nimg, int Kp, int KC, int RC, __half* __restrict__ img,
-                                                         float* __restrict__ bias_out, float* __restrict__ scale_out) {
+struct PackJob {
+  const float* W; const float* gamma; const float* beta; const float* b;
+  int N, K, Nimg, Kp, KC, RC;
+  __half* img; float* bias_out; float* scale_out;
+  int cta0, ctas;          // this job's CTA range in the launch
+};
+struct PackJobs { PackJob j[4]; int n; };
+
+__global__ void __launch_bounds__(256) fused_pack_kernel(PackJobs jobs) {
   __shared__ float smax[8];
   __shared__ float sscale;
+  int ji = 0;
+  for (int q = 1; q < jobs.n; ++q) if ((int)blockIdx.x >= jobs.j[q].cta0) ji = q;
+  const PackJob& J = jobs.j[ji];
+  const int cta = blockIdx.x - J.cta0;
+  const float* __restrict__ W = J.W;
+  const float* __restrict__ gamma = J.gamma;
+  const int N = J.N, K = J.K, Nimg = J.Nimg, Kp = J.Kp, KC = J.KC, RC = J.RC;
+  __half* __restrict__ img = J.img;
   float mx = 0.f;
   for (int i = threadIdx.x; i < N * K; i += 256) mx = fmaxf(mx, fabsf(W[i] * (gamma ? gamma[i % K] : 1.f)));
   mx = warp_max(mx);
@@ -862,12 +910,12 @@ __global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict
     if (m > 0.f) frexpf(m, &ex);                     // m = f * 2^ex, f in [0.5, 1)
     ex = ex < -20 ? -20 : (ex > 20 ? 20 : ex);
     sscale = m > 0.f ? exp2f((float)(8 - ex)) : 1.f;
-    if (blockIdx.x == 0 && scale_out != nullptr) *scale_out = sscale;
+    if (cta == 0 && J.scale_out != nullptr) *J.scale_out = sscale;
   }
   __syncthreads();
   const float sc = sscale;
   const int total = Nimg * Kp;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+  for (int i = cta * 256 + threadIdx.x; i < total; i += J.ctas * 256) {
     const int n = i / Kp, k = i % Kp;
     const float v = (n < N && k < K) ? W[n * K + k] * (gamma ? gamma[k] : 1.f) * sc : 0.f;
     const __half hi = __float2half_rn(v);
@@ -887,23 +935,25 @@ __global__ void __launch_bounds__(256) fused_pack_kernel(const float* __restrict
     img[chunk0 + e] = hi;
     img[chunk0 + (size_t)Nimg * kc + e] = lo;
   }
-  if (blockIdx.x == 0 && bias_out != nullptr) {
+  if (cta == 0 && J.bias_out != nullptr) {
     for (int n = threadIdx.x; n < Nimg; n += 256) {
       float v = 0.f;
       if (n < N) {
-        v = b[n];
-        if (beta)
-          for (int k = 0; k < K; ++k) v += W[n * K + k] * beta[k];
+        v = J.b[n];
+        if (J.beta)
+          for (int k = 0; k < K; ++k) v += W[n * K + k] * J.beta[k];
       }
-      bias_out[n] = v;
+      J.bias_out[n] = v;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ slot reduction
 struct Regions { int n; int off[8]; int len[8]; float scale[8]; };
-__global__ void fused_slot_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int slots, long long stride,
-                                         int total, Regions R, const double* __restrict__ norm3, double host_scale) {
+// grad[i] = scale_i * norm * sum over the CTA slots (coalesced across threads, 16 independent loads in flight per thread)
+__global__ void __launch_bounds__(128) fused_slot_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int slots,
+                                                                long long stride, int total, Regions R, const double* __restrict__ norm3,
+                                                                double host_scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   float sc = 0.f;
@@ -911,11 +961,43 @@ __global__ void fused_slot_reduce_kernel(float* __restrict__ grad, const float* 
   for (int q = 0; q < R.n; ++q)
     if (i >= R.off[q] && i < R.off[q] + R.len[q]) { sc = R.scale[q]; in = true; }
   if (!in) { grad[i] = 0.f; return; }
-  float acc = 0.f;
-#pragma unroll 4
-  for (int s = 0; s < slots; ++s) acc += part[(long long)s * stride + i];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int s = 0;
+  for (; s + 16 <= slots; s += 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = part[(long long)(s + u) * stride + i];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc[u & 3] += v[u];
+  }
+  for (; s < slots; ++s) acc[0] += part[(long long)s * stride + i];
   const double nrm = host_scale * (norm3 ? 1.0 / norm3[2] : 1.0);
-  grad[i] = (float)((double)acc * (double)sc * nrm);
+  grad[i] = (float)((double)((acc[0] + acc[1]) + (acc[2] + acc[3])) * (double)sc * nrm);
+}
+
+// LayerNorm-affine unfolding for every consumer (layer 0 / layer 1 / head) in one launch: one warp per input column k.
+//   G = d/dW', gb = d/db' (in the W / b slots of grad):  dgamma[k] = sum_n W[n][k] G[n][k],  dbeta[k] = sum_n W[n][k] gb[n],
+//   dW[n][k] = gamma[k] G[n][k] + beta[k] gb[n],  db = gb      (optim.cu featnorm_grad_fold_kernel, warp-parallel over n)
+struct Folds { int n; int w[3], b[3], gw[3], gb[3], N[3], K[3], col0[3]; };
+__global__ void __launch_bounds__(128) fused_unfold_kernel(const float* __restrict__ params, float* __restrict__ grad, Folds F, int cols) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= cols) return;
+  int f = 0;
+  for (int q = 1; q < F.n; ++q) if (warp >= F.col0[q]) f = q;
+  const int k = warp - F.col0[f], N = F.N[f], K = F.K[f];
+  const float gam = params[F.gw[f] + k], bet = params[F.gb[f] + k];
+  double dg = 0.0, dbt = 0.0;
+  for (int n = lane; n < N; n += 32) {
+    const float w = params[F.w[f] + n * K + k];
+    const float G = grad[F.w[f] + n * K + k];
+    const float gb = grad[F.b[f] + n];
+    dg += (double)w * (double)G;
+    dbt += (double)w * (double)gb;
+    grad[F.w[f] + n * K + k] = fmaf(gam, G, bet * gb);
+  }
+  dg = warp_sum_d(dg);
+  dbt = warp_sum_d(dbt);
+  if (lane == 0) { grad[F.gw[f] + k] = (float)dg; grad[F.gb[f] + k] = (float)dbt; }
 }
 
 static std::atomic<int> g_enabled{-1};
@@ -960,17 +1042,24 @@ int launch_fused_pack(const hb_net_desc* d, const ParamLayout& P, const PrepLayo
                       cudaStream_t st) {
   const int H = d->hidden[0];
   float* sc = prepared + Q.fz_scale;
-  fz::fused_pack_kernel<<<8, 256, 0, st>>>(params + P.w[0], params + P.fn_w, params + P.fn_b, params + P.b[0], H, d->in_dim, H,
-                                           Q.fz_k0p, 32, 0, reinterpret_cast<__half*>(prepared + Q.fz_w[0]), prepared + Q.fz_bias[0], sc + 0);
-  HB_LAUNCH_DONE(st, "fused_pack");
-  fz::fused_pack_kernel<<<16, 256, 0, st>>>(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32, 0,
-                                            reinterpret_cast<__half*>(prepared + Q.fz_w[1]), prepared + Q.fz_bias[1], sc + 1);
-  HB_LAUNCH_DONE(st, "fused_pack");
-  fz::fused_pack_kernel<<<16, 256, 0, st>>>(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32, 32,
-                                            reinterpret_cast<__half*>(prepared + Q.fz_w1b), nullptr, nullptr);
-  HB_LAUNCH_DONE(st, "fused_pack");
-  fz::fused_pack_kernel<<<4, 256, 0, st>>>(params + P.hw, params + P.lnw[1], params + P.lnb[1], params + P.hbias, d->out_dim, H,
-                                           fz::NH, H, H, 0, reinterpret_cast<__half*>(prepared + Q.fz_hw), prepared + Q.fz_hbias, sc + 2);
+  fz::PackJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  int cta = 0;
+  auto add = [&](const float* W, const float* g, const float* be, const float* b, int N, int K, int Nimg, int Kp, int KC, int RC,
+                 float* img, float* bias_out, float* scale_out, int ctas) {
+    fz::PackJob& J = jobs.j[jobs.n++];
+    J.W = W; J.gamma = g; J.beta = be; J.b = b; J.N = N; J.K = K; J.Nimg = Nimg; J.Kp = Kp; J.KC = KC; J.RC = RC;
+    J.img = reinterpret_cast<__half*>(img); J.bias_out = bias_out; J.scale_out = scale_out; J.cta0 = cta; J.ctas = ctas;
+    cta += ctas;
+  };
+  add(params + P.w[0], params + P.fn_w, params + P.fn_b, params + P.b[0], H, d->in_dim, H, Q.fz_k0p, 32, 0, prepared + Q.fz_w[0],
+      prepared + Q.fz_bias[0], sc + 0, 8);
+  add(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32, 0, prepared + Q.fz_w[1],
+      prepared + Q.fz_bias[1], sc + 1, 16);
+  add(params + P.w[1], params + P.lnw[0], params + P.lnb[0], params + P.b[1], H, H, H, H, 32, 32, prepared + Q.fz_w1b, nullptr, nullptr, 16);
+  add(params + P.hw, params + P.lnw[1], params + P.lnb[1], params + P.hbias, d->out_dim, H, fz::NH, H, H, 0, prepared + Q.fz_hw,
+      prepared + Q.fz_hbias, sc + 2, 4);
+  fz::fused_pack_kernel<<<cta, 256, 0, st>>>(jobs);
   HB_LAUNCH_DONE(st, "fused_pack");
   return HB_OK;
 }
@@ -978,7 +1067,7 @@ int launch_fused_pack(const hb_net_desc* d, const ParamLayout& P, const PrepLayo
 size_t fused_smem_bytes(int H, int K0p) {
   size_t b = 2 * (size_t)fz::TILE * K0p * 2 + 2 * 2 * (size_t)fz::TILE * 128 * 2 + 3 * (size_t)fz::TILE * fz::NH * 2 +
              2 * (size_t)fz::NH * H * 2 + (size_t)(K0p <= 32 ? 3 : 2) * fz::STAGE_BYTES;
-  b += 2 * 128 * 4 + fz::NH * 4 + 4 * fz::NH * 4 + 2 * fz::NH * 4 + 16 * 8 + 2 * fz::TILE * 2 * 4 + 10 * 8 + 16;
+  b += 2 * 128 * 4 + fz::NH * 4 + 4 * fz::NH * 4 + 2 * fz::NH * 4 + 16 * 8 + 2 * fz::TILE * 2 * 4 + 10 * 8 + 16 * 8 + 16;
   return b + 1024;
 }
 
@@ -1010,7 +1099,12 @@ int launch_fused_update(const hb_net_desc* d, const PrepLayout& Q, const ParamLa
   a.scales = prepared + Q.fz_scale;
   a.log_std = prepared + Q.log_std; a.std_x = d->std_x_coef; a.std_y = d->std_y_coef;
   a.pw0 = P.w[0]; a.pb0 = P.b[0]; a.pw1 = P.w[1]; a.pb1 = P.b[1]; a.phw = P.hw; a.phb = P.hbias; a.plogstd = P.log_std;
-  a.stage_obs = (a.index == nullptr && (reinterpret_cast<uintptr_t>(a.obs) & 15) == 0) ? 1 : 0;
+  {
+    const void* ptrs[] = {a.obs, a.actions, a.old_logp, a.adv, a.factor, a.active, a.avail, a.value_preds, a.returns};
+    uintptr_t bits = 0;
+    for (const void* q : ptrs) bits |= reinterpret_cast<uintptr_t>(q);
+    a.stage_obs = (a.index == nullptr && (bits & 15) == 0) ? 1 : 0;   // TMA bulk copies need 16-byte aligned sources
+  }
   const long long ntiles = (a.rows + fz::TILE - 1) / fz::TILE;
   const int grid = (int)(ntiles < 148 ? ntiles : 148);
   if (grid_out) *grid_out = grid;
@@ -1041,10 +1135,20 @@ int launch_fused_finish(const hb_net_desc* d, const ParamLayout& P, const float*
   R.n = n;
   fz::fused_slot_reduce_kernel<<<(P.total + 127) / 128, 128, 0, st>>>(grad, part, slots, stride, P.total, R, norm3, host_scale);
   HB_LAUNCH_DONE(st, "fused_slot_reduce");
-  int rc = launch_featnorm_fold_at(params, grad, P.hw, P.hbias, P.lnw[1], P.lnb[1], d->out_dim, H, st);
-  if (rc) return rc;
-  if ((rc = launch_featnorm_fold_at(params, grad, P.w[1], P.b[1], P.lnw[0], P.lnb[0], H, H, st))) return rc;
-  return launch_featnorm_fold_at(params, grad, P.w[0], P.b[0], P.fn_w, P.fn_b, H, d->in_dim, st);
+  fz::Folds F;
+  memset(&F, 0, sizeof(F));
+  int cols = 0;
+  auto fold = [&](int w, int b, int gw, int gb, int N, int K) {
+    const int q = F.n++;
+    F.w[q] = w; F.b[q] = b; F.gw[q] = gw; F.gb[q] = gb; F.N[q] = N; F.K[q] = K; F.col0[q] = cols;
+    cols += K;
+  };
+  fold(P.w[0], P.b[0], P.fn_w, P.fn_b, H, d->in_dim);
+  fold(P.w[1], P.b[1], P.lnw[0], P.lnb[0], H, H);
+  fold(P.hw, P.hbias, P.lnw[1], P.lnb[1], d->out_dim, H);
+  fz::fused_unfold_kernel<<<(cols * 32 + 127) / 128, 128, 0, st>>>(params, grad, F, cols);
+  HB_LAUNCH_DONE(st, "ln_affine_grad_fold");
+  return HB_OK;
 }
 
 }  // namespace hb

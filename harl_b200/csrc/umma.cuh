@@ -144,15 +144,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits for |x| well inside the fp16 range
-// (callers pre-scale by a power of two); eight values -> two 16-byte image chunks.
+// x = hi + lo with hi = x truncated to 11 significant bits (exactly representable in fp16 inside its range) and
+// lo = fp16(x - hi): |lo| <= 2^-10 |x|, so x = hi + lo up to 2^-21 |x| (callers pre-scale by a power of two into the fp16
+// range).  Truncating with an integer mask instead of rounding means hi needs no conversion back to fp32 for the
+// residual -- the fp16 <-> fp32 conversions run on the XU pipe at a fraction of the FP32 rate and were the busiest pipe
+// of the epilogues (profiles/ncu_fused_r02_summary.txt).  Eight values -> two 16-byte image chunks.
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-    const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    const float h0 = __uint_as_float(__float_as_uint(x[2 * i]) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x[2 * i + 1]) & 0xFFFFE000u);
+    const __half2 hh = __floats2half2_rn(h0, h1);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - h0, x[2 * i + 1] - h1);
     h[i] = *reinterpret_cast<const uint32_t*>(&hh);
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }

@@ -190,7 +190,9 @@ def test_evaluate_and_factor_update_fused_equals_layerwise(head, out):
 
     (lf, ff), (ll, fl) = _both(run)
     np.testing.assert_allclose(lf.cpu().numpy(), ll.cpu().numpy(), rtol=2e-5, atol=3e-5)   # Box log-probs reach -70: relative
-    np.testing.assert_allclose(ff.cpu().numpy(), fl.cpu().numpy(), rtol=5e-5, atol=0)
+    # a Gaussian log-prob magnifies an error d of the mean by |action - mean| / var (~10 here): the factor exp(logp - ref)
+    # of the two GEMM arithmetics (fp16 hi/lo split vs 3xTF32) agrees to that many more ulps
+    np.testing.assert_allclose(ff.cpu().numpy(), fl.cpu().numpy(), rtol=5e-4 if head == "Box" else 5e-5, atol=0)
 
 
 def test_fused_kernel_is_what_runs_by_default():
