@@ -243,6 +243,17 @@ static int policy_act_impl(const hb_net_desc* d, const float* prepared, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ch = chunk_of(d, rows);
   if (rows == 0) return HB_OK;
+  if (!d->rnn_layers && fused_enabled()) {   // the same tensor-core kernel as hb_rollout_collect (one net)
+    fz::ActArgs F;
+    memset(&F, 0, sizeof(F));
+    bool ok = false;
+    if ((rc = fused_act_fill(&F.net[0], d, prepared, obs, avail, actions, logp, seed, rows, &ok))) return rc;
+    if (ok) {
+      F.n_nets = 1; F.H = d->hidden[0]; F.act = d->activation; F.deterministic = deterministic;
+      F.offset = offset; F.offset_base = reinterpret_cast<const unsigned long long*>(offset_base);
+      return launch_fused_act(F, st);
+    }
+  }
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;
   const int ad = d->head == HB_HEAD_DISCRETE ? 1 : d->out_dim;
@@ -278,6 +289,16 @@ static int value_forward_impl(const hb_net_desc* d, const float* prepared, const
   HB_CHECK_ARG(!d->rnn_layers || (h_in && masks && h_out), "recurrent critic: rnn_states, masks and rnn_states_out are required");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return HB_OK;
+  if (!d->rnn_layers && fused_enabled()) {
+    fz::ActArgs F;
+    memset(&F, 0, sizeof(F));
+    bool ok = false;
+    if ((rc = fused_act_fill(&F.net[0], d, prepared, cent_obs, nullptr, values, nullptr, 0ull, rows, &ok))) return rc;
+    if (ok) {
+      F.n_nets = 1; F.H = d->hidden[0]; F.act = d->activation;
+      return launch_fused_act(F, st);
+    }
+  }
   const int64_t ch = chunk_of(d, rows);
   Work w;
   if ((rc = carve(Q, ch, 0, ws, ws_bytes, &w))) return rc;

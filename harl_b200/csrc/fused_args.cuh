@@ -30,9 +30,35 @@ struct Args {
   float* logp_out; const float* logp_ref; float* factor_inout;
 };
 
+// ---- rollout inference (fused_act_kernel): every actor and the critic of one rollout step in ONE launch
+constexpr int ACT_MAX_NETS = 24;
+struct ActNet {
+  const float* prep; const float* obs; const float* avail;
+  float* out0;                 // actions [rows, ad] | values [rows]
+  float* out1;                 // log-probs [rows, ad] | unused
+  unsigned long long seed;
+  long long rows;
+  int in_dim, out, head, K0p, nch0;
+  int o_w0, o_w1, o_hw, o_b0, o_b1, o_bh, o_sc, o_ls;   // float offsets into prep (PrepLayout fz_* / log_std)
+  float std_x, std_y;
+  int tile0, stage;            // first CTA of this net; 1 = full tiles' inputs arrive by TMA bulk copy
+};
+struct ActArgs {
+  int n_nets, H, act, deterministic, K0p_max, pad_;
+  unsigned long long offset;
+  const unsigned long long* offset_base;
+  ActNet net[ACT_MAX_NETS];
+};
+
 }  // namespace fz
 
 bool fused_enabled();
+// all nets of one rollout step (hb_rollout_collect) / a single net (hb_policy_act, hb_value_forward) on the fused path;
+// *handled = false: some net is outside the fused kernel's shapes -> caller falls back to the FP32 kernels
+struct hb_collect_args;
+int launch_fused_act(fz::ActArgs& A, cudaStream_t st);
+int fused_act_fill(fz::ActNet* n, const hb_net_desc* d, const float* prepared, const float* obs, const float* avail, float* out0,
+                   float* out1, unsigned long long seed, long long rows, bool* ok);
 void set_fused_enabled(int on);
 inline int fused_max_slots() { return 148; }   // persistent grid: one CTA (one split-buffer slot) per SM
 // mode 0 = forward + loss + backward into the split buffer, 1 = evaluate (log-probs / values, factor update)

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "head_rows.cuh"
+#include "fused_args.cuh"
 #include "kernels.cuh"
 
 namespace hb {
@@ -365,6 +366,26 @@ extern "C" int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_
       return hb_value_forward_rnn(a->critic_desc, a->critic_prepared, a->share_obs, a->critic_rows, a->critic_rnn,
                                   a->critic_masks, a->values, a->critic_rnn_out, ws, ws_bytes, stream);
     return HB_OK;
+  }
+  // tensor-core path: every net inside the fused kernel's shapes, one trunk width / activation for all of them
+  if (fused_enabled() && a->n_agents + (a->critic_desc ? 1 : 0) <= fz::ACT_MAX_NETS) {
+    static thread_local fz::ActArgs F;
+    F.n_nets = a->n_agents + (a->critic_desc ? 1 : 0);
+    F.H = d0->hidden[0]; F.act = d0->activation; F.deterministic = a->deterministic;
+    F.offset = a->offset; F.offset_base = reinterpret_cast<const unsigned long long*>(a->offset_base);
+    bool all = true;
+    for (int i = 0; all && i < F.n_nets; ++i) {
+      const bool critic = i == a->n_agents;
+      const hb_net_desc* d = critic ? a->critic_desc : a->actor_desc[i];
+      bool ok = false;
+      int rc = fused_act_fill(&F.net[i], d, critic ? a->critic_prepared : a->actor_prepared[i], critic ? a->share_obs : a->obs[i],
+                              critic ? nullptr : a->avail[i], critic ? a->values : a->actions[i], critic ? nullptr : a->logp[i],
+                              critic ? 0ull : a->seed[i], critic ? a->critic_rows : a->rows, &ok);
+      if (rc) return rc;
+      all = ok && d->hidden[0] == F.H && d->activation == F.act;
+      HB_CHECK_ARG(F.net[i].prep && F.net[i].obs && F.net[i].out0 && (critic || F.net[i].out1), "NULL buffer");
+    }
+    if (all) return launch_fused_act(F, st);
   }
   A.n_nets = a->n_agents + (a->critic_desc ? 1 : 0);
   A.n_layers = d0->n_layers;

@@ -876,6 +876,247 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+
+// ================================================================================================ rollout inference
+// One launch per rollout step for every actor and the critic (OnPolicyBaseRunner.collect, on_policy_base_runner.py:285-340):
+// CTA = one 128-row tile of one net; the same tcgen05 forward as the update kernel (feature norm -> 2 x [MMA, act + LayerNorm
+// epilogue] -> head MMA) followed by the sampling head (Philox4x32-10 keyed exactly like the FP32 kernels it replaces:
+// fused_infer.cu / rowwise.cu) or the value head.  Replaces the FP32 FFMA fused_infer_kernel for the shapes the fused kernel covers.
+constexpr uint32_t ACT_TMEM_COLS = 256;
+
+template <int ACT>
+__global__ void __launch_bounds__(THREADS, 1) fused_act_kernel(const __grid_constant__ ActArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int ni = 0;
+  for (int q = 1; q < A.n_nets; ++q) if ((int)blockIdx.x >= A.net[q].tile0) ni = q;
+  const ActNet& N = A.net[ni];
+  const long long t = (long long)blockIdx.x - N.tile0;
+  const int H = A.H, K0p = N.K0p;
+  const int wch0 = K0p >> 3, wchx = 16, wchh = H >> 3;
+  const uint32_t x0_bytes = TILE * A.K0p_max * 2, x_bytes = TILE * 128 * 2, wh_bytes = NH * H * 2;
+  unsigned char* p = smem;
+  unsigned char* X0 = p; p += 2 * x0_bytes;
+  unsigned char* X1 = p; p += 2 * x_bytes;
+  unsigned char* X2 = p; p += 2 * x_bytes;
+  unsigned char* WH = p; p += 2 * wh_bytes;
+  unsigned char* ring = p; p += 2 * STAGE_BYTES;
+  float* sb0 = reinterpret_cast<float*>(p); p += 128 * 4;
+  float* sb1 = reinterpret_cast<float*>(p); p += 128 * 4;
+  float* sbh = reinterpret_cast<float*>(p); p += NH * 4;
+  float* xch = reinterpret_cast<float*>(p); p += 2 * TILE * 2 * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p); p += 8 * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p);
+  uint64_t* w_full = bars;        // [2]
+  uint64_t* w_empty = bars + 2;   // [2]
+  uint64_t* e2m = bars + 4;
+  uint64_t* m2e = bars + 5;
+  uint64_t* obs_full = bars + 6;
+  unsigned char* OBS = X2;        // staging image: idle until the layer-1 epilogue
+  constexpr int STG = 2;
+  const __half* img0 = reinterpret_cast<const __half*>(N.prep + N.o_w0);
+  const __half* img1 = reinterpret_cast<const __half*>(N.prep + N.o_w1);
+  const int nch1 = H >> 5;
+  const bool full = (t + 1) * TILE <= N.rows;
+  const bool st_obs = N.stage && full;
+  const uint32_t obs_bytes = (uint32_t)TILE * (uint32_t)N.in_dim * 4u;
+  const uint32_t o_av = (N.head == HB_HEAD_DISCRETE && N.avail != nullptr) ? obs_bytes : 0u;
+  const uint32_t stage_bytes = obs_bytes + (o_av ? (uint32_t)TILE * N.out * 4u : 0u);
+
+  if (H < 128) {
+    for (int i = tid; i < (int)((2 * x_bytes) / 16); i += THREADS) {
+      reinterpret_cast<uint4*>(X1)[i] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(X2)[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int i = tid; i < (int)((2 * wh_bytes) / 16); i += THREADS)
+    reinterpret_cast<uint4*>(WH)[i] = reinterpret_cast<const uint4*>(N.prep + N.o_hw)[i];
+  for (int i = tid; i < 128; i += THREADS) { sb0[i] = i < H ? N.prep[N.o_b0 + i] : 0.f; sb1[i] = i < H ? N.prep[N.o_b1 + i] : 0.f; }
+  if (tid < NH) sbh[tid] = N.prep[N.o_bh + tid];
+  if (tid == 0) {
+    for (int i = 0; i < STG; ++i) { um::mbar_init(&w_full[i], 1); um::mbar_init(&w_empty[i], 1); }
+    um::mbar_init(e2m, 8);
+    um::mbar_init(m2e, 1);
+    um::mbar_init(obs_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um::smem_u32(tmem_slot)), "r"(ACT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  um::fence_async_smem();
+  um::tc_fence_before();
+  __syncthreads();
+  um::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float ws0 = N.prep[N.o_sc], ws1 = N.prep[N.o_sc + 1], wsh = N.prep[N.o_sc + 2];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (st_obs) {
+        um::mbar_expect_tx(obs_full, stage_bytes);
+        um::tma_bulk_g2s(OBS, N.obs + t * TILE * N.in_dim, obs_bytes, obs_full);
+        if (o_av) um::tma_bulk_g2s(OBS + o_av, N.avail + t * TILE * N.out, TILE * N.out * 4, obs_full);
+      }
+      uint32_t it = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int nch = pass == 0 ? N.nch0 : nch1, kp = pass == 0 ? K0p : H;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(pass == 0 ? img0 : img1);
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int kc = kp - 32 * c < 32 ? kp - 32 * c : 32;
+          const uint32_t bytes = 2u * (uint32_t)H * (uint32_t)kc * 2u;
+          const uint32_t st = it % STG, use = it / STG;
+          if (use > 0) um::mbar_wait(&w_empty[st], (use - 1) & 1);
+          um::mbar_expect_tx(&w_full[st], bytes);
+          um::tma_bulk_g2s(ring + st * STAGE_BYTES, src + (size_t)c * (2u * H * 32u * 2u), bytes, &w_full[st]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, pe = 0;
+      const uint32_t X0a = um::smem_u32(X0), X1a = um::smem_u32(X1), X2a = um::smem_u32(X2), WHa = um::smem_u32(WH), RGa = um::smem_u32(ring);
+      auto wait_e = [&]() { um::mbar_wait(e2m, pe); pe ^= 1; um::tc_fence_after(); };
+      auto chunk = [&](int kc, auto&& body) {
+        const uint32_t st = it % STG, use = it / STG;
+        um::mbar_wait(&w_full[st], use & 1);
+        um::tc_fence_after();
+        body(RGa + st * STAGE_BYTES, (uint32_t)H * (uint32_t)kc * 2u);
+        um::commit(&w_empty[st]);
+        ++it;
+      };
+      wait_e();
+      for (int c = 0; c < N.nch0; ++c) {
+        const int kc = K0p - 32 * c < 32 ? K0p - 32 * c : 32;
+        chunk(kc, [&](uint32_t wb, uint32_t wimg) {
+          gemm3(tmem + C_F, op_kmajor(X0a, x0_bytes, wch0, 4 * c), op_kmajor(wb, wimg, kc >> 3, 0), kc >> 4, um::idesc_f16(H, 0, 0), c > 0);
+        });
+      }
+      um::commit(m2e);
+      wait_e();
+      for (int c = 0; c < nch1; ++c)
+        chunk(32, [&](uint32_t wb, uint32_t wimg) {
+          gemm3(tmem + C_F, op_kmajor(X1a, x_bytes, wchx, 4 * c), op_kmajor(wb, wimg, 4, 0), 2, um::idesc_f16(H, 0, 0), c > 0);
+        });
+      um::commit(m2e);
+      wait_e();
+      gemm3(tmem + 128, op_kmajor(X2a, x_bytes, wchx, 0), op_kmajor(WHa, wh_bytes, wchh, 0), H >> 4, um::idesc_f16(NH, 0, 0), false);
+      um::commit(m2e);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const RowPair RP{xch, half, r, 2 + q};
+    uint32_t pm = 0;
+    auto wait_m = [&]() { um::mbar_wait(m2e, pm); pm ^= 1; um::tc_fence_after(); };
+    auto signal = [&]() { um::fence_async_smem(); um::tc_fence_before(); __syncwarp(); if (lane == 0) um::mbar_arrive(e2m); };
+    const long long row = t * TILE + r;
+    const bool ok = row < N.rows;
+    const bool ld = ok && half == 0;
+    const int na = N.out;
+    if (st_obs && half == 0) um::mbar_wait(obs_full, 0);
+    const float* stg = reinterpret_cast<const float*>(OBS);
+    unsigned avm = 0xffffu;
+    if (N.head == HB_HEAD_DISCRETE && N.avail != nullptr && ld) {
+      const float* av = st_obs ? stg + (o_av >> 2) + r * na : N.avail + row * na;
+      avm = 0u;
+#pragma unroll
+      for (int j = 0; j < NH; ++j) avm |= (j < na && av[j < na ? j : 0] != 0.f) ? (1u << j) : 0u;
+    }
+    const float* o = st_obs ? stg + r * N.in_dim : N.obs + (ok ? row : 0) * N.in_dim;
+    float mean = 0.f, rs = 0.f;
+    if (half == 0) {
+      float s = 0.f;
+      for (int k0 = 0; k0 < N.in_dim; k0 += 16) {
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = (ld && k0 + j < N.in_dim) ? o[k0 + j] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += x[j];
+      }
+      mean = s / (float)N.in_dim;
+      float qv = 0.f;
+      for (int k0 = 0; k0 < N.in_dim; k0 += 16) {
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = (ld && k0 + j < N.in_dim) ? o[k0 + j] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float d = x[j] - mean; qv = k0 + j < N.in_dim ? fmaf(d, d, qv) : qv; }
+      }
+      rs = rsqrtf(qv / (float)N.in_dim + 1e-5f);
+      const float rsx = rs * XS;
+      for (int k0 = 0; k0 < K0p; k0 += 16) {
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = (ld && k0 + j < N.in_dim) ? (o[k0 + j] - mean) * rsx : 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float xc[8] = {x[c * 8], x[c * 8 + 1], x[c * 8 + 2], x[c * 8 + 3], x[c * 8 + 4], x[c * 8 + 5], x[c * 8 + 6], x[c * 8 + 7]};
+          uint4 hi, lo;
+          um::split8(xc, hi, lo);
+          const uint32_t off = img_off(r, (k0 >> 3) + c, wch0);
+          *reinterpret_cast<uint4*>(X0 + off) = hi;
+          *reinterpret_cast<uint4*>(X0 + x0_bytes + off) = lo;
+        }
+      }
+    }
+    signal();
+    float mu0, rstd0, mu1, rstd1;
+    uint32_t mask0[2], mask1[2];
+    wait_m();
+    fwd_epilogue<ACT>(A.act, tl + C_F, H, sb0, 1.f / (XS * ws0), X1, x_bytes, wchx, RP, mu0, rstd0, mask0);
+    signal();
+    wait_m();
+    fwd_epilogue<ACT>(A.act, tl + C_F, H, sb1, 1.f / (XS * ws1), X2, x_bytes, wchx, RP, mu1, rstd1, mask1);
+    signal();
+    wait_m();
+    if (half == 0) {
+      float hv[NH];
+      um::tmem_ld16(tl + 128, hv);
+      const float hdesc = 1.f / (XS * wsh);
+      const unsigned long long off = A.offset + (A.offset_base ? *A.offset_base : 0ull);
+      if (N.head == HB_HEAD_VALUE) {
+        if (ok) N.out0[row] = fmaf(hv[0], hdesc, sbh[0]);
+      } else if (N.head == HB_HEAD_DISCRETE) {
+        float lg[NH], lp[NH], pj[NH];
+#pragma unroll
+        for (int j = 0; j < NH; ++j) lg[j] = hv[j] * hdesc;
+        rows::categorical<NH>(lg, sbh, na, avm, lp, pj);
+        const int pick = rows::categorical_pick<NH>(pj, na, A.deterministic != 0, A.deterministic ? 0.f : rows::row_uniform(row, N.seed, off));
+        const float lpp = rows::select<NH>(lp, pick);
+        if (ok) { N.out0[row] = (float)pick; N.out1[row] = lpp; }
+      } else {
+        const float* log_std = N.prep + N.o_ls;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < na) {
+            const float mean_j = fmaf(hv[j], hdesc, sbh[j]);
+            const float sig = 1.f / (1.f + expf(-log_std[j] / N.std_x));
+            const float sd = sig * N.std_y, lsd = logf(sd);
+            float act = mean_j;
+            if (!A.deterministic) {
+              const uint4 rnd = philox4x32(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32), (uint32_t)j, (uint32_t)off),
+                                           make_uint2((uint32_t)N.seed, (uint32_t)(N.seed >> 32) ^ (uint32_t)(off >> 32)));
+              const float u1 = u01(rnd.x), u2 = u01(rnd.y);
+              act = mean_j + sd * (sqrtf(-2.f * logf(u1)) * cospif(2.f * u2));
+            }
+            if (ok) {
+              const float dv = act - mean_j;
+              N.out0[row * na + j] = act;
+              N.out1[row * na + j] = -(dv * dv) / (2.f * sd * sd) - lsd - 0.5f * HB_LOG_2PI_F;
+            }
+          }
+        }
+      }
+    }
+  }
+  um::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ACT_TMEM_COLS) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ weight images
 // One launch per weight matrix: W'[n][k] = W[n][k] * gamma[k], scaled by a power of two so that max |W'| lands in
 // [128, 256), split into fp16 hi / lo, written as KC-wide k-chunks of K-major core matrices; folded bias b' = b + W beta.
@@ -1061,6 +1302,49 @@ int launch_fused_pack(const hb_net_desc* d, const ParamLayout& P, const PrepLayo
       prepared + Q.fz_hbias, sc + 2, 4);
   fz::fused_pack_kernel<<<cta, 256, 0, st>>>(jobs);
   HB_LAUNCH_DONE(st, "fused_pack");
+  return HB_OK;
+}
+
+
+int fused_act_fill(fz::ActNet* n, const hb_net_desc* d, const float* prepared, const float* obs, const float* avail, float* out0,
+                   float* out1, unsigned long long seed, long long rows, bool* ok) {
+  PrepLayout Q;
+  int rc = make_layouts(d, nullptr, &Q, nullptr);
+  if (rc) return rc;
+  *ok = Q.fz_ok != 0 && (d->head != HB_HEAD_BOX || d->out_dim <= 8);
+  if (!*ok) return HB_OK;
+  n->prep = prepared; n->obs = obs; n->avail = avail; n->out0 = out0; n->out1 = out1; n->seed = seed; n->rows = rows;
+  n->in_dim = d->in_dim; n->out = d->out_dim; n->head = d->head; n->K0p = Q.fz_k0p; n->nch0 = Q.fz_chunks[0];
+  n->o_w0 = Q.fz_w[0]; n->o_w1 = Q.fz_w[1]; n->o_hw = Q.fz_hw; n->o_b0 = Q.fz_bias[0]; n->o_b1 = Q.fz_bias[1]; n->o_bh = Q.fz_hbias;
+  n->o_sc = Q.fz_scale; n->o_ls = Q.log_std; n->std_x = d->std_x_coef; n->std_y = d->std_y_coef;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(avail);
+  n->stage = (bits & 15) == 0 ? 1 : 0;
+  return HB_OK;
+}
+
+// A.n_nets, A.H, A.act, A.deterministic, A.offset(_base) and every net (fused_act_fill) set by the caller
+int launch_fused_act(fz::ActArgs& A, cudaStream_t st) {
+  int tiles = 0, k0 = 16;
+  for (int i = 0; i < A.n_nets; ++i) {
+    A.net[i].tile0 = tiles;
+    tiles += (int)((A.net[i].rows + fz::TILE - 1) / fz::TILE);
+    k0 = A.net[i].K0p > k0 ? A.net[i].K0p : k0;
+  }
+  A.K0p_max = k0;
+  if (tiles == 0) return HB_OK;
+  const size_t smem = 2 * (size_t)fz::TILE * k0 * 2 + 2 * 2 * (size_t)fz::TILE * 128 * 2 + 2 * (size_t)fz::NH * A.H * 2 + 2 * fz::STAGE_BYTES +
+                      2 * 128 * 4 + fz::NH * 4 + 2 * fz::TILE * 2 * 4 + 8 * 8 + 16 + 1024;
+#define HB_FZA(ACTV)                                                                                  \
+  {                                                                                                   \
+    auto kern = fz::fused_act_kernel<ACTV>;                                                           \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    kern<<<tiles, fz::THREADS, smem, st>>>(A);                                                        \
+  }
+  if (A.act == HB_ACT_RELU) HB_FZA(HB_ACT_RELU)
+  else if (A.act == HB_ACT_TANH) HB_FZA(HB_ACT_TANH)
+  else HB_FZA(-1)
+#undef HB_FZA
+  HB_LAUNCH_DONE(st, "fused_act");
   return HB_OK;
 }
 
