@@ -46,9 +46,12 @@ WORKLOADS = {
     "C5": dict(desc="HAPPO MAMuJoCo Humanoid-v2 17x1 n_rollout_threads=1024 per GPU T=200",
                env="mamujoco", env_args=dict(scenario="Humanoid-v2", agent_conf="17x1"), n=1024, T=200,
                hidden=[128, 128, 128], algo=dict(clip_param=0.1, entropy_coef=0.0)),
-    # the two halves of BASELINE.json's C4 (HATRPO + GRU is the one combination not built): the trust-region update at
-    # C2 shapes, and GRU policies / FP critic at the synthetic-SMAC shapes.  Secondary workloads (--workload), run with
-    # --no-cpu-baseline --no-e2e.
+    # C1 on the learnable task itself: the batched CUDA simple_spread env (harl_b200/envs/mpe_spread.py), tuned N = 20
+    "C1M": dict(desc="HAPPO pettingzoo_mpe simple_spread_v2 3 agents n_rollout_threads=20, native batched env (tuned config)",
+                env="pettingzoo_mpe", env_args=dict(scenario="simple_spread_v2", continuous_actions=False, backend="native"), n=20,
+                T=200, hidden=[128, 128], algo={}),
+    # BASELINE.json's C4 and its two halves: the trust-region update at C2 shapes (C2T), GRU policies / FP critic at the
+    # synthetic-SMAC shapes under HAPPO (C4R).  Secondary workloads (--workload), run with --no-cpu-baseline --no-e2e.
     "C2T": dict(desc="HATRPO synthetic-MPE obs_dim=18 act_dim=5 3 agents n_rollout_threads=4096 T=200",
                 env="pettingzoo_mpe", env_args=dict(scenario="simple_spread_v2", continuous_actions=False), n=4096, T=200,
                 hidden=[128, 128], algo={}, algo_name="hatrpo"),
@@ -62,6 +65,9 @@ WORKLOADS = {
 }
 
 
+STRONG = False   # --scaling strong: the workload's n_rollout_threads is the GLOBAL count
+
+
 def make_args(wl, world, host_env=False, n_override=None):
     from harl_b200.utils.configs_tools import get_defaults_yaml_args
 
@@ -70,7 +76,7 @@ def make_args(wl, world, host_env=False, n_override=None):
     env_args.update(w["env_args"])
     env_args["host"] = host_env
     n = n_override or w["n"]
-    algo_args["train"].update(n_rollout_threads=n * world, episode_length=w["T"], num_env_steps=10**12,
+    algo_args["train"].update(n_rollout_threads=n * (1 if STRONG else world), episode_length=w["T"], num_env_steps=10**12,
                               log_interval=10**9, eval_interval=10**9)
     algo_args["eval"]["use_eval"] = False
     algo_args["model"]["hidden_sizes"] = list(w["hidden"])
@@ -185,6 +191,25 @@ def kernel_profile(runner, torch):
 
 
 GEMM_LABEL = re.compile(r"^(tc_)?(linear_ln_fwd|dx_ln_bwd|dw_accum)")
+FUSED_LABEL = re.compile(r"^fused_(actor_update|critic_update|evaluate)")
+NET_SHAPES = {}   # filled from the runner: od, sd, na (Discrete) / ad (Box), hidden, avail
+
+
+def _fused_work(label):
+    """Algorithmic (bytes, FLOPs) per launch of a fused kernel, SURVEY.md section 8(d): every input element of a row is
+    moved once (weights excluded); FLOPs = 2 * in * out per Linear, x3 for forward + backward."""
+    m = re.match(r"(\w+)\[M(\d+),N(\d+),K(\d+)\]", label)
+    name, M, H, K = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4))
+    sh = NET_SHAPES
+    out = 1 if name == "fused_critic_update" else sh.get("out", 5)
+    fwd = 2.0 * (K * H + H * H + H * out)
+    if name == "fused_critic_update":
+        return M * 4.0 * (K + 2), M * 3.0 * fwd
+    aw = 1 if sh.get("discrete", True) else sh.get("out", 1)          # stored action / log-prob width
+    avail = 4.0 * sh.get("out", 5) if (sh.get("discrete", True) and sh.get("avail", True)) else 0.0
+    if name == "fused_actor_update":
+        return M * (4.0 * K + 4.0 * aw + 4.0 * aw + 12.0 + avail), M * 3.0 * fwd
+    return M * (4.0 * K + 4.0 * aw + avail + 4.0 * aw), M * fwd        # evaluate: + the log-probs written
 
 
 def _algorithmic(label):
@@ -193,6 +218,9 @@ def _algorithmic(label):
     if not m:
         return None, None
     name, M, N, K = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4))
+    if FUSED_LABEL.match(name):
+        nbytes, flops = _fused_work(label)
+        return "gemm", (flops, nbytes)
     if GEMM_LABEL.match(name):
         # algorithmic FLOPs: one fp32-accurate product (3xTF32 issues 3 MMAs for it); algorithmic bytes: every operand /
         # result row moved once -- forward reads X[M,K], writes Z and Y [M,N]; dX reads dZ[M,K'] and Z[M,N], writes dZ'[M,N];
@@ -246,12 +274,13 @@ def roofline_of(rows, peaks):
     label, cnt, ms = rows[0]
     out = {"kernel": label, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share_of_update_phase": ms / total,
            "scope": "update phase (runner.train) of one iteration; phases in config.phases_ms",
-           "gemm_impl": {0: "fp32 SIMT", 1: "tcgen05 3xTF32", 2: "tcgen05 TF32"}[L.lib.hb_get_gemm_impl()],
+           "gemm_impl": ("fused tcgen05 kernel (fp16 hi/lo split, fp32 accumulate); layer-wise fallback: " if L.lib.hb_get_fused_update() else "") +
+                        {0: "fp32 SIMT", 1: "tcgen05 3xTF32", 2: "tcgen05 TF32"}[L.lib.hb_get_gemm_impl()],
            "peak_source": peaks["_source"],
            "top5": [{"kernel": r[0], "launches": r[1], "avg_us": round(1e3 * r[2] / r[1], 2), "share": round(r[2] / total, 4)}
                     for r in rows[:5]]}
     out.update(_rate(rows[0], peaks))
-    gem = [r for r in rows if GEMM_LABEL.match(r[0])]
+    gem = [r for r in rows if GEMM_LABEL.match(r[0]) or FUSED_LABEL.match(r[0])]
     if gem:
         g = dict(kernel=gem[0][0], launches=gem[0][1], avg_us=1e3 * gem[0][2] / gem[0][1], share=gem[0][2] / total)
         g.update(_rate(gem[0], peaks))
@@ -362,8 +391,11 @@ def _ref_spec(wl, n, steps, warmup, cuda, threads, budget_s):
         # NumPy >= 1.24); the MPE logger is the plain base logger
         args = dict(args, env="pettingzoo_mpe")
         env_args.update(scenario="simple_spread_v2", continuous_actions=False)
-    return dict(args=args, algo_args=algo_args, env_args=env_args, shapes=shapes, n_rollout_threads=n, steps=steps,
+    spec = dict(args=args, algo_args=algo_args, env_args=env_args, shapes=shapes, n_rollout_threads=n, steps=steps,
                 warmup=warmup, cuda=bool(cuda), torch_threads=threads, budget_s=budget_s)
+    if env_args.pop("backend", None) == "native":   # the learnable task: the reference runs on the NumPy twin of the CUDA env
+        spec["env_kind"] = "mpe_spread"
+    return spec
 
 
 def _ref_subprocess(spec, timeout_s):
@@ -451,6 +483,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=256, help="n_rollout_threads of the bounded CPU sample")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU keeps the workload's n_rollout_threads; strong: they are divided over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-n", type=int, default=0, help="--impl reference: n_rollout_threads (default: the workload's own)")
     ap.add_argument("--ref-cuda", action="store_true", help="--impl reference: device.cuda=True (the reference on the B200)")
@@ -468,11 +502,14 @@ def main():
     sys.stdout = sys.stderr
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    global STRONG
+    STRONG = a.scaling == "strong"
     wl = WORKLOADS[a.workload]
     T = wl["T"]
     base = dict(metric="env-steps/sec (whole box) HAPPO update loop", unit="env-steps/s", n_gpus=a.gpus, steps=a.steps,
-                warmup=a.warmup, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config={"workload": f"{a.workload}: {wl['desc']}", "n_rollout_threads_per_gpu": wl["n"],
+                warmup=a.warmup, higher_is_better=True, scaling=a.scaling, vs_baseline=None, dtype="f32", data="synthetic",
+                config={"workload": f"{a.workload}: {wl['desc']}",
+                        "n_rollout_threads_per_gpu": wl["n"] // (world if a.scaling == "strong" else 1),
                         "episode_length": T, "algo": wl.get("algo_name", "happo"),
                         "l2_policy": "rollout buffers + activations per iteration exceed the 126 MB L2 (no flush needed)"})
 
@@ -511,8 +548,11 @@ def main():
     runner = RUNNER_REGISTRY[args["algo"]](args, algo_args, env_args)
     runner.warmup()
     runner.logger.init(10**9)
+    sp = runner.envs.action_space[0]
+    NET_SHAPES.update(out=(sp.n if sp.__class__.__name__ == "Discrete" else sp.shape[0]), discrete=sp.__class__.__name__ == "Discrete",
+                      avail=runner.actor_buffer[0].available_actions is not None)
     ms, launches, clocks = timed_iterations(runner, a.steps, a.warmup, torch, dist_on, sample_clocks=(rank == 0))
-    n_global = wl["n"] * world
+    n_global = wl["n"] * (1 if STRONG else world)
     value = T * n_global * a.steps / (ms / 1e3)
     line = dict(base, value=value, ms_per_step=ms / a.steps, gpu_launches=int(launches), clocks=clocks)
     # ---- roofline of the dominant kernel (separate profiled iteration, same stream)
@@ -523,7 +563,7 @@ def main():
         named = {"gae": gae_microbench(torch, T, runner.critic_buffer.value_preds[0].numel(), load_peaks()),
                  # the same kernel where launch + fill latency and the T-step serial recurrence are amortised
                  "gae_16x_columns": gae_microbench(torch, T, 16 * runner.critic_buffer.value_preds[0].numel(), load_peaks(), sets=2, reps=3)}
-        ppo = [r for r in rows if r[0].startswith("policy_head_grad")]
+        ppo = [r for r in rows if r[0].startswith("fused_actor_update")] or [r for r in rows if r[0].startswith("policy_head_grad")]
         if ppo:
             named["ppo_update"] = dict(kernel=ppo[0][0], launches=ppo[0][1], avg_us=1e3 * ppo[0][2] / ppo[0][1], **_rate(ppo[0], load_peaks()))
         line["roofline"]["named_kernels"] = named
@@ -548,7 +588,7 @@ def main():
         r2.logger.init(10**9)
         ms2, _, _ = timed_iterations(r2, max(1, min(a.steps, 3)), 1, torch, dist_on)
         k2 = max(1, min(a.steps, 3))
-        A, N = r2.num_agents, wl["n"]
+        A, N = r2.num_agents, r2.n_local
         od = r2.envs.observation_space[0].shape[0]
         sd = r2.envs.share_observation_space[0].shape[0]
         aw = r2.actor[0].actor.act_width

@@ -127,6 +127,8 @@ SIGNATURES = {
     "hb_policy_act": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, C.c_int, C.c_uint64, C.c_uint64, P, P, P,
                                 C.c_size_t, P]),
     "hb_value_forward": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, C.c_size_t, P]),
+    "hb_set_gae_impl": (C.c_int, [C.c_int]),
+    "hb_get_gae_impl": (C.c_int, []),
     "hb_gae_returns": (C.c_int, [P, P, P, P, P, P, P, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_int, C.c_int,
                                  P, P]),
     "hb_masked_moments": (C.c_int, [P, P, C.c_int64, P, P]),

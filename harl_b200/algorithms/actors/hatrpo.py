@@ -19,6 +19,7 @@ in CUDA over the buffer rows in place (no minibatch is materialised):
 With the rollout sharded over GPUs the gradient, every Fisher-vector product and the line-search sums are
 sum-allreduced, so all ranks take the identical step.
 """
+import numpy as np
 import torch
 
 from ... import _lib as L
@@ -107,7 +108,10 @@ class HATRPO(OnPolicyBase):
             kl = float(s[3] / global_rows)
             ent = float(s[1] / norm)
             ratio = float(s[2] / global_rows)
-            if kl < self.kl_threshold and improve / expected > self.accept_ratio and improve > 0:
+            # NumPy semantics of the reference (hatrpo.py:179-183): a zero expected improvement gives inf / nan, which rejects
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rel = float(np.float64(improve) / np.float64(expected))
+            if kl < self.kl_threshold and rel > self.accept_ratio and improve > 0:
                 flag = True
                 break
             expected *= self.backtrack_coeff

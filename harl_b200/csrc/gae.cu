@@ -21,6 +21,11 @@ bool launch_gae_tma(const float* rewards, float* value_preds, const float* masks
                     const float* next_value, float* returns, float* advantages, int T, int64_t C, float gamma, float gl,
                     int ptl, const float* vn, cudaStream_t st, int* rc);
 
+// gae_seg.cu
+bool launch_gae_seg(const float* rewards, float* value_preds, const float* masks, const float* bad_masks,
+                    const float* next_value, float* returns, float* advantages, int T, int64_t C, float gamma, float gl,
+                    int ptl, const float* vn, cudaStream_t st, int* rc);
+
 struct VNConst { float mean, std; int on; };
 
 __device__ __forceinline__ VNConst vn_load(const float* __restrict__ vn) {
@@ -289,6 +294,12 @@ int hb_gae_returns(const float* rewards, float* value_preds, const float* masks,
   HB_CHECK_ARG(rewards && value_preds && masks && bad_masks && next_value && returns, "NULL buffer");
   HB_CHECK_ARG(T > 0 && C > 0, "T and C must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_gae) {  // register-resident, time-segmented kernel (gae_seg.cu): T <= 256 unless hb_set_gae_impl(0)
+    int rc = HB_OK;
+    if (hb::launch_gae_seg(rewards, value_preds, masks, bad_masks, next_value, returns, advantages, T, C, gamma, gamma_lambda,
+                           use_proper_time_limits, vn_state, st, &rc))
+      return rc;
+  }
   const size_t per_col = (size_t)(4 * (size_t)T + 3) * sizeof(float);
   const size_t budget = 200 * 1024;
   int cw = 0;

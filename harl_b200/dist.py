@@ -6,9 +6,13 @@ advantage / ValueNorm moments), so the replicas stay bit-identical after each op
 """
 import torch
 
+# tests/dist_check_global_batch.py: run a runner with single-process semantics (no sharding, no exchanges) inside an
+# initialised process group, to compare the sharded update with the same update on the whole global batch
+FORCE_SINGLE = False
+
 
 def is_dist():
-    return torch.distributed.is_available() and torch.distributed.is_initialized()
+    return not FORCE_SINGLE and torch.distributed.is_available() and torch.distributed.is_initialized()
 
 
 def world_size():

@@ -41,6 +41,22 @@ class OnPolicyBaseRunner:
         self.fixed_order = algo_args["algo"]["fixed_order"]
         set_seed(algo_args["seed"])
         self.device = init_device(algo_args["device"])
+        if dist.world_size() > 1:
+            # every replica must start from the same weights and draw the same agent orders / permutations: all of them come
+            # from the torch CPU generator, so every rank adopts rank 0's seed (with seed_specify = false each rank would
+            # otherwise draw its own) and re-seeds
+            seed_t = torch.tensor([int(algo_args["seed"]["seed"])], dtype=torch.int64, device=self.device)
+            torch.distributed.broadcast(seed_t, src=0)
+            if int(seed_t.item()) != int(algo_args["seed"]["seed"]):
+                algo_args["seed"]["seed"] = int(seed_t.item())
+                set_seed({**algo_args["seed"], "seed_specify": True})
+        if self.share_param and (algo_args["model"].get("use_recurrent_policy") or algo_args["model"].get("use_naive_recurrent_policy")):
+            # fail before the first rollout, not at the first train() (the reference accepts this combination: README / DESIGN.md)
+            raise NotImplementedError("share_param with recurrent (GRU) policies is not implemented: the reference interleaves the "
+                                      "agents' sequences when it concatenates their minibatches (mappo.py:149-222)")
+        T_, L_ = algo_args["train"]["episode_length"], algo_args["model"].get("data_chunk_length", 1)
+        if algo_args["model"].get("use_recurrent_policy") and T_ % L_ != 0:
+            raise NotImplementedError(f"episode_length ({T_}) must be a multiple of data_chunk_length ({L_}) for recurrent policies")
         if algo_args["render"]["use_render"]:
             raise NotImplementedError("rendering needs the third-party simulators, which are out of scope")
         self.world, self.rank = dist.world_size(), dist.rank()

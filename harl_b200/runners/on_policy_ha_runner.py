@@ -36,6 +36,11 @@ class OnPolicyHARunner(OnPolicyBaseRunner):
         else:
             agent_order = list(torch.randperm(self.num_agents).numpy())
         self.last_agent_order = agent_order
+        if self.world > 1 and not self.fixed_order:   # the gradient exchanges pair up agents by position in this order
+            o = torch.tensor([int(a) for a in agent_order], dtype=torch.int64, device=dev)
+            o0 = o.clone()
+            torch.distributed.broadcast(o0, src=0)
+            assert torch.equal(o, o0), "agent order differs across ranks (unsynchronised torch CPU generator)"
         infos = []
         agg_prod = self.action_aggregation == "prod"
         # The critic update (reference :128) shares no state with the actor updates: enqueue it first on a side

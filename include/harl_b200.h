@@ -206,6 +206,13 @@ int hb_gae_returns(const float* rewards, float* value_preds, const float* masks,
                    float* advantages, int32_t T, int64_t C, float gamma, float gamma_lambda,
                    int use_gae, int use_proper_time_limits, const float* vn_state, void* stream);
 
+/* Which kernel runs the GAE branch of hb_gae_returns: 0 = column tiles staged in shared memory (gae.cu),
+ * 1 = time-segmented, register-resident, sequential carry (default; bit-identical to 0 and to the reference's
+ * on_policy_critic_buffer_ep.py:111-140 loop), 2 = same with a parallel affine scan for the carry between segments
+ * (advantages within 1e-6 of max|adv| of the sequential result).  Env HB_GAE_IMPL sets the initial value. */
+int hb_set_gae_impl(int impl);
+int hb_get_gae_impl(void);
+
 /* Masked moments for happo.py:122-127 / on_policy_ha_runner.py:36-45:
  * out3 (device double[3]) += (sum x*w, sum x*x*w, sum w) with w = (weight != 0) or 1. */
 int hb_masked_moments(const float* x, const float* weight, int64_t n, double* out3, void* stream);

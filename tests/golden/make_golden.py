@@ -409,9 +409,13 @@ def case_ma_train():
         save(f"ma_train_{tag}", **out)
 
 
-def case_single_update():
+ACTIVATIONS = ("sigmoid", "tanh", "relu", "leaky_relu", "selu", "hardswish", "identity")   # models_tools.py:28-50
+
+
+def case_single_update(cases=None):
     """One HAPPO.update and one VCritic.update: raw gradients before clipping."""
-    for tag, over, act_space in (("disc", {}, Discrete(5)), ("box", dict(hidden_sizes=[32, 32, 32]), Box(3))):
+    cases = cases or (("disc", {}, Discrete(5)), ("box", dict(hidden_sizes=[32, 32, 32]), Box(3)))
+    for tag, over, act_space in cases:
         torch.manual_seed(21)
         g = torch.Generator().manual_seed(22)
         rng = np.random.default_rng(23)
@@ -685,6 +689,16 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     if len(sys.argv) > 1 and sys.argv[1] == "generators":
         case_generators()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "activations":  # one HAPPO.update / VCritic.update per activation function
+        unusable = []
+        for name in ACTIVATIONS:
+            try:
+                case_single_update([(f"act_{name}", dict(activation_func=name), Discrete(5))])
+            except ValueError as e:      # mlp.py:20 nn.init.calculate_gain rejects hardswish and identity: no reference net exists
+                unusable.append((name, str(e)))
+        case_single_update([("act_tanh_box", dict(activation_func="tanh"), Box(3)), ("act_selu_box", dict(activation_func="selu"), Box(2))])
+        print("reference cannot build:", unusable)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "hatrpo":  # regenerate only the HATRPO vectors
         case_hatrpo_parts()

@@ -85,7 +85,21 @@ def test_mappo_iteration_vs_oracle(action_type, state_type, share):
     runner.close()
 
 
-def _load_runner_from_golden(g, cfg, m, actor_cls=None):
+def _replay_perms(monkeypatch, g):
+    """torch.randperm replaced by the permutations the unmodified reference drew while the golden was recorded
+    (tests/golden/make_golden.py PermRecorder), in the same call order."""
+    it = iter([g[f"perm{i}"] for i in range(int(g["n_perms"]))])
+
+    def fake(n, *a, **k):
+        p = next(it)
+        assert len(p) == n, (len(p), n)
+        return torch.from_numpy(np.ascontiguousarray(p)).long()
+
+    monkeypatch.setattr(torch, "randperm", fake)
+    return it
+
+
+def _load_runner_from_golden(g, cfg, m, actor_cls=None, runner_cls=None, share=False):
     """A runner shell (no env / dirs) holding the golden buffers and weights."""
     from harl_b200.algorithms.actors.happo import HAPPO
     from harl_b200.common.buffers.on_policy_critic_buffer_fp import OnPolicyCriticBufferFP
@@ -99,15 +113,20 @@ def _load_runner_from_golden(g, cfg, m, actor_cls=None):
     dev = torch.device("cuda:0")
     A = m["A"]
     act_space = Discrete(m["act_dim"]) if m["head"] == "Discrete" else Box(shape=(m["act_dim"],))
-    r = object.__new__(OnPolicyHARunner)
+    r = object.__new__(runner_cls or OnPolicyHARunner)
+    r.share_param, r.world = share, 1
+    r.overlap_critic_update = False   # the reference draws the actors' permutations before the critic's
     r.algo_args = {"train": cfg, "algo": cfg, "model": cfg}
     r.device, r.n_local, r.num_agents, r.state_type = dev, cfg["n_rollout_threads"], A, m["state_type"]
     r.fixed_order, r.action_aggregation = True, cfg["action_aggregation"]
     r.actor, r.actor_buffer = [], []
     for a in range(A):
-        ac = (actor_cls or HAPPO)(cfg, Box(shape=(m["od"],)), act_space, device=dev)
-        ac.actor.load_state_dict(U.params_of(g, f"actor{a}/"))
-        r.actor.append(ac)
+        if share and a > 0:
+            r.actor.append(r.actor[0])
+        else:
+            ac = (actor_cls or HAPPO)(cfg, Box(shape=(m["od"],)), act_space, device=dev)
+            ac.actor.load_state_dict(U.params_of(g, f"actor{a}/"))
+            r.actor.append(ac)
         b = OnPolicyActorBuffer(cfg, Box(shape=(m["od"],)), act_space, device=dev)
         for k in ("obs", "actions", "action_log_probs", "masks", "active_masks") + (("rnn_states",) if b.recurrent else ()):
             getattr(b, k).copy_(torch.from_numpy(g[f"a{a}.{k}"]))
@@ -131,16 +150,50 @@ def _load_runner_from_golden(g, cfg, m, actor_cls=None):
     return r
 
 
-@pytest.mark.parametrize("name", ["ha_train_mlp_disc_EP", "ha_train_mlp_box_EP"])
-def test_reference_ha_train_golden(name):
-    """The unmodified reference's OnPolicyHARunner.train() outputs, reproduced by the device path."""
+@pytest.mark.parametrize("name", ["ha_train_mlp_disc_EP", "ha_train_mlp_box_EP", "ha_train_mlp_disc_mb2_EP"])
+def test_reference_ha_train_golden(name, monkeypatch):
+    """The unmodified reference's OnPolicyHARunner.train() outputs, reproduced by the device path (two minibatches:
+    on the reference's own recorded permutations)."""
     g = U.load(name)
     cfg, m = U.cfg_of(g), U.meta_of(g)
     r = _load_runner_from_golden(g, cfg, m)
+    if cfg["actor_num_mini_batch"] > 1 or cfg["critic_num_mini_batch"] > 1:
+        left = _replay_perms(monkeypatch, g)
     infos, cinfo = r.train()
+    if cfg["actor_num_mini_batch"] > 1 or cfg["critic_num_mini_batch"] > 1:
+        assert next(left, None) is None   # every recorded permutation was consumed
     torch.cuda.synchronize()
     for a in range(m["A"]):
         np.testing.assert_allclose(r.actor_buffer[a].factor.cpu().numpy(), g[f"out.factor{a}"], rtol=3e-4, atol=3e-5)
+        got = [infos[a][k] for k in ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio")]
+        np.testing.assert_allclose(got, g[f"out.info{a}"], rtol=3e-4, atol=3e-5)
+        for k, v in r.actor[a].actor.state_dict().items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"out.actor{a}/" + k], rtol=0, atol=3e-5, err_msg=k)
+    np.testing.assert_allclose([cinfo["value_loss"], cinfo["critic_grad_norm"]], g["out.cinfo"], rtol=3e-4)
+    for k, v in r.critic.critic.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), g["out.critic/" + k], rtol=0, atol=3e-5, err_msg=k)
+    np.testing.assert_allclose(r.value_normalizer.state.cpu().numpy(), g["out.vn"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", U.names("ma_train_"))
+def test_reference_ma_train_golden(name, monkeypatch):
+    """The unmodified reference's OnPolicyMARunner.train() (MAPPO; separate actors, shared parameters, shared
+    parameters with two minibatches and FP state) reproduced by the device path."""
+    from harl_b200.algorithms.actors.mappo import MAPPO
+    from harl_b200.runners.on_policy_ma_runner import OnPolicyMARunner
+
+    g = U.load(name)
+    cfg, m = U.cfg_of(g), U.meta_of(g)
+    share = bool(int(g["share"][0]))
+    r = _load_runner_from_golden(g, cfg, m, actor_cls=MAPPO, runner_cls=OnPolicyMARunner, share=share)
+    multi = cfg["actor_num_mini_batch"] > 1 or cfg["critic_num_mini_batch"] > 1
+    if multi:
+        left = _replay_perms(monkeypatch, g)
+    infos, cinfo = r.train()
+    torch.cuda.synchronize()
+    if multi:
+        assert next(left, None) is None
+    for a in range(m["A"]):
         got = [infos[a][k] for k in ("policy_loss", "dist_entropy", "actor_grad_norm", "ratio")]
         np.testing.assert_allclose(got, g[f"out.info{a}"], rtol=3e-4, atol=3e-5)
         for k, v in r.actor[a].actor.state_dict().items():

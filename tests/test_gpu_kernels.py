@@ -67,13 +67,25 @@ def test_gae_golden_bit_exact(name):
     assert np.array_equal(adv.reshape(g["advantages"].shape), g["advantages"])
 
 
-@pytest.mark.parametrize("C_,T", [(4096, 200), (1024 * 6, 50), (8, 200), (4099, 33)])
+@pytest.fixture(params=[1, 0], ids=["seg", "tiled"])
+def gae_impl(request):
+    """Both bit-exact GAE kernels: 1 = time-segmented register kernel (default, gae_seg.cu), 0 = shared-memory tiles."""
+    from harl_b200 import _lib as L
+
+    L.call("hb_set_gae_impl", request.param)
+    yield request.param
+    L.call("hb_set_gae_impl", 1)
+
+
+@pytest.mark.parametrize("C_,T", [(4096, 200), (1024 * 6, 50), (8, 200), (4099, 33), (100, 256), (64, 257), (37, 5), (4096, 129)])
 @pytest.mark.parametrize("flags", [(1, 1, 1), (1, 0, 0), (0, 1, 1), (0, 0, 0)])
-def test_gae_large_vs_oracle(C_, T, flags):
-    """BASELINE sizes (tiled cp.async kernel) and ragged widths (column kernel) vs the oracle, bit-exact."""
+def test_gae_large_vs_oracle(C_, T, flags, gae_impl):
+    """BASELINE sizes and ragged widths / lengths vs the oracle, bit-exact, on both sequential-carry kernels."""
     from oracle import buffers as ob
 
     use_gae, ptl, use_vn = flags
+    if not use_gae and gae_impl == 0:
+        pytest.skip("the return branch without GAE has one kernel")
     rng = np.random.default_rng(C_ + T)
     rew = rng.standard_normal((T, C_, 1)).astype(np.float32)
     vp = rng.standard_normal((T + 1, C_, 1)).astype(np.float32)
@@ -95,6 +107,34 @@ def test_gae_large_vs_oracle(C_, T, flags):
         assert np.array_equal(vpo.reshape(T + 1, C_, 1), vp_o)
     else:
         assert np.array_equal(ret[-1].reshape(C_, 1), ret_o[-1])
+
+
+@pytest.mark.parametrize("C_,T,ptl,use_vn", [(4096, 200, 1, 1), (4099, 33, 0, 0), (96, 256, 1, 0), (1000, 7, 0, 1)])
+def test_gae_parallel_scan_within_1e6_of_sequential(C_, T, ptl, use_vn):
+    """hb_set_gae_impl(2): the carry between time segments comes from a parallel affine scan (FMAs) instead of the
+    sequential hand-over.  Stated tolerance: 1e-6 of max|advantage| (the steps inside a segment are replayed exactly)."""
+    from harl_b200 import _lib as L
+
+    rng = np.random.default_rng(C_ * 7 + T)
+    rew = rng.standard_normal((T, C_, 1)).astype(np.float32)
+    vp = rng.standard_normal((T + 1, C_, 1)).astype(np.float32)
+    masks = (rng.random((T + 1, C_, 1)) > 0.02).astype(np.float32)
+    bad = np.where((masks == 0) & (rng.random(masks.shape) < 0.5), 0, 1).astype(np.float32)
+    nv = rng.standard_normal((C_, 1)).astype(np.float32)
+    vs = np.array([0.3, 1.9, 0.8], np.float32) if use_vn else None
+    out = {}
+    for impl in (1, 2):
+        L.call("hb_set_gae_impl", impl)
+        try:
+            out[impl] = _run_gae(rew, vp, masks, bad, nv, 0.99, 0.95, 1, ptl, vs)
+        finally:
+            L.call("hb_set_gae_impl", 1)
+    (ret1, vp1, adv1), (ret2, vp2, adv2) = out[1], out[2]
+    assert np.array_equal(vp1, vp2)
+    scale = np.abs(adv1).max()
+    assert np.abs(adv2 - adv1).max() <= 1e-6 * scale
+    assert np.abs(ret2[:-1] - ret1[:-1]).max() <= 1e-6 * max(scale, np.abs(ret1[:-1]).max())
+    assert (adv1 == adv2).mean() > 0.5   # most entries are identical: only the carried term differs by an ulp or two
 
 
 def test_gae_linearity_in_rewards():
@@ -412,3 +452,15 @@ def test_actor_grad_vs_oracle_baseline_shapes(shape):
     np.testing.assert_allclose(lp_dev.cpu().numpy(), lp_all.numpy(), rtol=1e-5, atol=3e-5)
     ref_fac = oa.factor_update(factor, lp_all, torch.from_numpy(old_lp), cfg)
     np.testing.assert_allclose(fac.cpu().numpy().reshape(-1, 1), ref_fac, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("act", ["hardswish", "identity"])
+def test_activations_the_reference_cannot_build_raise_the_same_error(act):
+    """models_tools.py:28-50 lists hardswish and identity, but every MLP goes through mlp.py:20
+    nn.init.calculate_gain(activation_func), which rejects both: the reference raises ValueError at construction
+    (tests/golden/make_golden.py `activations` records it), and so does DeviceNet."""
+    from harl_b200 import _lib as L
+    from harl_b200.nets import DeviceNet
+
+    with pytest.raises(ValueError, match="Unsupported nonlinearity"):
+        DeviceNet(U.base_args(activation_func=act), 12, L.HEAD_DISCRETE, 5, "cuda:0")
