@@ -45,6 +45,7 @@ def run_ours(a):
     env_args["backend"] = "native"
     algo_args["train"]["log_interval"] = a.log_interval
     r = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+    r.disable_fast_rollout = bool(a.generic_rollout)
     r.warmup()
     T = algo_args["train"]["episode_length"]
     episodes = a.steps // T // a.n
@@ -91,6 +92,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--log-interval", type=int, default=5)
     ap.add_argument("--threads", type=int, default=4, help="reference: device.torch_threads (tuned config: 4)")
+    ap.add_argument("--generic-rollout", action="store_true",
+                    help="ours: the reference-shaped collect / step / insert loop instead of the zero-copy CUDA-graph rollout")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     res = run_ours(a) if a.impl == "ours" else run_reference(a)

@@ -94,6 +94,26 @@ class AdamHyper(C.Structure):
 HB_MPE_MAX_AGENTS = 8
 
 
+class CopySeg(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("bytes", C.c_int64)]
+
+
+def copy_segments(dsts, srcs):
+    """dst[i].copy_(src[i]) for all i in ONE launch (hb_copy_segments); the tensors must be contiguous, equal-sized,
+    4-byte typed and start on 16-byte boundaries -- returns False (nothing done) otherwise, for the caller's fallback."""
+    n = len(dsts)
+    if n == 0 or n > 16:
+        return False
+    segs = (CopySeg * n)()
+    for i, (d, s) in enumerate(zip(dsts, srcs)):
+        if not (d.is_cuda and s.is_cuda and d.is_contiguous() and s.is_contiguous() and d.dtype == s.dtype and d.element_size() == 4
+                and d.numel() == s.numel() and d.data_ptr() % 16 == 0 and s.data_ptr() % 16 == 0):
+            return False
+        segs[i].dst, segs[i].src, segs[i].bytes = d.data_ptr(), s.data_ptr(), d.numel() * 4
+    call("hb_copy_segments", segs, n, stream_ptr())
+    return True
+
+
 class MpeArgs(C.Structure):
     _fields_ = [("n_envs", C.c_int32), ("n_agents", C.c_int32), ("n_landmarks", C.c_int32), ("continuous", C.c_int32),
                 ("max_cycles", C.c_int32), ("reset_all", C.c_int32), ("seed", C.c_uint64),
@@ -127,6 +147,12 @@ SIGNATURES = {
     "hb_policy_act": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, C.c_int, C.c_uint64, C.c_uint64, P, P, P,
                                 C.c_size_t, P]),
     "hb_value_forward": (C.c_int, [C.POINTER(NetDesc), P, P, C.c_int64, P, P, C.c_size_t, P]),
+    "hb_copy_segments": (C.c_int, [P, C.c_int32, P]),
+    "hb_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), P]),
+    "hb_comm_open_peers": (C.c_int, [P, P]),
+    "hb_allreduce_bucket": (C.c_int, [P, P, C.c_int64, C.c_int32, P]),
+    "hb_comm_status": (C.c_int, [P]),
+    "hb_comm_destroy": (C.c_int, [P]),
     "hb_set_gae_impl": (C.c_int, [C.c_int]),
     "hb_get_gae_impl": (C.c_int, []),
     "hb_gae_returns": (C.c_int, [P, P, P, P, P, P, P, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_int, C.c_int,
@@ -178,7 +204,7 @@ HB_ERR_UNSUPPORTED = -2
 GEMM_IMPLS = {"fp32": 0, "3xtf32": 1, "tf32": 2}
 if os.environ.get("HB_GEMM_IMPL"):
     lib.hb_set_gemm_impl(GEMM_IMPLS[os.environ["HB_GEMM_IMPL"]])
-_NO_CHECK = {"hb_version", "hb_last_error", "hb_workspace_bytes", "hb_trpo_workspace_bytes", "hb_kernel_launch_count", "hb_profile_end", "hb_get_gemm_impl", "hb_get_rnn_impl", "hb_get_trpo_jvp_impl", "hb_get_fused_update"}
+_NO_CHECK = {"hb_version", "hb_last_error", "hb_workspace_bytes", "hb_trpo_workspace_bytes", "hb_kernel_launch_count", "hb_profile_end", "hb_get_gemm_impl", "hb_get_rnn_impl", "hb_get_trpo_jvp_impl", "hb_get_fused_update", "hb_get_gae_impl", "hb_comm_status"}
 
 # launches of library entry points since import (bench.py's gpu_launches bookkeeping)
 call_count = 0

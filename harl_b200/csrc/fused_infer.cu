@@ -383,7 +383,7 @@ extern "C" int hb_rollout_collect(const hb_collect_args* a, void* ws, size_t ws_
                               critic ? 0ull : a->seed[i], critic ? a->critic_rows : a->rows, &ok);
       if (rc) return rc;
       all = ok && d->hidden[0] == F.H && d->activation == F.act;
-      HB_CHECK_ARG(F.net[i].prep && F.net[i].obs && F.net[i].out0 && (critic || F.net[i].out1), "NULL buffer");
+      if (all) HB_CHECK_ARG(F.net[i].prep && F.net[i].obs && F.net[i].out0 && (critic || F.net[i].out1), "NULL buffer");
     }
     if (all) return launch_fused_act(F, st);
   }

@@ -12,6 +12,15 @@ import torch
 
 from .spaces import Box, Discrete
 
+
+def _copy_segments(dsts, srcs):
+    """All step outputs into their buffer slots in one launch (hb_copy_segments); False -> the caller copies itself."""
+    if not dsts[0].is_cuda:
+        return False
+    from .. import _lib as L
+
+    return L.copy_segments(dsts, srcs)
+
 # shapes of the BASELINE.json configs (SURVEY.md section 8(d))
 PRESETS = {
     ("pettingzoo_mpe", "simple_spread_v2"): dict(n_agents=3, obs_dim=18, share_obs_dim=54, action_dim=5, episode_limit=25),
@@ -192,7 +201,8 @@ class SyntheticBatchedEnv:
             dst["rewards"].copy_(rew.unsqueeze(1).expand(-1, A, -1))
         if dst.get("rewards_na") is not None:
             dst["rewards_na"].copy_(rew.expand(-1, A))
-        torch._foreach_copy_(dsts, srcs)
+        if not _copy_segments(dsts, srcs):
+            torch._foreach_copy_(dsts, srcs)
         if self._simple:
             self._ep_step_host += 1
             done = self._ep_step_host >= self.episode_limit
@@ -332,7 +342,8 @@ class SyntheticBatchedEnv:
         if avail_v is not None:
             dsts += list(dst["avail"])
             srcs += list(avail_v)
-        torch._foreach_copy_(dsts, srcs)
+        if not _copy_segments(dsts, srcs):
+            torch._foreach_copy_(dsts, srcs)
 
     def graph_period(self):
         """Number of steps after which the HOST side of ``step_into`` repeats itself (pool index, and in the simple

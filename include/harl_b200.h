@@ -206,6 +206,34 @@ int hb_gae_returns(const float* rewards, float* value_preds, const float* masks,
                    float* advantages, int32_t T, int64_t C, float gamma, float gamma_lambda,
                    int use_gae, int use_proper_time_limits, const float* vn_state, void* stream);
 
+/* One launch copying n <= HB_COPY_MAX_SEGS contiguous device segments (16-byte aligned starts, sizes in whole 4-byte
+ * words): an env's per-step outputs into their rollout-buffer slots -- what OnPolicyBaseRunner.insert
+ * (harl/runners/on_policy_base_runner.py:340-415) does with one NumPy assignment per array. */
+#define HB_COPY_MAX_SEGS 16
+typedef struct hb_copy_seg {
+  void* dst;
+  const void* src;
+  int64_t bytes;
+} hb_copy_seg;
+int hb_copy_segments(const hb_copy_seg* segs, int32_t n, void* stream);
+
+/* ---- multi-GPU exchange: one-shot sum-allreduce of a small bucket over NVLink peer memory.
+ * The reference is single-process; what is exchanged is the part of its batch means that lives on other GPUs when the
+ * rollout threads are sharded: the flat gradient of one optimiser step (happo.py:85-97, v_critic.py:116-140) and the
+ * loss / advantage / ValueNorm normalisers (happo.py:74-91, on_policy_ha_runner.py:38-47, valuenorm.py:47-64).
+ *
+ * hb_comm_create allocates this rank's exchange region on the current device (2 slots of slot_bytes + flags) and writes
+ * its 64-byte CUDA IPC handle to ipc_handle_out64; the caller gathers the handles of all ranks (any transport) and
+ * passes the world x 64 bytes, in rank order, to hb_comm_open_peers.  hb_allreduce_bucket sums buf[0..n) (dtype 0 =
+ * float32, 1 = float64) over the ranks IN RANK ORDER, in place, on `stream`: every rank obtains the bit-identical
+ * result.  All ranks must issue the same sequence of calls on a communicator; use one communicator per stream.
+ * hb_comm_status: 0, or 1 + r if rank r did not arrive within HB_COMM_TIMEOUT_S (default 20 s) in some exchange. */
+int hb_comm_create(int32_t rank, int32_t world, size_t slot_bytes, void** comm_out, void* ipc_handle_out64);
+int hb_comm_open_peers(void* comm, const void* all_handles);
+int hb_allreduce_bucket(void* comm, void* buf, int64_t n, int32_t dtype, void* stream);
+int hb_comm_status(void* comm);
+int hb_comm_destroy(void* comm);
+
 /* Which kernel runs the GAE branch of hb_gae_returns: 0 = column tiles staged in shared memory (gae.cu),
  * 1 = time-segmented, register-resident, sequential carry (default; bit-identical to 0 and to the reference's
  * on_policy_critic_buffer_ep.py:111-140 loop), 2 = same with a parallel affine scan for the carry between segments

@@ -409,6 +409,48 @@ def case_ma_train():
         save(f"ma_train_{tag}", **out)
 
 
+def case_checkpoint():
+    """A checkpoint directory written by the unmodified reference's OnPolicyBaseRunner.save() (on_policy_base_runner.py:
+    724-740) and what the reference computes from it: deterministic actions of every actor and the critic's values on a
+    fixed batch.  tests/golden/ckpt_ref/*.pt are the reference's own torch.save files."""
+    torch.manual_seed(41)
+    g = torch.Generator().manual_seed(42)
+    rng = np.random.default_rng(43)
+    args = base_args()
+    A, od, sd, na, n = 3, 7, 9, 5, 12
+    actors = [HAPPO(args, Box(od), Discrete(na)) for _ in range(A)]
+    critic = VCritic(args, Box(sd))
+    for a in actors:
+        perturb(a.actor, g, 0.3)
+    perturb(critic.critic, g, 0.3)
+    vn = ValueNorm(1)
+    vn.update(rng.standard_normal((64, 1)).astype(np.float32) * 2 + 0.5)
+    d = os.path.join(HERE, "ckpt_ref")
+    os.makedirs(d, exist_ok=True)
+    fake = SimpleNamespace(num_agents=A, actor=actors, critic=critic, value_normalizer=vn, save_dir=d)
+    OnPolicyBaseRunner.save(fake)
+    obs = rng.standard_normal((n, A, od)).astype(np.float32)
+    share = rng.standard_normal((n, sd)).astype(np.float32)
+    avail = (rng.random((n, A, na)) < 0.6).astype(np.float32)
+    avail[..., 2] = 1.0
+    rnn = np.zeros((n, 1, 32), np.float32)
+    masks = np.ones((n, 1), np.float32)
+    out = dict(obs=obs, share_obs=share, avail=avail)
+    for a in range(A):
+        for x in (actors[a], critic):
+            x.prep_rollout()
+        act, _ = actors[a].act(obs[:, a], rnn, masks, avail[:, a], deterministic=True)
+        out[f"det_action{a}"] = act.detach().numpy()
+        _, lp, _ = actors[a].get_actions(obs[:, a], rnn, masks, avail[:, a], deterministic=True)
+        out[f"det_logp{a}"] = lp.detach().numpy()
+    v, _ = critic.get_values(share, rnn, masks)
+    out["values"] = v.detach().numpy()
+    out["values_denorm"] = vn.denormalize(v.detach()) if not isinstance(vn.denormalize(v.detach()), torch.Tensor) else vn.denormalize(v.detach()).numpy()
+    out["vn"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(), vn.debiasing_term.item()], np.float32)
+    save("checkpoint_ref", **out)
+    print("files:", sorted(os.listdir(d)))
+
+
 ACTIVATIONS = ("sigmoid", "tanh", "relu", "leaky_relu", "selu", "hardswish", "identity")   # models_tools.py:28-50
 
 
@@ -689,6 +731,9 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     if len(sys.argv) > 1 and sys.argv[1] == "generators":
         case_generators()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        case_checkpoint()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "activations":  # one HAPPO.update / VCritic.update per activation function
         unusable = []

@@ -33,6 +33,23 @@ def test_iteration_vs_oracle(action_type, state_type, over):
     runner.close()
 
 
+@pytest.mark.parametrize("hidden,obs_dim,action_type", [((32, 32, 32), 7, "Discrete"), ((64, 64), 70, "Box"), ((128,), 7, "Discrete"),
+                                                        ((32, 64), 7, "Discrete")])
+def test_iteration_vs_oracle_on_shapes_outside_the_fused_kernels(hidden, obs_dim, action_type):
+    """Three hidden layers (C3 / C5), observations wider than 64 (C5: 393), one layer, unequal widths: the tcgen05 fused
+    rollout / update kernels decline these shapes and the layer-wise kernels take over inside the same entry points."""
+    from harl_b200.runners import RUNNER_REGISTRY
+
+    args, algo_args, env_args = small_config(action_type=action_type, hidden=hidden)
+    env_args.update(obs_dim=obs_dim, share_obs_dim=obs_dim + 2)
+    runner = RUNNER_REGISTRY["happo"](args, algo_args, env_args)
+    runner.warmup()
+    runner.logger.init(2)
+    check_iteration(runner)
+    check_iteration(runner)
+    runner.close()
+
+
 @pytest.mark.parametrize("use_gae,ptl,vn", [(True, False, False), (False, True, True), (False, False, False)])
 def test_iteration_return_branches(use_gae, ptl, vn):
     from harl_b200.runners import RUNNER_REGISTRY

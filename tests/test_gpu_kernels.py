@@ -464,3 +464,24 @@ def test_activations_the_reference_cannot_build_raise_the_same_error(act):
 
     with pytest.raises(ValueError, match="Unsupported nonlinearity"):
         DeviceNet(U.base_args(activation_func=act), 12, L.HEAD_DISCRETE, 5, "cuda:0")
+
+
+def test_copy_segments_equals_elementwise_copies():
+    """hb_copy_segments: every segment copied exactly, tails shorter than 16 bytes included, neighbours untouched."""
+    from harl_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(5)
+    sizes = [4096 * 18, 4096 * 54, 4096, 7, 4, 1, 4096 * 5 + 3, 16]
+    srcs = [torch.randn(n + 8, generator=g).to(_dev())[4:4 + n] for n in sizes]          # 16-byte aligned interior views
+    dsts = [torch.full((n + 8,), -7.0, device=_dev())[4:4 + n] for n in sizes]
+    assert L.copy_segments(dsts, srcs)
+    torch.cuda.synchronize()
+    for d, s in zip(dsts, srcs):
+        assert torch.equal(d, s)
+        full = d._base if d._base is not None else d
+        assert (full[:4] == -7.0).all() and (full[-4:] == -7.0).all()
+    ints = [torch.arange(100, dtype=torch.int32, device=_dev())]
+    outs = [torch.zeros(100, dtype=torch.int32, device=_dev())]
+    assert L.copy_segments(outs, ints) and torch.equal(outs[0], ints[0])
+    assert not L.copy_segments([torch.zeros(9, device=_dev())[1:]], [torch.zeros(9, device=_dev())[1:]])   # misaligned: declined
+    assert not L.copy_segments([torch.zeros(4, 4, device=_dev()).t()], [torch.zeros(4, 4, device=_dev())])   # not contiguous
