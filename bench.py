@@ -296,13 +296,22 @@ def roofline_of(rows, peaks):
     return out
 
 
-def gae_microbench(torch, T, C, peaks, sets=8, reps=5):
+def gae_microbench(torch, T, C, peaks, sets=8, reps=5, impl=None):
     """hb_gae_returns alone at the workload's [T, C]: CUDA events around sets x reps launches that rotate over
     `sets` independent buffer sets (8 x 19.7 MB at C2 > the 126 MB L2, so every launch streams from HBM).
     Algorithmic bytes = 24 B per (t, column): rewards, value_preds, masks, bad_masks read; returns, advantages
     written."""
     from harl_b200 import _lib as L
 
+    if impl is not None:   # 1 = sequential carry (default, bit-exact), 2 = parallel scan of the carry (1e-6 of max|adv|)
+        prev = L.lib.hb_get_gae_impl()
+        L.call("hb_set_gae_impl", impl)
+        try:
+            out = gae_microbench(torch, T, C, peaks, sets, reps)
+        finally:
+            L.call("hb_set_gae_impl", prev)
+        out["kernel"] += " impl=%d (%s)" % (impl, {0: "shared-memory tiles", 1: "segmented, sequential carry", 2: "segmented, parallel scan"}[impl])
+        return out
     dev = torch.device("cuda:0" if "LOCAL_RANK" not in os.environ else f"cuda:{os.environ['LOCAL_RANK']}")
     g = torch.Generator(device="cpu").manual_seed(3)
     bufs = []
@@ -562,12 +571,21 @@ def main():
         # the two kernels BASELINE.json's north_star names: the GAE scan and the PPO-update (clip-loss) kernel
         named = {"gae": gae_microbench(torch, T, runner.critic_buffer.value_preds[0].numel(), load_peaks()),
                  # the same kernel where launch + fill latency and the T-step serial recurrence are amortised
-                 "gae_16x_columns": gae_microbench(torch, T, 16 * runner.critic_buffer.value_preds[0].numel(), load_peaks(), sets=2, reps=3)}
+                 "gae_16x_columns": gae_microbench(torch, T, 16 * runner.critic_buffer.value_preds[0].numel(), load_peaks(), sets=2, reps=3),
+                 # opt-in variant (hb_set_gae_impl(2) / HB_GAE_IMPL=2): the carry between time segments by a parallel affine scan
+                 "gae_parallel_scan_opt_in": gae_microbench(torch, T, runner.critic_buffer.value_preds[0].numel(), load_peaks(), impl=2),
+                 "gae_parallel_scan_opt_in_16x_columns": gae_microbench(torch, T, 16 * runner.critic_buffer.value_preds[0].numel(),
+                                                                        load_peaks(), sets=2, reps=3, impl=2)}
         ppo = [r for r in rows if r[0].startswith("fused_actor_update")] or [r for r in rows if r[0].startswith("policy_head_grad")]
         if ppo:
             named["ppo_update"] = dict(kernel=ppo[0][0], launches=ppo[0][1], avg_us=1e3 * ppo[0][2] / ppo[0][1], **_rate(ppo[0], load_peaks()))
         line["roofline"]["named_kernels"] = named
         line["config"]["phases_ms"] = {k: round(v, 3) for k, v in getattr(runner, "phase_ms", {}).items()}
+        if dist_on:
+            from harl_b200 import dist as _d
+
+            line["config"]["exchanges"] = dict(_d.stats, transport="hb_allreduce_bucket (one-shot, NVLink peer memory)" if _d.stats["p2p"]
+                                               else "torch.distributed.all_reduce (NCCL)", note="issued by rank 0 over the whole run")
         if a.profile_out:
             tot = sum(r[2] for r in rows)
             with open(a.profile_out, "w") as fh:

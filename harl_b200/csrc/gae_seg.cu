@@ -174,9 +174,13 @@ bool launch_gae_seg(const float* rewards, float* value_preds, const float* masks
   const bool scan = impl == 2;
   const unsigned grid = (unsigned)ceil_div64(C, 32);
   static const int forced = getenv("HB_GAE_SEGS") ? atoi(getenv("HB_GAE_SEGS")) : 0;   // tuning knob: 4 / 8 / 13
+  // measured on B200 (profiles/gae_variants_r02.txt), T = 200: 13 segments x 16 steps wins for the sequential carry at
+  // every width and for the scan below ~16k columns (shorter per-thread chains, 416 threads per CTA); 8 x 25 wins for
+  // the scan on wide buffers (61 vs 84 us at 65536 columns: fewer, fatter threads keep more loads in flight per SM)
+  const bool seg13 = forced == 13 || (forced == 0 && T > 8 * 16 && T <= 13 * 16 && (!scan || C < 16384));
 #define HB_GO(S, LL) launch_seg<S, LL>(ptl != 0, scan, grid, st, rewards, value_preds, masks, bad_masks, next_value, returns, \
                                        advantages, T, C, gamma, gl, vn)
-  if (forced == 13 && T <= 13 * 16) HB_GO(13, 16);
+  if (seg13 && T <= 13 * 16) HB_GO(13, 16);
   else if (forced == 4 && T <= 4 * 32) HB_GO(4, 32);
   else if (T <= 8 * 4) HB_GO(8, 4);
   else if (T <= 8 * 8) HB_GO(8, 8);

@@ -235,19 +235,8 @@ def test_share_param_with_recurrent_policy_fails_loudly():
     args, algo_args, env_args = small_config(algo="mappo", T=8)
     algo_args["model"].update(data_chunk_length=4, use_recurrent_policy=True)
     algo_args["algo"]["share_param"] = True
-    runner = RUNNER_REGISTRY["mappo"](args, algo_args, env_args)
-    runner.warmup()
-    runner.logger.init(1)
-    runner.logger.episode_init(1)
-    for step in range(8):
-        values, actions, logp, rnn, rnn_c = runner.collect(step)
-        obs, share_obs, rewards, dones, infos, avail = runner.envs.step(actions)
-        runner.insert((obs, share_obs, rewards, dones, infos, avail, values, actions, logp, rnn, rnn_c))
-    runner.compute()
-    with pytest.raises(NotImplementedError):
-        runner.train()
-    torch.cuda.synchronize()
-    runner.close()
+    with pytest.raises(NotImplementedError, match="share_param"):   # at construction, before the first rollout
+        RUNNER_REGISTRY["mappo"](args, algo_args, env_args)
 
 
 @pytest.mark.parametrize("state_type,over", [("EP", dict(use_recurrent_policy=True)), ("FP", dict(use_naive_recurrent_policy=True))])
