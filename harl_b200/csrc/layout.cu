@@ -43,6 +43,8 @@ static int add_tensor(hb_net_layout* L, int* cursor, const char* name, int rows,
 int tc_nt_of(int n);
 int launch_pack_umma_tiles(const float* W, int ldn, int ldk, const float* scale, int N, int K, int NT, int nchunks,
                            float* dst, cudaStream_t st);
+int launch_pack_umma_jobs(int njobs, const float* const* W, const int* ldn, const int* ldk, const float* const* scale, const int* N,
+                          const int* K, const int* NT, const int* nchunks, float* const* dst, cudaStream_t st);
 
 bool fused_shape_ok(const hb_net_desc* d);   // fused_update.cu
 int launch_fused_pack(const hb_net_desc* d, const ParamLayout& P, const PrepLayout& Q, const float* params, float* prepared,
@@ -225,17 +227,20 @@ int prepare_launch(const hb_net_desc* d, const float* params, float* prepared, c
   if (rc) return rc;
   prepare_kernel<<<(Q.tk[0] + 255) / 256, 256, 0, st>>>(P, Q, d->feature_norm, d->head, d->out_dim, params, prepared);
   HB_LAUNCH_DONE(st,"hb_net_prepare");
-  if (gemm_impl() != 0) {
+  if (gemm_impl() != 0) {  // all tcgen05 operand images of the layer-wise kernels in one launch
+    const float* W[2 * HB_MAX_LAYERS]; const float* sc[2 * HB_MAX_LAYERS]; float* dst[2 * HB_MAX_LAYERS];
+    int ldn[2 * HB_MAX_LAYERS], ldk[2 * HB_MAX_LAYERS], N[2 * HB_MAX_LAYERS], K[2 * HB_MAX_LAYERS], NT[2 * HB_MAX_LAYERS],
+        nch[2 * HB_MAX_LAYERS], nj = 0;
     for (int l = 0; l < Q.n_layers; ++l) {
-      rc = launch_pack_umma_tiles(params + P.w[l], Q.k[l], 1, (l == 0 && d->feature_norm) ? params + P.fn_w : nullptr,
-                                  Q.n[l], Q.k[l], Q.tk_nt[l], Q.tk_chunks[l], prepared + Q.tk[l], st);
-      if (rc) return rc;
+      W[nj] = params + P.w[l]; ldn[nj] = Q.k[l]; ldk[nj] = 1; sc[nj] = (l == 0 && d->feature_norm) ? params + P.fn_w : nullptr;
+      N[nj] = Q.n[l]; K[nj] = Q.k[l]; NT[nj] = Q.tk_nt[l]; nch[nj] = Q.tk_chunks[l]; dst[nj] = prepared + Q.tk[l]; ++nj;
       if (l >= 1) {  // W^T images: rows = input feature k, reduction = output feature n
-        rc = launch_pack_umma_tiles(params + P.w[l], 1, Q.k[l], nullptr, Q.k[l], Q.n[l], Q.tkt_nt[l], Q.tkt_chunks[l],
-                                    prepared + Q.tkt[l], st);
-        if (rc) return rc;
+        W[nj] = params + P.w[l]; ldn[nj] = 1; ldk[nj] = Q.k[l]; sc[nj] = nullptr; N[nj] = Q.k[l]; K[nj] = Q.n[l];
+        NT[nj] = Q.tkt_nt[l]; nch[nj] = Q.tkt_chunks[l]; dst[nj] = prepared + Q.tkt[l]; ++nj;
       }
     }
+    rc = launch_pack_umma_jobs(nj, W, ldn, ldk, sc, N, K, NT, nch, dst, st);
+    if (rc) return rc;
   }
   if (Q.fz_ok) return launch_fused_pack(d, P, Q, params, prepared, st);
   return HB_OK;

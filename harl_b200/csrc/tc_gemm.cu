@@ -126,6 +126,51 @@ int launch_pack_umma_tiles(const float* W, int ldn, int ldk, const float* scale,
   return HB_OK;
 }
 
+// All images of one net in ONE launch (blockIdx.y = job): hb_net_prepare runs after every optimiser step, and three
+// 3-6 us launches per net were 2 % of the C2 update phase.
+struct PackUmmaJobs {
+  const float* W[2 * HB_MAX_LAYERS];
+  const float* scale[2 * HB_MAX_LAYERS];
+  float* dst[2 * HB_MAX_LAYERS];
+  int ldn[2 * HB_MAX_LAYERS], ldk[2 * HB_MAX_LAYERS], N[2 * HB_MAX_LAYERS], K[2 * HB_MAX_LAYERS], NT[2 * HB_MAX_LAYERS],
+      nchunks[2 * HB_MAX_LAYERS];
+};
+__global__ void pack_umma_jobs_kernel(const __grid_constant__ PackUmmaJobs J) {
+  const int j = blockIdx.y;
+  const float* __restrict__ W = J.W[j];
+  const float* __restrict__ scale = J.scale[j];
+  float* __restrict__ dst = J.dst[j];
+  const int NT = J.NT[j], N = J.N[j], K = J.K[j], ldn = J.ldn[j], ldk = J.ldk[j];
+  const int per_chunk = 2 * NT * TC_KC;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < J.nchunks[j] * NT * TC_KC; i += gridDim.x * blockDim.x) {
+    const int c = i / (NT * TC_KC), e = i % (NT * TC_KC);
+    const int k4 = e & 3, n8 = (e >> 2) & 7, kc = (e >> 5) & 7, ng = e >> 8;
+    const int n = ng * 8 + n8, k = c * TC_KC + kc * 4 + k4;
+    float v = 0.f;
+    if (n < N && k < K) { v = W[(int64_t)n * ldn + (int64_t)k * ldk]; if (scale) v *= scale[k]; }
+    const float hi = tf32_hi(v);
+    dst[(int64_t)c * per_chunk + e] = hi;
+    dst[(int64_t)c * per_chunk + NT * TC_KC + e] = tf32_lo(v, hi);
+  }
+}
+
+// jobs: (W, ldn, ldk, scale, N, K, NT, nchunks, dst) x njobs
+int launch_pack_umma_jobs(int njobs, const float* const* W, const int* ldn, const int* ldk, const float* const* scale, const int* N,
+                          const int* K, const int* NT, const int* nchunks, float* const* dst, cudaStream_t st) {
+  if (njobs <= 0) return HB_OK;
+  PackUmmaJobs J;
+  int most = 0;
+  for (int j = 0; j < njobs; ++j) {
+    J.W[j] = W[j]; J.scale[j] = scale[j]; J.dst[j] = dst[j]; J.ldn[j] = ldn[j]; J.ldk[j] = ldk[j]; J.N[j] = N[j]; J.K[j] = K[j];
+    J.NT[j] = NT[j]; J.nchunks[j] = nchunks[j];
+    const int total = nchunks[j] * NT[j] * TC_KC;
+    most = total > most ? total : most;
+  }
+  pack_umma_jobs_kernel<<<dim3((most + 255) / 256, njobs), 256, 0, st>>>(J);
+  HB_LAUNCH_DONE(st, "pack_umma_tiles");
+  return HB_OK;
+}
+
 // ------------------------------------------------------------------ forward block on tcgen05
 template <int NT>
 struct TcSmem {
