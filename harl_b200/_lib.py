@@ -164,6 +164,8 @@ SIGNATURES = {
     "hb_policy_evaluate": (C.c_int, [C.POINTER(NetDesc), P, C.POINTER(ActorBatch), P, P, P, C.c_int, P, C.c_size_t, P]),
     "hb_ppo_actor_grad": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(ActorBatch), C.POINTER(PPOHyper), P, P, P, P,
                                     C.c_size_t, P]),
+    "hb_ppo_actor_grad_logp": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(ActorBatch), C.POINTER(PPOHyper), P, P, P, P, P,
+                                         C.c_size_t, P]),
     "hb_value_grad": (C.c_int, [C.POINTER(NetDesc), P, P, C.POINTER(CriticBatch), C.POINTER(ValueHyper), P,
                                 C.c_double, P, P, P, C.c_size_t, P]),
     "hb_clip_adam_step": (C.c_int, [C.POINTER(NetDesc), P, P, P, P, P, C.POINTER(AdamHyper), P, P]),

@@ -27,13 +27,15 @@ class HAPPO(OnPolicyBase):
         self.use_max_grad_norm = args["use_max_grad_norm"]
         self.max_grad_norm = args["max_grad_norm"]
 
+    first_epoch_logp = True   # train(old_logp_out=...) is supported
+
     def _hyper(self):
         return L.PPOHyper(float(self.clip_param), float(self.entropy_coef), int(bool(self.use_policy_active_masks)),
                           int(self.action_aggregation == "prod"), int(self.use_clip))
 
-    def _step(self, batch, norm3, scalars_row):
+    def _step(self, batch, norm3, scalars_row, logp_out=None):
         """One update on a device batch: grad -> (allreduce) -> clip + Adam. Returns nothing (async)."""
-        self.actor.actor_grad(batch, self._hyper(), norm3, scalars_row)
+        self.actor.actor_grad(batch, self._hyper(), norm3, scalars_row, logp_out)
         dist.all_reduce_sum_(self.actor.grad)
         self.actor.adam_step(self.cur_lr, self.opti_eps, self.weight_decay, self.max_grad_norm, self.use_max_grad_norm)
 
@@ -63,8 +65,14 @@ class HAPPO(OnPolicyBase):
         s, n = scal.cpu().numpy(), norm3[2].item()
         return s[0] / n, s[1] / n, self.actor.grad_norm.item(), s[2] / s[3]
 
-    def train(self, actor_buffer, advantages, state_type):
-        """Reference happo.py:104-158.  ``advantages``: [T, N, 1] (tensor on the device or NumPy)."""
+    def train(self, actor_buffer, advantages, state_type, moments=None, old_logp_out=None):
+        """Reference happo.py:104-158.  ``advantages``: [T, N, 1] (tensor on the device or NumPy).
+
+        ``old_logp_out`` [T*N, ad]: filled with the log-probs of the buffer's actions under the PRE-update weights by the
+        forward of the first epoch (whole-buffer minibatch only; see ``first_epoch_logp``) -- what the sequential-update
+        runner otherwise obtains from a separate evaluate sweep (on_policy_ha_runner.py:66-83).  ``self.old_logp_filled``
+        says whether that happened."""
+        self.old_logp_filled = False
         info = dict(policy_loss=0.0, dist_entropy=0.0, actor_grad_norm=0.0, ratio=0.0)
         d = self.device
         buf = actor_buffer
@@ -72,10 +80,13 @@ class HAPPO(OnPolicyBase):
         rows = T * N
         adv = to_device(advantages, d).reshape(rows)
         active = buf.active_masks[:-1].reshape(rows)
-        m3 = torch.zeros(3, dtype=torch.float64, device=d)
-        L.call("hb_masked_moments", L.ptr(adv), L.ptr(active), rows, L.ptr(m3), L.stream_ptr())
-        dist.all_reduce_sum_(m3)
-        n_active = m3[2].item()  # the one host read before the update loop (reference early-out, happo.py:119)
+        if moments is not None:   # (device double[3], host count): computed for all agents at once by the runner
+            m3, n_active = moments
+        else:
+            m3 = torch.zeros(3, dtype=torch.float64, device=d)
+            L.call("hb_masked_moments", L.ptr(adv), L.ptr(active), rows, L.ptr(m3), L.stream_ptr())
+            dist.all_reduce_sum_(m3)
+            n_active = m3[2].item()  # the one host read before the update loop (reference early-out, happo.py:119)
         if n_active == 0:
             return info
         if state_type == "EP":
@@ -110,7 +121,9 @@ class HAPPO(OnPolicyBase):
                     dist.all_reduce_sum_(norms[u])
                 batch = DeviceNet.actor_batch(obs, actions, old_lp, adv, factor, active, avail, idx, nrows,
                                               rnn_states=rnn, masks=masks, seq_len=seq_len)
-                self._step(batch, norms[u], scal[u])
+                first = u == 0 and old_logp_out is not None and (idx is None) and nrows == rows
+                self._step(batch, norms[u], scal[u], old_logp_out if first else None)
+                self.old_logp_filled = self.old_logp_filled or first
                 gnorm[u] = self.actor.grad_norm[0]
                 u += 1
         dist.all_reduce_sum_(scal)

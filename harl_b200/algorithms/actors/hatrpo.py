@@ -148,7 +148,7 @@ class HATRPO(OnPolicyBase):
         c = cnt.cpu().numpy()
         return self._update_on_batch(batch, float(c[0]), float(c[1]))
 
-    def train(self, actor_buffer, advantages, state_type):
+    def train(self, actor_buffer, advantages, state_type, moments=None):
         """Reference hatrpo.py:196-247: one update on the whole buffer."""
         info = dict(kl=0.0, dist_entropy=0.0, loss_improve=0.0, expected_improve=0.0, ratio=0.0)
         d = self.device
@@ -157,10 +157,13 @@ class HATRPO(OnPolicyBase):
         rows = T * N
         adv = to_device(advantages, d).reshape(rows)
         active = buf.active_masks[:-1].reshape(rows)
-        m3 = torch.zeros(3, dtype=torch.float64, device=d)
-        L.call("hb_masked_moments", L.ptr(adv), L.ptr(active), rows, L.ptr(m3), L.stream_ptr())
-        dist.all_reduce_sum_(m3)
-        n_active = m3[2].item()
+        if moments is not None:   # (device double[3], host count): computed for all agents at once by the runner
+            m3, n_active = moments
+        else:
+            m3 = torch.zeros(3, dtype=torch.float64, device=d)
+            L.call("hb_masked_moments", L.ptr(adv), L.ptr(active), rows, L.ptr(m3), L.stream_ptr())
+            dist.all_reduce_sum_(m3)
+            n_active = m3[2].item()
         if n_active == 0:
             return info
         if state_type == "EP":

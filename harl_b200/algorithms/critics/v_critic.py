@@ -71,13 +71,19 @@ class VCritic:
                             int(bool(self.use_huber_loss)), int(bool(self.use_clipped_value_loss)))
 
     def _step(self, share_obs, value_preds, returns, index, rows, global_rows, value_normalizer, scalars_row,
-              rnn_states=None, masks=None, seq_len=0):
+              rnn_states=None, masks=None, seq_len=0, whole=None):
         d = self.device
         if value_normalizer is not None:
-            m3 = torch.zeros(3, dtype=torch.float64, device=d)
-            src = returns if index is None else returns[index.long()]
-            L.call("hb_masked_moments", L.ptr(src.contiguous()), None, rows, L.ptr(m3), L.stream_ptr())
-            dist.all_reduce_sum_(m3)
+            # ValueNorm.update(return_batch) runs in every update (v_critic.py:93-96 via cal_value_loss); when the minibatch
+            # is the whole buffer its batch moments are the same in every epoch: computed and exchanged once per train()
+            m3 = whole.get("m3") if whole is not None and index is None else None
+            if m3 is None:
+                m3 = torch.zeros(3, dtype=torch.float64, device=d)
+                src = returns if index is None else returns[index.long()]
+                L.call("hb_masked_moments", L.ptr(src.contiguous()), None, rows, L.ptr(m3), L.stream_ptr())
+                dist.all_reduce_sum_(m3)
+                if whole is not None and index is None:
+                    whole["m3"] = m3
             value_normalizer.update_from_moments(m3)
         cb = DeviceNet.critic_batch(share_obs, value_preds, returns, index, rows, rnn_states, masks, seq_len)
         vn = value_normalizer.state if value_normalizer is not None else None
@@ -125,9 +131,10 @@ class VCritic:
         scal = torch.zeros(n_up, 4, dtype=torch.float64, device=d)
         gnorm = torch.zeros(n_up, dtype=torch.float32, device=d)
         u = 0
+        whole = {}
         for _ in range(self.critic_epoch):
             for idx, n, seq_len in seq_index.minibatches(T, Cn, nmb, mode, self.data_chunk_length, d):
-                self._step(so, vp, rt, idx, n, float(n * dist.world_size()), value_normalizer, scal[u], rnn, masks, seq_len)
+                self._step(so, vp, rt, idx, n, float(n * dist.world_size()), value_normalizer, scal[u], rnn, masks, seq_len, whole)
                 gnorm[u] = self.critic.grad_norm[0]
                 u += 1
         dist.all_reduce_sum_(scal)

@@ -394,9 +394,16 @@ int hb_policy_evaluate(const hb_net_desc* d, const float* prepared, const hb_act
 int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* prepared, const hb_actor_batch* b,
                       const hb_ppo_hyper* h, const double* norm3, float* grad, double* scalars, void* ws,
                       size_t ws_bytes, void* stream) {
+  return hb_ppo_actor_grad_logp(d, params, prepared, b, h, norm3, grad, scalars, nullptr, ws, ws_bytes, stream);
+}
+
+int hb_ppo_actor_grad_logp(const hb_net_desc* d, const float* params, const float* prepared, const hb_actor_batch* b,
+                           const hb_ppo_hyper* h, const double* norm3, float* grad, double* scalars, float* logp_out, void* ws,
+                           size_t ws_bytes, void* stream) {
   using namespace hb;
   HB_CHECK_ARG(params && prepared && b && h && norm3 && grad && scalars, "NULL argument");
   HB_CHECK_ARG(b->obs && b->actions && b->old_logp && b->adv && b->active && b->rows >= 0, "incomplete batch");
+  HB_CHECK_ARG(!logp_out || !b->index, "logp_out needs an identity batch (rows of the batch = rows of logp_out)");
   ParamLayout P;
   PrepLayout Q;
   hb_net_layout L;
@@ -414,9 +421,14 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
     fa.clip = h->clip_param; fa.entropy_coef = h->entropy_coef; fa.use_active = h->use_policy_active_masks;
     fa.use_clip = h->use_clip; fa.agg_prod = h->action_aggregation_prod;
     fa.part = (float*)ws; fa.part_stride = L.total; fa.scalars = scalars;
+    fa.logp_out = logp_out;
     int slots = 0;
     if ((rc = launch_fused_update(d, Q, P, prepared, fa, 0, &slots, st))) return rc;
     return launch_fused_finish(d, P, params, grad, (const float*)ws, slots, L.total, norm3, 1.0, st);
+  }
+  if (logp_out && b->rows > 0) {  // layer-wise kernels: a separate forward sweep writes the log-probs
+    rc = hb_policy_evaluate(d, prepared, b, logp_out, nullptr, nullptr, h->action_aggregation_prod, ws, ws_bytes, stream);
+    if (rc) return rc;
   }
   cudaError_t ce = cudaMemsetAsync(grad, 0, (size_t)L.total * sizeof(float), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "hb_ppo_actor_grad(memset)");

@@ -691,6 +691,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
             float m;
             const float dm = dmin_dratio(ratio, adv, a.clip, a.use_clip, &m);
             const float okf = ok ? 1.f : 0.f;
+            if (ok && a.logp_out) a.logp_out[row] = lpa;     // the log-probs under the weights of this pass, for free
             const float c_lp = -fac * w * dm * ratio * okf;
             const float c_h = a.entropy_coef * w * okf;
             if (ok) { s_loss += -fac * m * w; s_ent += ent * w; s_ratio += ratio; s_rows += 1.f; }
@@ -731,6 +732,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
             }
           } else {
             const float w = in_w, fac = in_fac, adv = in_adv;
+            if (ok && a.logp_out) {
+#pragma unroll
+              for (int j = 0; j < NH; ++j)
+                if (j < na) a.logp_out[row * na + j] = lpj[j];
+            }
             float e[NH];
             float ratio = a.agg_prod ? 1.f : 0.f;
 #pragma unroll
@@ -1176,44 +1182,55 @@ __global__ void __launch_bounds__(256) fused_pack_kernel(PackJobs jobs) {
     img[chunk0 + e] = hi;
     img[chunk0 + (size_t)Nimg * kc + e] = lo;
   }
-  if (cta == 0 && J.bias_out != nullptr) {
-    for (int n = threadIdx.x; n < Nimg; n += 256) {
+  if (J.bias_out != nullptr) {   // b' = b + W beta: one warp per output row (coalesced reads of the row), rows over the job's CTAs
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = cta * 8 + warp; n < Nimg; n += J.ctas * 8) {
       float v = 0.f;
-      if (n < N) {
-        v = J.b[n];
-        if (J.beta)
-          for (int k = 0; k < K; ++k) v += W[n * K + k] * J.beta[k];
-      }
-      J.bias_out[n] = v;
+      if (n < N && J.beta)
+        for (int k = lane; k < K; k += 32) v += W[n * K + k] * J.beta[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) J.bias_out[n] = n < N ? J.b[n] + v : 0.f;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ slot reduction
 struct Regions { int n; int off[8]; int len[8]; float scale[8]; };
-// grad[i] = scale_i * norm * sum over the CTA slots (coalesced across threads, 16 independent loads in flight per thread)
-__global__ void __launch_bounds__(128) fused_slot_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int slots,
-                                                                long long stride, int total, Regions R, const double* __restrict__ norm3,
-                                                                double host_scale) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+// grad[i] = scale_i * norm * sum over the CTA slots.  A CTA owns 32 consecutive parameters; warp g sums slot group g (every load
+// of a warp is one coalesced 128-byte line, all <= 24 loads of a thread in flight at once), the groups are added in order by
+// warp 0: deterministic, and one memory round trip instead of slots / 16.
+constexpr int SR_GROUPS = 8, SR_MAXPER = 24;
+__global__ void __launch_bounds__(32 * SR_GROUPS) fused_slot_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int slots,
+                                                                           long long stride, int total, const __grid_constant__ Regions R,
+                                                                           const double* __restrict__ norm3, double host_scale) {
+  __shared__ float sm[SR_GROUPS][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int per = (slots + SR_GROUPS - 1) / SR_GROUPS;
+  const int s0 = g * per, s1 = s0 + per < slots ? s0 + per : slots;
+  float acc = 0.f;
+  if (i < total) {
+    for (int sb = s0; sb < s1; sb += SR_MAXPER) {
+      float v[SR_MAXPER];
+#pragma unroll
+      for (int u = 0; u < SR_MAXPER; ++u) v[u] = sb + u < s1 ? part[(long long)(sb + u) * stride + i] : 0.f;
+#pragma unroll
+      for (int u = 0; u < SR_MAXPER; ++u) acc += v[u];
+    }
+  }
+  sm[g][lane] = acc;
+  __syncthreads();
+  if (g != 0 || i >= total) return;
   float sc = 0.f;
   bool in = false;
   for (int q = 0; q < R.n; ++q)
     if (i >= R.off[q] && i < R.off[q] + R.len[q]) { sc = R.scale[q]; in = true; }
   if (!in) { grad[i] = 0.f; return; }
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int s = 0;
-  for (; s + 16 <= slots; s += 16) {
-    float v[16];
+  float t = 0.f;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = part[(long long)(s + u) * stride + i];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) acc[u & 3] += v[u];
-  }
-  for (; s < slots; ++s) acc[0] += part[(long long)s * stride + i];
+  for (int q = 0; q < SR_GROUPS; ++q) t += sm[q][lane];
   const double nrm = host_scale * (norm3 ? 1.0 / norm3[2] : 1.0);
-  grad[i] = (float)((double)((acc[0] + acc[1]) + (acc[2] + acc[3])) * (double)sc * nrm);
+  grad[i] = (float)((double)t * (double)sc * nrm);
 }
 
 // LayerNorm-affine unfolding for every consumer (layer 0 / layer 1 / head) in one launch: one warp per input column k.
@@ -1417,7 +1434,7 @@ int launch_fused_finish(const hb_net_desc* d, const ParamLayout& P, const float*
   add(P.hw, d->out_dim * H, sw);  add(P.hbias, d->out_dim, sb);
   if (d->head == HB_HEAD_BOX) add(P.log_std, d->out_dim, sb);
   R.n = n;
-  fz::fused_slot_reduce_kernel<<<(P.total + 127) / 128, 128, 0, st>>>(grad, part, slots, stride, P.total, R, norm3, host_scale);
+  fz::fused_slot_reduce_kernel<<<(P.total + 31) / 32, 32 * fz::SR_GROUPS, 0, st>>>(grad, part, slots, stride, P.total, R, norm3, host_scale);
   HB_LAUNCH_DONE(st, "fused_slot_reduce");
   fz::Folds F;
   memset(&F, 0, sizeof(F));

@@ -240,11 +240,13 @@ class DeviceNet:
         L.call("hb_policy_evaluate", C.byref(self.desc), L.ptr(self.prepared), C.byref(batch), L.ptr(logp_out),
                L.ptr(logp_ref), L.ptr(factor_inout), int(bool(agg_prod)), L.ptr(ws), n, L.stream_ptr())
 
-    def actor_grad(self, batch, hyper, norm3, scalars):
+    def actor_grad(self, batch, hyper, norm3, scalars, logp_out=None):
+        """PPO-clip gradient of the batch into ``self.grad``; ``logp_out`` [rows, ad] (identity batches) also receives the
+        log-probs of the batch actions under the current weights (hb_ppo_actor_grad_logp)."""
         self._need_cuda()
         ws, n = self._ws(batch.rows, 1)
-        L.call("hb_ppo_actor_grad", C.byref(self.desc), L.ptr(self.params), L.ptr(self.prepared), C.byref(batch),
-               C.byref(hyper), L.ptr(norm3), L.ptr(self.grad), L.ptr(scalars), L.ptr(ws), n, L.stream_ptr())
+        L.call("hb_ppo_actor_grad_logp", C.byref(self.desc), L.ptr(self.params), L.ptr(self.prepared), C.byref(batch),
+               C.byref(hyper), L.ptr(norm3), L.ptr(self.grad), L.ptr(scalars), L.ptr(logp_out), L.ptr(ws), n, L.stream_ptr())
 
     def value_grad(self, batch, hyper, vn_state, inv_count, scalars):
         self._need_cuda()

@@ -53,6 +53,15 @@ class OnPolicyHARunner(OnPolicyBaseRunner):
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 critic_pending = self.critic.train(cb, self.value_normalizer, defer=True)
+        # masked advantage moments of every agent (happo.py:119-127: nanmean / nanstd over the agent's active steps) do not
+        # depend on the sequential updates: one [A, 3] bucket, one exchange, one host read instead of one per agent
+        adv_m3 = torch.zeros(self.num_agents, 3, dtype=torch.float64, device=dev)
+        for a in range(self.num_agents):
+            adv_a = advantages if self.state_type == "EP" else advantages[:, :, a].contiguous()
+            L.call("hb_masked_moments", L.ptr(adv_a), L.ptr(self.actor_buffer[a].active_masks[:-1]), rows, L.ptr(adv_m3[a]),
+                   L.stream_ptr())
+        dist.all_reduce_sum_(adv_m3)
+        n_active = adv_m3[:, 2].cpu().numpy()
         for agent_id in agent_order:
             buf, actor = self.actor_buffer[agent_id], self.actor[agent_id]
             buf.update_factor(factor)
@@ -65,9 +74,18 @@ class OnPolicyHARunner(OnPolicyBaseRunner):
             else:
                 sweep = DeviceNet.actor_batch(fl(buf.obs[:-1]), fl(buf.actions), avail=avail)
             old_logp = torch.empty(rows, actor.actor.act_width, dtype=torch.float32, device=dev)
-            actor.actor.evaluate(sweep, logp_out=old_logp)                       # :66-83
             adv_a = advantages if self.state_type == "EP" else advantages[:, :, agent_id].contiguous()
-            infos.append(actor.train(buf, adv_a, self.state_type))               # :86-93
+            # :66-83 evaluates the buffer under the pre-update weights = the weights of the first PPO epoch, whose forward
+            # (same rows, same order, when the minibatch is the whole buffer) writes those log-probs on its way
+            fuse = (getattr(actor, "first_epoch_logp", False) and not actor.recurrent and getattr(actor, "actor_num_mini_batch", 0) == 1
+                    and n_active[agent_id] > 0 and getattr(self, "fuse_old_logp", True))
+            if not fuse:
+                actor.actor.evaluate(sweep, logp_out=old_logp)                   # :66-83
+                infos.append(actor.train(buf, adv_a, self.state_type, moments=(adv_m3[agent_id], float(n_active[agent_id]))))  # :86-93
+            else:
+                infos.append(actor.train(buf, adv_a, self.state_type, moments=(adv_m3[agent_id], float(n_active[agent_id])),
+                                         old_logp_out=old_logp))
+                assert actor.old_logp_filled
             actor.actor.evaluate(sweep, logp_ref=old_logp, factor_inout=factor.reshape(rows), agg_prod=agg_prod)  # :96-124
         if critic_pending is not None:
             torch.cuda.current_stream(dev).wait_stream(self._side_stream)

@@ -300,6 +300,14 @@ int hb_ppo_actor_grad(const hb_net_desc* d, const float* params, const float* pr
                       const hb_actor_batch* b, const hb_ppo_hyper* h, const double* norm3,
                       float* grad, double* scalars, void* ws, size_t ws_bytes, void* stream);
 
+/* hb_ppo_actor_grad that also writes the log-probabilities of the batch actions under the weights it differentiates
+ * (logp_out [rows, ad], identity batches only; NULL = plain hb_ppo_actor_grad).  The sequential update needs exactly
+ * these numbers for the agent it is about to train -- on_policy_ha_runner.py:66-83 evaluates the whole buffer with the
+ * pre-update weights, which are the weights of the first PPO epoch -- so the forward of that epoch serves both. */
+int hb_ppo_actor_grad_logp(const hb_net_desc* d, const float* params, const float* prepared, const hb_actor_batch* b,
+                           const hb_ppo_hyper* h, const double* norm3, float* grad, double* scalars, float* logp_out,
+                           void* ws, size_t ws_bytes, void* stream);
+
 typedef struct hb_value_hyper { /* happo.yaml algo.*: VCritic, v_critic.py:24-37 */
   float clip_param;
   float huber_delta;

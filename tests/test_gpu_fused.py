@@ -216,3 +216,48 @@ def test_fused_kernel_is_what_runs_by_default():
     n = L.lib.hb_profile_end(buf, len(buf))
     labels = buf.raw[:max(n, 0)].decode()
     assert "fused_actor_update" in labels and "tc_linear_ln_fwd" not in labels, labels
+
+
+@pytest.mark.parametrize("head,out,fused", [("Discrete", 5, 1), ("Box", 3, 1), ("Discrete", 5, 0)])
+def test_grad_pass_also_returns_the_log_probs_of_its_forward(head, out, fused):
+    """hb_ppo_actor_grad_logp: the log-probs written by the gradient pass equal a separate evaluate sweep under the same
+    weights (the sequential-update runner uses them as the pre-update log-probs, on_policy_ha_runner.py:66-83), and the
+    gradient itself is unchanged by asking for them."""
+    from harl_b200 import _lib as L
+    from harl_b200.nets import DeviceNet
+
+    od, rows = 18, 1000
+    net = _net(128, "relu", od, head, out, 23)
+    g = torch.Generator().manual_seed(29)
+    cu = lambda t: t.cuda().contiguous()
+    obs = cu(torch.randn(rows, od, generator=g))
+    ad = 1 if head == "Discrete" else out
+    if head == "Discrete":
+        actions = cu(torch.randint(0, out, (rows, 1), generator=g).float())
+        avail = (torch.rand(rows, out, generator=g) < 0.8).float()
+        avail[torch.arange(rows), actions[:, 0].long().cpu()] = 1.0
+        avail = cu(avail)
+    else:
+        actions, avail = cu(0.2 * torch.randn(rows, out, generator=g)), None
+    old = cu(-1.5 + 0.1 * torch.randn(rows, ad, generator=g))
+    adv, active = cu(torch.randn(rows, generator=g)), cu((torch.rand(rows, generator=g) < 0.9).float())
+    batch = DeviceNet.actor_batch(obs, actions, old, adv, None, active, avail)
+    hyper = L.PPOHyper(0.2, 0.01, 1, 1, 1)
+    norm3 = torch.tensor([0.0, 0.0, float(active.sum())], dtype=torch.float64, device="cuda")
+    L.call("hb_set_fused_update", fused)
+    try:
+        scal = torch.zeros(4, dtype=torch.float64, device="cuda")
+        net.actor_grad(batch, hyper, norm3, scal)
+        g_plain = net.grad.clone()
+        lp = torch.full((rows, ad), float("nan"), device="cuda")
+        scal2 = torch.zeros(4, dtype=torch.float64, device="cuda")
+        net.actor_grad(batch, hyper, norm3, scal2, logp_out=lp)
+        g_with = net.grad.clone()
+        ref = torch.empty(rows, ad, device="cuda")
+        net.evaluate(DeviceNet.actor_batch(obs, actions, avail=avail), logp_out=ref)
+        torch.cuda.synchronize()
+    finally:
+        L.call("hb_set_fused_update", 1)
+    np.testing.assert_allclose(g_with.cpu().numpy(), g_plain.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(scal2.cpu().numpy(), scal.cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(lp.cpu().numpy(), ref.cpu().numpy(), rtol=1e-6, atol=1e-6)
