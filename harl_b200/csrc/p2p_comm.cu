@@ -10,9 +10,10 @@
 // Protocol (every rank runs the same kernel, `seq` = number of exchanges on this communicator so far + 1):
 //   1. each CTA copies its part of the local bucket into this rank's slot `seq & 1` of a cudaMalloc'ed region that
 //      every peer has mapped through CUDA IPC; the last CTA to finish (device counter) publishes `seq` into flag
-//      [rank] of EVERY peer's flag array with a system-scope release store;
+//      [rank] of EVERY peer's flag array with system-scope release stores, one thread per peer (in parallel);
 //   2. every CTA spins (system-scope acquire loads, bounded by a clock64 budget) until its own flag array shows
-//      `seq` for all ranks, then reads all `world` slots straight out of peer memory and adds them IN RANK ORDER --
+//      `seq` for all ranks, then reads all `world` slots straight out of peer memory (all loads of an element in flight
+//      together: one NVLink round trip) and adds them IN RANK ORDER --
 //      every rank computes the bit-identical sum, so the replicas never drift;
 //   3. no trailing barrier: slots are double-buffered by `seq & 1`, and a rank can only overwrite slot parity p again
 //      at seq + 2, which it reaches only after every peer has published seq + 1, i.e. finished reading seq.
@@ -24,7 +25,7 @@
 namespace hb {
 
 constexpr int COMM_MAX_WORLD = 16;
-constexpr int COMM_GRID = 16;        // fixed: the arrival counter assumes it
+constexpr int COMM_GRID = 16;        // CTAs for a gradient-sized bucket (small buckets use fewer)
 constexpr int COMM_THREADS = 512;
 constexpr size_t COMM_HEADER = 4096;  // flags[COMM_MAX_WORLD] (u32), arrival counter (u64), error word
 
@@ -63,27 +64,31 @@ __global__ void __launch_bounds__(COMM_THREADS) allreduce_oneshot_kernel(const _
                                                                          long long spin_budget, int* err) {
   unsigned char* mine = peers.p[rank];
   uint32_t* flags = reinterpret_cast<uint32_t*>(mine);
-  unsigned long long* arrive = reinterpret_cast<unsigned long long*>(mine + 256);
+  unsigned int* arrive = reinterpret_cast<unsigned int*>(mine + 256);
   const size_t slot_off = COMM_HEADER + (size_t)(seq & 1u) * slot_bytes;
   T* my_slot = reinterpret_cast<T*>(mine + slot_off);
   const int64_t nv = n / VN;
-  const int64_t tid = (int64_t)blockIdx.x * COMM_THREADS + threadIdx.x, stride = (int64_t)COMM_GRID * COMM_THREADS;
+  const int64_t tid = (int64_t)blockIdx.x * COMM_THREADS + threadIdx.x, stride = (int64_t)gridDim.x * COMM_THREADS;
+  __shared__ int s_last, s_ok;
   // ---- 1. publish the local bucket
   for (int64_t i = tid; i < nv; i += stride) reinterpret_cast<V*>(my_slot)[i] = reinterpret_cast<const V*>(buf)[i];
   for (int64_t i = nv * VN + tid; i < n; i += stride) my_slot[i] = buf[i];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned long long got = atomicAdd(arrive, 1ull) + 1ull;
-    if (got == (unsigned long long)seq * COMM_GRID) {   // last CTA of this exchange: every CTA's slot writes are fenced
-      __threadfence_system();
-      for (int r = 0; r < world; ++r) st_release_sys(reinterpret_cast<uint32_t*>(peers.p[r]) + rank, seq);
+    s_ok = 1;
+    const unsigned int got = atomicAdd(arrive, 1u) + 1u;
+    s_last = got == gridDim.x;
+    if (s_last) {                       // every CTA of this exchange has arrived; the next exchange is a later kernel on the stream
+      *arrive = 0;
+      __threadfence_system();           // acquire side of the other CTAs' fence + arrive: their slot writes precede our flag stores
     }
   }
-  // ---- 2. wait for every rank's flag, then sum the slots in rank order
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) s_ok = 1;
   __syncthreads();
+  if (s_last && threadIdx.x < world) {  // last CTA: all slot writes are fenced; the flags of all peers go out in parallel
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.p[threadIdx.x]) + rank, seq);
+  }
+  // ---- 2. wait for every rank's flag, then sum the slots in rank order
   if (threadIdx.x < world) {
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - seq) < 0) {
@@ -92,21 +97,33 @@ __global__ void __launch_bounds__(COMM_THREADS) allreduce_oneshot_kernel(const _
         *err = 1 + (int)threadIdx.x;     // which rank never arrived
         break;
       }
-      __nanosleep(20);
     }
   }
   __syncthreads();
   if (!s_ok) return;                     // the host sees *err; the bucket is left unreduced
+  // all `world` peer loads of an element are issued before the first add: one NVLink round trip, not `world` of them
   for (int64_t i = tid; i < nv; i += stride) {
-    V acc = ld_peer(reinterpret_cast<const V*>(peers.p[0] + slot_off) + i);
-    for (int r = 1; r < world; ++r) {
-      acc_add(acc, ld_peer(reinterpret_cast<const V*>(peers.p[r] + slot_off) + i));
-    }
+    V x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) x[r] = ld_peer(reinterpret_cast<const V*>(peers.p[r] + slot_off) + i);
+    V acc = x[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+      if (r < world) acc_add(acc, x[r]);
+    for (int r = 8; r < world; ++r) acc_add(acc, ld_peer(reinterpret_cast<const V*>(peers.p[r] + slot_off) + i));
     reinterpret_cast<V*>(buf)[i] = acc;
   }
   for (int64_t i = nv * VN + tid; i < n; i += stride) {
-    T acc = __ldcv(reinterpret_cast<const T*>(peers.p[0] + slot_off) + i);
-    for (int r = 1; r < world; ++r) acc += __ldcv(reinterpret_cast<const T*>(peers.p[r] + slot_off) + i);
+    T x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < world) x[r] = __ldcv(reinterpret_cast<const T*>(peers.p[r] + slot_off) + i);
+    T acc = x[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+      if (r < world) acc += x[r];
+    for (int r = 8; r < world; ++r) acc += __ldcv(reinterpret_cast<const T*>(peers.p[r] + slot_off) + i);
     buf[i] = acc;
   }
 }
@@ -170,7 +187,10 @@ int hb_allreduce_bucket(void* comm, void* buf, int64_t n, int32_t dtype, void* s
   const uint32_t seq = ++c->seq;
   static const long long budget = (long long)(getenv("HB_COMM_TIMEOUT_S") ? atof(getenv("HB_COMM_TIMEOUT_S")) : 20.0) * 1900000000ll;
   cudaStream_t st = (cudaStream_t)stream;
-#define HB_AR(T, V, VN) allreduce_oneshot_kernel<T, V, VN><<<COMM_GRID, COMM_THREADS, 0, st>>>(peers, (T*)buf, n, c->rank, c->world, seq, \
+  const int64_t per_cta = (int64_t)COMM_THREADS * (16 / (dtype == 0 ? 4 : 8));   // one 16-byte vector per thread
+  int grid = (int)((n + per_cta - 1) / per_cta);
+  grid = grid < 1 ? 1 : (grid > COMM_GRID ? COMM_GRID : grid);
+#define HB_AR(T, V, VN) allreduce_oneshot_kernel<T, V, VN><<<grid, COMM_THREADS, 0, st>>>(peers, (T*)buf, n, c->rank, c->world, seq, \
                                                                                               c->slot_bytes, budget, c->dev_err)
   if (dtype == 0) { if (vec) HB_AR(float, float4, 4); else HB_AR(float, float, 1); }
   else            { if (vec) HB_AR(double, double2, 2); else HB_AR(double, double, 1); }

@@ -21,8 +21,9 @@ FORCE_SINGLE = False
 
 P2P_SLOT_BYTES = 1 << 20          # gradients of the supported nets are <= 0.5 MB; larger buckets go through NCCL
 _comms = {}                       # cuda stream handle -> communicator (or None when peer mapping failed)
-_p2p_off = os.environ.get("HB_P2P_ALLREDUCE", "1") == "0"
-stats = {"p2p": 0, "nccl": 0}     # exchanges issued by this process, by transport
+_p2p_mode = os.environ.get("HB_P2P_ALLREDUCE", "auto")   # "1": always the one-shot kernel, "0": always NCCL, "auto": the faster
+_p2p_off = _p2p_mode == "0"
+stats = {"p2p": 0, "nccl": 0}     # exchanges issued by this process, by transport; "calibration" once measured
 
 
 def is_dist():
@@ -67,7 +68,45 @@ def _comm_for_current_stream(device):
     torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)   # all ranks or none
     torch.cuda.synchronize(device)
     _comms[key] = handle if int(ok.item()) else None
+    if _comms[key] is not None and _p2p_mode == "auto":
+        _calibrate(device, _comms[key])
     return _comms[key]
+
+
+def _calibrate(device, comm):
+    """Measure, don't guess: time a gradient-sized bucket and a 3-double normaliser through both transports on this box
+    (CUDA events around 40 back-to-back exchanges, max over ranks) and keep the one-shot kernel only if it is not slower.
+    Runs once per process, the first time a stream exchanges something; all ranks take the same decision."""
+    global _p2p_off
+    if "calibration" in stats:
+        return
+    from . import _lib as L
+
+    res = {}
+    for name, t in (("grad_100KB", torch.zeros(25000, device=device)), ("moments_24B", torch.zeros(3, dtype=torch.float64, device=device))):
+        for transport in ("p2p", "nccl"):
+            def fn():
+                if transport == "p2p":
+                    L.call("hb_allreduce_bucket", comm, L.ptr(t), t.numel(), 0 if t.dtype == torch.float32 else 1, L.stream_ptr())
+                else:
+                    torch.distributed.all_reduce(t)
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(40):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(device)
+            us = torch.tensor([1e3 * e0.elapsed_time(e1) / 40], device=device)
+            torch.distributed.all_reduce(us, op=torch.distributed.ReduceOp.MAX)
+            res[f"{name}_{transport}_us"] = round(float(us.item()), 2)
+    p2p = res["grad_100KB_p2p_us"] + res["moments_24B_p2p_us"]
+    nccl = res["grad_100KB_nccl_us"] + res["moments_24B_nccl_us"]
+    res["chosen"] = "p2p" if p2p <= 1.05 * nccl else "nccl"
+    stats["calibration"] = res
+    _p2p_off = res["chosen"] == "nccl"
 
 
 def all_reduce_sum_(t):
@@ -77,7 +116,7 @@ def all_reduce_sum_(t):
     if (t.is_cuda and not _p2p_off and t.dtype in (torch.float32, torch.float64) and t.is_contiguous()
             and 0 < t.numel() * t.element_size() <= P2P_SLOT_BYTES):
         comm = _comm_for_current_stream(t.device)
-        if comm is not None:
+        if comm is not None and not _p2p_off:
             from . import _lib as L
 
             L.call("hb_allreduce_bucket", comm, L.ptr(t), t.numel(), 0 if t.dtype == torch.float32 else 1, L.stream_ptr())

@@ -14,6 +14,7 @@ import torch
 import torch.distributed as td
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("HB_P2P_ALLREDUCE", "1")   # this script tests the one-shot kernel itself, whatever the calibration would pick
 
 
 def main():
