@@ -1197,10 +1197,11 @@ __global__ void __launch_bounds__(256) fused_pack_kernel(PackJobs jobs) {
 // ------------------------------------------------------------------------------------------------ slot reduction
 struct Regions { int n; int off[8]; int len[8]; float scale[8]; };
 // grad[i] = scale_i * norm * sum over the CTA slots.  A CTA owns 32 consecutive parameters; warp g sums slot group g (every load
-// of a warp is one coalesced 128-byte line, all <= 24 loads of a thread in flight at once), the groups are added in order by
-// warp 0: deterministic, and one memory round trip instead of slots / 16.
-constexpr int SR_GROUPS = 8, SR_MAXPER = 24;
-__global__ void __launch_bounds__(32 * SR_GROUPS) fused_slot_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int slots,
+// of a warp is one coalesced 128-byte line, 16 loads of a thread in flight at once), the groups are added in order by
+// warp 0: deterministic, two memory round trips instead of slots / 16.  <= 42 registers x 256 threads so that the CTA fits
+// on an SM next to a CTA of the other stream's persistent update kernel.
+constexpr int SR_GROUPS = 8, SR_MAXPER = 16;
+__global__ void __launch_bounds__(32 * SR_GROUPS, 6) fused_slot_reduce_kernel(float* __restrict__ grad, const float* __restrict__ part, int slots,
                                                                            long long stride, int total, const __grid_constant__ Regions R,
                                                                            const double* __restrict__ norm3, double host_scale) {
   __shared__ float sm[SR_GROUPS][32];

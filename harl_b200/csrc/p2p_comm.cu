@@ -25,8 +25,12 @@
 namespace hb {
 
 constexpr int COMM_MAX_WORLD = 16;
-constexpr int COMM_GRID = 16;        // CTAs for a gradient-sized bucket (small buckets use fewer)
-constexpr int COMM_THREADS = 512;
+// Small CTAs on purpose: an exchange kernel spins while it waits for its peers, and the OTHER stream's persistent update
+// kernel (148 CTAs x 320 threads x 168 registers, 222 KB of shared memory) must still find room on every SM -- a 128-thread,
+// <= 64-register CTA co-resides with it; a 512-thread one did not, and a persistent kernel that starts 16 CTAs late runs
+// up to twice as long (measured: +2.5 ms per iteration at 2 GPUs with the critic update on a side stream).
+constexpr int COMM_GRID = 32;        // CTAs for a gradient-sized bucket (small buckets use fewer)
+constexpr int COMM_THREADS = 128;
 constexpr size_t COMM_HEADER = 4096;  // flags[COMM_MAX_WORLD] (u32), arrival counter (u64), error word
 
 struct Comm {
@@ -101,29 +105,33 @@ __global__ void __launch_bounds__(COMM_THREADS) allreduce_oneshot_kernel(const _
   }
   __syncthreads();
   if (!s_ok) return;                     // the host sees *err; the bucket is left unreduced
-  // all `world` peer loads of an element are issued before the first add: one NVLink round trip, not `world` of them
+  // the peer loads of an element are issued four at a time before the adds (one NVLink round trip per four ranks, rank order kept)
   for (int64_t i = tid; i < nv; i += stride) {
-    V x[8];
+    V acc;
+    for (int r0 = 0; r0 < world; r0 += 4) {
+      V x[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < world) x[r] = ld_peer(reinterpret_cast<const V*>(peers.p[r] + slot_off) + i);
-    V acc = x[0];
+      for (int q = 0; q < 4; ++q)
+        if (r0 + q < world) x[q] = ld_peer(reinterpret_cast<const V*>(peers.p[r0 + q] + slot_off) + i);
+      if (r0 == 0) acc = x[0]; else acc_add(acc, x[0]);
 #pragma unroll
-    for (int r = 1; r < 8; ++r)
-      if (r < world) acc_add(acc, x[r]);
-    for (int r = 8; r < world; ++r) acc_add(acc, ld_peer(reinterpret_cast<const V*>(peers.p[r] + slot_off) + i));
+      for (int q = 1; q < 4; ++q)
+        if (r0 + q < world) acc_add(acc, x[q]);
+    }
     reinterpret_cast<V*>(buf)[i] = acc;
   }
   for (int64_t i = nv * VN + tid; i < n; i += stride) {
-    T x[8];
+    T acc = (T)0;
+    for (int r0 = 0; r0 < world; r0 += 4) {
+      T x[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < world) x[r] = __ldcv(reinterpret_cast<const T*>(peers.p[r] + slot_off) + i);
-    T acc = x[0];
+      for (int q = 0; q < 4; ++q)
+        if (r0 + q < world) x[q] = __ldcv(reinterpret_cast<const T*>(peers.p[r0 + q] + slot_off) + i);
+      if (r0 == 0) acc = x[0]; else acc += x[0];
 #pragma unroll
-    for (int r = 1; r < 8; ++r)
-      if (r < world) acc += x[r];
-    for (int r = 8; r < world; ++r) acc += __ldcv(reinterpret_cast<const T*>(peers.p[r] + slot_off) + i);
+      for (int q = 1; q < 4; ++q)
+        if (r0 + q < world) acc += x[q];
+    }
     buf[i] = acc;
   }
 }
@@ -187,7 +195,7 @@ int hb_allreduce_bucket(void* comm, void* buf, int64_t n, int32_t dtype, void* s
   const uint32_t seq = ++c->seq;
   static const long long budget = (long long)(getenv("HB_COMM_TIMEOUT_S") ? atof(getenv("HB_COMM_TIMEOUT_S")) : 20.0) * 1900000000ll;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t per_cta = (int64_t)COMM_THREADS * (16 / (dtype == 0 ? 4 : 8));   // one 16-byte vector per thread
+  const int64_t per_cta = (int64_t)COMM_THREADS * 2 * (16 / (dtype == 0 ? 4 : 8));   // two 16-byte vectors per thread
   int grid = (int)((n + per_cta - 1) / per_cta);
   grid = grid < 1 ? 1 : (grid > COMM_GRID ? COMM_GRID : grid);
 #define HB_AR(T, V, VN) allreduce_oneshot_kernel<T, V, VN><<<grid, COMM_THREADS, 0, st>>>(peers, (T*)buf, n, c->rank, c->world, seq, \
