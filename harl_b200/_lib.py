@@ -98,18 +98,23 @@ class CopySeg(C.Structure):
     _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("bytes", C.c_int64)]
 
 
-def copy_segments(dsts, srcs):
-    """dst[i].copy_(src[i]) for all i in ONE launch (hb_copy_segments); the tensors must be contiguous, equal-sized,
-    4-byte typed and start on 16-byte boundaries -- returns False (nothing done) otherwise, for the caller's fallback."""
+def copy_segments(dsts, srcs, src_pinned=False, dst_pinned=False):
+    """dst[i].copy_(src[i]) for all i in ONE launch (hb_copy_segments).  Either side may be on the device or in PINNED host
+    memory (device-accessible under unified addressing: the kernel then reads / writes it over PCIe), not both on the host.  Tensors must
+    be contiguous, equal-sized and -typed, hold whole 4-byte words and start on 16-byte boundaries -- returns False (nothing
+    done) otherwise, for the caller's fallback.  ``src_pinned``: the caller vouches that host sources are pinned (skips one
+    cudaPointerGetAttributes per tensor)."""
     n = len(dsts)
     if n == 0 or n > 16:
         return False
     segs = (CopySeg * n)()
     for i, (d, s) in enumerate(zip(dsts, srcs)):
-        if not (d.is_cuda and s.is_cuda and d.is_contiguous() and s.is_contiguous() and d.dtype == s.dtype and d.element_size() == 4
-                and d.numel() == s.numel() and d.data_ptr() % 16 == 0 and s.data_ptr() % 16 == 0):
+        nbytes = d.numel() * d.element_size()
+        if not ((d.is_cuda or dst_pinned or d.is_pinned()) and (s.is_cuda or src_pinned or s.is_pinned()) and (d.is_cuda or s.is_cuda)
+                and d.is_contiguous() and s.is_contiguous() and d.dtype == s.dtype
+                and d.numel() == s.numel() and nbytes % 4 == 0 and d.data_ptr() % 16 == 0 and s.data_ptr() % 16 == 0):
             return False
-        segs[i].dst, segs[i].src, segs[i].bytes = d.data_ptr(), s.data_ptr(), d.numel() * 4
+        segs[i].dst, segs[i].src, segs[i].bytes = d.data_ptr(), s.data_ptr(), nbytes
     call("hb_copy_segments", segs, n, stream_ptr())
     return True
 

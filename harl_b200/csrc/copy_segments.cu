@@ -5,7 +5,9 @@
 // own rollout-buffer slot (the reference copies them one by one in OnPolicyBaseRunner.insert,
 // harl/runners/on_policy_base_runner.py:340-415).  Separate copy kernels are launch-bound (2-3 us each for < 1 MB)
 // and torch's multi-tensor apply spends 18 us on these ~4 MB; here every CTA walks the concatenation of all segments
-// in 16-byte vectors.
+// in 16-byte vectors.  Either side of a segment may be pinned host memory (unified addressing): a host-resident env's step
+// outputs then cross PCIe inside this one kernel instead of through three DMA set-ups and a device-side scatter, and the
+// sampled actions go back the same way.
 #include "common.cuh"
 
 namespace hb {
@@ -25,13 +27,13 @@ __global__ void __launch_bounds__(256) copy_segments_kernel(const __grid_constan
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
     while (i >= S.end_v[seg]) ++seg;
     const long long off = i - (seg ? S.end_v[seg - 1] : 0);
-    reinterpret_cast<uint4*>(S.dst[seg])[off] = __ldg(reinterpret_cast<const uint4*>(S.src[seg]) + off);
+    reinterpret_cast<uint4*>(S.dst[seg])[off] = __ldcv(reinterpret_cast<const uint4*>(S.src[seg]) + off);   // .cv: a source may be host memory the CPU rewrites every step
   }
   if (blockIdx.x == 0) {
     for (int s = 0; s < S.n; ++s) {
       const long long nv = S.end_v[s] - (s ? S.end_v[s - 1] : 0);
       if (threadIdx.x < S.tail_w[s])
-        reinterpret_cast<uint32_t*>(S.dst[s])[nv * 4 + threadIdx.x] = reinterpret_cast<const uint32_t*>(S.src[s])[nv * 4 + threadIdx.x];
+        reinterpret_cast<uint32_t*>(S.dst[s])[nv * 4 + threadIdx.x] = __ldcv(reinterpret_cast<const uint32_t*>(S.src[s]) + nv * 4 + threadIdx.x);
     }
   }
 }

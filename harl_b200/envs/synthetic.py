@@ -13,13 +13,14 @@ import torch
 from .spaces import Box, Discrete
 
 
-def _copy_segments(dsts, srcs):
-    """All step outputs into their buffer slots in one launch (hb_copy_segments); False -> the caller copies itself."""
-    if not dsts[0].is_cuda:
+def _copy_segments(dsts, srcs, src_pinned=False, dst_pinned=False):
+    """All step outputs into their buffer slots in one launch (hb_copy_segments; sources on the device or in pinned host
+    memory); False -> the caller copies itself."""
+    if not (dsts[0].is_cuda or srcs[0].is_cuda):
         return False
     from .. import _lib as L
 
-    return L.copy_segments(dsts, srcs)
+    return L.copy_segments(dsts, srcs, src_pinned, dst_pinned)
 
 # shapes of the BASELINE.json configs (SURVEY.md section 8(d))
 PRESETS = {
@@ -240,9 +241,12 @@ class SyntheticBatchedEnv:
         A = self.n_agents
         if self._act_host is None:
             self._act_host = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in dst["actions"]]
-        for a in range(A):
-            self._act_host[a].copy_(dst["actions"][a], non_blocking=True)
-            self.d2h_bytes += self._act_host[a].numel() * 4
+        # all agents' actions in one launch (the kernel writes the pinned block over PCIe) instead of A D2H DMA set-ups
+        if not (getattr(self, "_act_zero_copy_ok", True) and _copy_segments(self._act_host, list(dst["actions"]), dst_pinned=True)):
+            self._act_zero_copy_ok = False
+            for a in range(A):
+                self._act_host[a].copy_(dst["actions"][a], non_blocking=True)
+        self.d2h_bytes += sum(x.numel() * 4 for x in self._act_host)
         torch.cuda.current_stream().synchronize()  # also: last step's H2D copies have drained the staging buffers
         self.last_actions = self._act_host
         self._t += 1
@@ -317,16 +321,31 @@ class SyntheticBatchedEnv:
             dev = dst["share_obs"].device
             self._pack, self._pack_d = pack, torch.empty(P, device=dev)
             d = self._pack_d
-            self._pack_views = ([d[a * N * od:(a + 1) * N * od].view(N, od) for a in range(A)], d[o0:o1].view(self._state[0].shape),
-                                d[o1:o2].view(N, 1), [d[o2 + a * N * ad:o2 + (a + 1) * N * ad].view(N, ad) for a in range(A)] if ad else None)
-        self._pack_d.copy_(self._pack[k], non_blocking=True)
-        self.h2d_bytes += self._pack_d.numel() * 4
+            views = lambda d: ([d[a * N * od:(a + 1) * N * od].view(N, od) for a in range(A)], d[o0:o1].view(self._state[0].shape),
+                               d[o1:o2].view(N, 1), [d[o2 + a * N * ad:o2 + (a + 1) * N * ad].view(N, ad) for a in range(A)] if ad else None)
+            self._pack_views = views(self._pack_d)
+            self._pack_host_views = [views(pack[kk]) for kk in range(self.pool)]   # the same layout, in the pinned block
         self._ep_step_host += 1
         done = self._ep_step_host >= self.episode_limit
         if done:
             self._ep_step_host = 0
         self._dones_h.fill_(1 if done else 0)
         self._bad_h.fill_(1 if done else 0)
+        # Zero-copy path: ONE kernel (hb_copy_segments) reads the pinned host block over PCIe and writes every output --
+        # observations, state, rewards, availability masks, done and bad-transition flags -- straight into its buffer slot.
+        # (Pinned memory is device-accessible under unified addressing.)  One launch instead of three H2D DMA set-ups plus a
+        # device-side scatter; the bytes that cross PCIe are the same.
+        if self.state_type == "EP" and dst.get("rewards_na") is None and getattr(self, "_zero_copy_ok", True):
+            hv = self._pack_host_views[k]
+            dsts = list(dst["obs"]) + [dst["share_obs"], dst["rewards"]] + (list(dst["avail"]) if hv[3] is not None else []) + \
+                [dst["dones"], dst["bad"]]
+            srcs = list(hv[0]) + [hv[1], hv[2]] + (list(hv[3]) if hv[3] is not None else []) + [self._dones_h, self._bad_h]
+            if _copy_segments(dsts, srcs, src_pinned=True):
+                self.h2d_bytes += self._pack_d.numel() * 4 + 2 * self._dones_h.numel()
+                return
+            self._zero_copy_ok = False   # misaligned shapes: the staged path below
+        self._pack_d.copy_(self._pack[k], non_blocking=True)
+        self.h2d_bytes += self._pack_d.numel() * 4
         dst["dones"].copy_(self._dones_h, non_blocking=True)
         dst["bad"].copy_(self._bad_h, non_blocking=True)
         self.h2d_bytes += 2 * self._dones_h.numel()

@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${NGPU:-2}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+B="--steps 8 --warmup 3 --no-cpu-baseline --no-e2e"
+set -x
+timeout 300 $TR --master-port 29511 tests/dist_check_allreduce.py > gpurun_out/dist_check_allreduce_${N}gpu.log 2>&1; tail -2 gpurun_out/dist_check_allreduce_${N}gpu.log
+timeout 400 $TR --master-port 29514 bench.py --gpus $N $B > gpurun_out/bench_c2_r02_${N}gpu.json 2> gpurun_out/bench_c2_r02_${N}gpu.err
+HB_P2P_ALLREDUCE=0 timeout 400 $TR --master-port 29515 bench.py --gpus $N $B > gpurun_out/bench_c2_r02_${N}gpu_nccl.json 2> gpurun_out/bench_c2_r02_${N}gpu_nccl.err
+python - <<PY
+import json
+for f in ("bench_c2_r02_${N}gpu", "bench_c2_r02_${N}gpu_nccl"):
+    try:
+        d = json.loads(open("gpurun_out/" + f + ".json").read().strip().splitlines()[-1]); print(f, round(d["value"]), round(d["ms_per_step"], 2), d["scaling"], d["config"].get("phases_ms"), d["config"].get("exchanges"))
+    except Exception as e:
+        print(f, "FAILED", e); print(open("gpurun_out/" + f + ".err").read()[-600:])
+PY

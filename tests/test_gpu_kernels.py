@@ -480,6 +480,20 @@ def test_copy_segments_equals_elementwise_copies():
         assert torch.equal(d, s)
         full = d._base if d._base is not None else d
         assert (full[:4] == -7.0).all() and (full[-4:] == -7.0).all()
+    # sources in pinned host memory: the kernel reads them over PCIe (the host env's step outputs take this path)
+    hsrc = [torch.randn(n, generator=g).pin_memory() for n in (4096 * 18, 12, 4096)] + [torch.randint(0, 2, (4096, 3), dtype=torch.uint8).pin_memory()]
+    hdst = [torch.zeros(t.shape, dtype=t.dtype, device=_dev()) for t in hsrc]
+    assert L.copy_segments(hdst, hsrc)
+    torch.cuda.synchronize()
+    for d, s in zip(hdst, hsrc):
+        assert torch.equal(d.cpu(), s)
+    back = [torch.zeros(t.shape, dtype=t.dtype).pin_memory() for t in hsrc]             # device -> pinned host (the actions' way)
+    assert L.copy_segments(back, hdst)
+    torch.cuda.synchronize()
+    for b, s in zip(back, hsrc):
+        assert torch.equal(b, s)
+    assert not L.copy_segments([torch.zeros(8, device=_dev())], [torch.zeros(8)])   # pageable host memory: declined
+    assert not L.copy_segments([torch.zeros(8).pin_memory()], [torch.zeros(8).pin_memory()])   # host -> host: not this kernel's job
     ints = [torch.arange(100, dtype=torch.int32, device=_dev())]
     outs = [torch.zeros(100, dtype=torch.int32, device=_dev())]
     assert L.copy_segments(outs, ints) and torch.equal(outs[0], ints[0])
