@@ -532,7 +532,9 @@ def main():
         line = dict(base, impl="reference", value=res["value"], ms_per_step=1e3 * res["seconds_per_step"],
                     cpu_baseline=res, gpu_launches=0,
                     e2e={"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-        line["reference"] = {"kind": res["kind"], "n_rollout_threads": n_ref, "same_config": n_ref == wl["n"],
+        n_glob = wl["n"] * (1 if a.scaling == "strong" else world)
+        line["reference"] = {"kind": res["kind"], "n_rollout_threads": n_ref, "same_config": n_ref == n_glob,
+                             "global_n_rollout_threads_of_our_arm": n_glob,
                              "timed_iterations": res.get("timed_iterations"), "cuda": bool(a.ref_cuda),
                              "note": "unmodified PKU-MARL/HARL OnPolicy*Runner.run() from baseline/_ref (two shims: tensorboardX "
                                      "stub, synthetic batched env), see baseline/ref_runner.py"}

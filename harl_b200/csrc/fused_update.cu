@@ -134,10 +134,14 @@ struct RowPair {
 // Linear -> act -> LayerNorm epilogue of the columns [cb, cb + H/2) of one row.  ONE pass over TMEM: a = act(z) goes to
 // the image as fp16 hi / lo (22 bits); the two statistics passes and the normalisation then run over the thread's own image
 // row in shared memory (cheap) instead of over TMEM, and xhat * XS overwrites a in place.
-template <int ACT>
+// `mid()` is called once the first half of this thread's columns holds the final xhat (both threads of a row reach it together:
+// columns [0, H/4) and [H/2, 3H/4)), so that the MMA issuer can start the k-chunks of the next GEMM that read them while
+// the other half is still being normalised.
+struct NoMid { __device__ __forceinline__ void operator()() const {} };
+template <int ACT, typename Mid = NoMid>
 __device__ __forceinline__ void fwd_epilogue(int act_rt, uint32_t tacc, int H, const float* __restrict__ sbias, float descale,
                                              unsigned char* img, uint32_t img_bytes, int wch, const RowPair& P, float& mu, float& rstd,
-                                             uint32_t (&mask)[2]) {
+                                             uint32_t (&mask)[2], Mid mid = Mid()) {
   const int r = P.r, nc = H >> 1, cb = P.half * nc;
   const float inv_n = 1.f / (float)H;
   uint32_t va[16], vb[16];
@@ -193,16 +197,20 @@ __device__ __forceinline__ void fwd_epilogue(int act_rt, uint32_t tacc, int H, c
     um::split8(x, hi, lo);
     *reinterpret_cast<uint4*>(img + off) = hi;
     *reinterpret_cast<uint4*>(img + img_bytes + off) = lo;
+    if (c8 == (nc >> 4) - 1) mid();
   }
 }
 
 // LayerNorm + activation backward of this thread's columns of one row: G = accumulator (= g / descale, g = dL/dxhat), x = XS * xhat
 // from the image; writes DZS * dZ over xhat.  With s1 = sum G, s2 = sum G x:
 //   dZ = rstd (g - mean(g) - xhat mean(g xhat)) act'   =   [rstd descale] (G - s1 / H - x s2 / (H XS^2)) act'
-template <int ACT>
+// `pre()` runs between the read-only statistics pass and the in-place write-back: the caller waits there for the MMAs that
+// still READ this image (the weight-gradient GEMMs of the layer above, committed separately from the dX GEMM whose result
+// this epilogue consumes), so those MMAs overlap the statistics pass instead of delaying the whole epilogue.
+template <int ACT, typename Pre>
 __device__ __forceinline__ void bwd_epilogue(int act_rt, uint32_t tacc, int H, float descale, unsigned char* img,
                                              uint32_t img_bytes, int wch, const RowPair& P, float mu, float rstd,
-                                             const uint32_t (&mask)[2], bool row_ok) {
+                                             const uint32_t (&mask)[2], bool row_ok, Pre pre) {
   const int r = P.r, nc = H >> 1, cb = P.half * nc;
   const float inv_n = 1.f / (float)H;
   // two passes over TMEM (sums, then the write-back): keeping the 64 accumulator values of a thread in registers across the
@@ -236,6 +244,7 @@ __device__ __forceinline__ void bwd_epilogue(int act_rt, uint32_t tacc, int H, f
   const float m1 = P.total(0, p1) * inv_n, m2 = P.total(1, p2) * inv_n * (1.f / (XS * XS));
   const float stdx = 1.f / (rstd * XS);
   const float k = row_ok ? rstd * descale * DZS : 0.f;
+  pre();
   for (int cc = 0; cc * 16 < nc; ++cc) {
     uint32_t v[16];
     um::tmem_ld16_issue(tacc + cb + cc * 16, v);
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   float* sacc = reinterpret_cast<float*>(p); p += 2 * NH * 4;       // end-of-kernel sums: head bias grads, log_std grads
   double* sred = reinterpret_cast<double*>(p); p += 4 * 4 * 8;
   float* xch = reinterpret_cast<float*>(p); p += 2 * TILE * 2 * 4;  // row-pair exchange of partial sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p); p += 10 * 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p); p += 12 * 8;
   unsigned long long* sclk = reinterpret_cast<unsigned long long*>(p); p += 16 * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p);
   uint64_t* w_full = bars;                // [STAGES] weight chunk landed
@@ -321,6 +330,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   uint64_t* m2e = e2m + 1;            // MMA warp -> epilogue warps (tcgen05.commit)
   uint64_t* obs_free = e2m + 2;       // MMA warp -> producer: the staging image of the next tile's observations is dead
   uint64_t* obs_full = e2m + 3;       // producer's bulk copy -> epilogue warps
+  uint64_t* e2m_h = e2m + 4;          // epilogue warps -> MMA warp: the first column half of a forward epilogue is final
+  uint64_t* m2e_b = e2m + 5;          // MMA warp -> epilogue warps: the weight-gradient MMAs that read an image have retired
   unsigned char* OBS = MODE == M_GRAD ? X2 : X1;   // staging buffer = an activation image that is idle at that point
   const uint32_t obs_bytes = (uint32_t)TILE * (uint32_t)a.in_dim * 4u;
   // per-row inputs of the head phase ride along in the same staging image, behind the observation block (byte offsets; 0 = absent)
@@ -372,6 +383,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { um::mbar_init(&w_full[i], 1); um::mbar_init(&w_empty[i], 1); }
     um::mbar_init(e2m, 8);             // one arrival per epilogue warp
+    um::mbar_init(e2m_h, 8);
+    um::mbar_init(m2e_b, 1);
     um::mbar_init(m2e, 1);
     um::mbar_init(obs_free, 1);
     um::mbar_init(obs_full, 1);
@@ -412,7 +425,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
           const int layer = pass == 0 ? 0 : 1;
           const int nch = layer == 0 ? a.nch0 : nch1, kp = layer == 0 ? K0p : H;
           const unsigned char* src = reinterpret_cast<const unsigned char*>(pass == 0 ? a.img0 : (pass == 1 ? a.img1 : a.img1b));
-          for (int c = 0; c < nch; ++c, ++it) {
+          for (int ci = 0; ci < nch; ++ci, ++it) {
+            // layer-1 forward at H = 128: the k-chunks of the two column quarters that are final first (0, 2) go first
+            const int c = (pass == 1 && nch == 4) ? ((ci & 1) * 2 + (ci >> 1)) : ci;
             const int kc = kp - 32 * c < 32 ? kp - 32 * c : 32;
             const uint32_t bytes = 2u * (uint32_t)H * (uint32_t)kc * 2u;
             const uint32_t st = it % STAGES, use = it / STAGES;
@@ -430,12 +445,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one lane)
     if (lane == 0) {
-      uint32_t it = 0, pe = 0;
+      uint32_t it = 0, pe = 0, peh = 0;
       bool first = true;
       const uint32_t X0a = um::smem_u32(X0), X1a = um::smem_u32(X1), X2a = um::smem_u32(X2), DLa = um::smem_u32(DL);
       const uint32_t ONa = um::smem_u32(ONES), WHa = um::smem_u32(WH), RGa = um::smem_u32(ring);
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         auto wait_e = [&]() { um::mbar_wait(e2m, pe); pe ^= 1; um::tc_fence_after(); };
+        auto wait_eh = [&]() { um::mbar_wait(e2m_h, peh); peh ^= 1; um::tc_fence_after(); };
         auto chunk = [&](int kc, auto&& body) {   // consume the next ring stage
           const uint32_t st = it % STAGES, use = it / STAGES;
           um::mbar_wait(&w_full[st], use & 1);
@@ -454,28 +470,52 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
           });
         }
         um::commit(m2e);
-        // -- layer 1: C_F = X1 W1'^T
-        wait_e();
-        for (int c = 0; c < nch1; ++c)
-          chunk(32, [&](uint32_t wb, uint32_t wimg) {
-            gemm3(tmem + C_F, op_kmajor(X1a, x_bytes, wchx, 4 * c), op_kmajor(wb, wimg, 4, 0), 2, um::idesc_f16(H, 0, 0), c > 0);
-          });
+        // -- layer 1: C_F = X1 W1'^T.  H = 128: the k-chunks of the column quarters [0, 32) and [64, 96) start as soon as the
+        // layer-0 epilogue has finalised them (e2m_h), the other two when it is done (the ring delivers them in that order)
+        wait_eh();
+        if (nch1 == 4) {
+          auto l1 = [&](int c, bool acc) {
+            chunk(32, [&](uint32_t wb, uint32_t wimg) {
+              gemm3(tmem + C_F, op_kmajor(X1a, x_bytes, wchx, 4 * c), op_kmajor(wb, wimg, 4, 0), 2, um::idesc_f16(H, 0, 0), acc);
+            });
+          };
+          l1(0, false); l1(2, true);
+          wait_e();
+          l1(1, true); l1(3, true);
+        } else {
+          wait_e();
+          for (int c = 0; c < nch1; ++c)
+            chunk(32, [&](uint32_t wb, uint32_t wimg) {
+              gemm3(tmem + C_F, op_kmajor(X1a, x_bytes, wchx, 4 * c), op_kmajor(wb, wimg, 4, 0), 2, um::idesc_f16(H, 0, 0), c > 0);
+            });
+        }
         um::commit(m2e);
         if (!GRAD) um::commit(obs_free);   // evaluate: X1 (the staging image) is dead after these MMAs
-        // -- head: C_H = X2 Wh'^T
-        wait_e();
-        gemm3(tmem + C_H, op_kmajor(X2a, x_bytes, wchx, 0), op_kmajor(WHa, wh_bytes, wchh, 0), H >> 4, um::idesc_f16(NH, 0, 0), false);
+        // -- head: C_H = X2 Wh'^T (same split over the column quarters of the layer-1 epilogue)
+        wait_eh();
+        if (H == 128) {
+          auto hd = [&](int q, bool acc) {
+            gemm3(tmem + C_H, op_kmajor(X2a, x_bytes, wchx, 4 * q), op_kmajor(WHa, wh_bytes, wchh, 4 * q), 2, um::idesc_f16(NH, 0, 0), acc);
+          };
+          hd(0, false); hd(2, true);
+          wait_e();
+          hd(1, true); hd(3, true);
+        } else {
+          wait_e();
+          gemm3(tmem + C_H, op_kmajor(X2a, x_bytes, wchx, 0), op_kmajor(WHa, wh_bytes, wchh, 0), H >> 4, um::idesc_f16(NH, 0, 0), false);
+        }
         um::commit(m2e);
         if (GRAD) {
           // -- head backward: C_F = DL Wh' (dL/dxhat_1);  C_WH += X2^T DL
           wait_e();
           gemm3(tmem + C_F, op_kmajor(DLa, dl_bytes, wchd, 0), op_mnmajor(WHa, wh_bytes, wchh, 0), 1, um::idesc_f16(H, 0, 1), false);
+          um::commit(m2e);                 // the layer-1 backward epilogue only needs C_F; the sums below still READ X2 and DL
           gemm3(tmem + C_WH, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(DLa, dl_bytes, wchd, 0), TILE >> 4,
                 um::idesc_f16(NH, 1, 1), !first);
           // column sums of DL over the rows: M = 128 reads past the 16 real columns (finite garbage in lanes >= 16, unused)
           gemm3(tmem + C_BH, op_mnmajor(DLa, dl_bytes, wchd, 0), op_mnmajor(ONa, dl_bytes, wchd, 0), TILE >> 4,
                 um::idesc_f16(NH, 1, 1), !first, false);
-          um::commit(m2e);
+          um::commit(m2e_b);               // ... the epilogue waits for this one before it overwrites X2
           // -- layer 1 backward: C_W1 += dZ1^T X1;  C_B1 += dZ1^T 1;  C_F = dZ1 W1' (dL/dxhat_0), one weight chunk at a time
           wait_e();
           // the chunks already sitting in the ring go first, so their stages are released (and refilled by the producer)
@@ -488,14 +528,17 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
                     um::idesc_f16(H, 0, 1), c > 0);
             });
           };
+          // the bias column sums (small) run while the last weight chunk streams in; the big weight-gradient GEMM goes AFTER the
+          // commit that releases the layer-0 backward epilogue (which needs only C_F) and is waited for separately (m2e_b)
           const int nres = nch1 < STAGES ? nch1 : STAGES;
           for (int c = 0; c < nres; ++c) dx_chunk(c);
-          gemm3(tmem + C_W1, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(X1a, x_bytes, wchx, 0), TILE >> 4,
-                um::idesc_f16(H, 1, 1), !first);
           gemm3(tmem + C_B1, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(ONa, dl_bytes, wchd, 0), TILE >> 4,
                 um::idesc_f16(NH, 1, 1), !first, false);
           for (int c = nres; c < nch1; ++c) dx_chunk(c);
           um::commit(m2e);
+          gemm3(tmem + C_W1, op_mnmajor(X2a, x_bytes, wchx, 0), op_mnmajor(X1a, x_bytes, wchx, 0), TILE >> 4,
+                um::idesc_f16(H, 1, 1), !first);
+          um::commit(m2e_b);
           um::commit(obs_free);            // X2 (the staging image) is dead after these MMAs
           // -- layer 0 backward: C_W0 += dZ0^T X0;  C_B0 += dZ0^T 1
           wait_e();
@@ -518,6 +561,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
     uint32_t pm = 0, po = 0;
     auto wait_m = [&]() { um::mbar_wait(m2e, pm); pm ^= 1; um::tc_fence_after(); };
     auto signal = [&]() { um::fence_async_smem(); um::tc_fence_before(); __syncwarp(); if (lane == 0) um::mbar_arrive(e2m); };
+    auto mid = [&]() { um::fence_async_smem(); um::tc_fence_before(); __syncwarp(); if (lane == 0) um::mbar_arrive(e2m_h); };
+    uint32_t pmb = 0;
+    auto wait_mb = [&]() { um::mbar_wait(m2e_b, pmb); pmb ^= 1; um::tc_fence_after(); };
     const int na = a.out;
     float s_loss = 0.f, s_ent = 0.f, s_ratio = 0.f, s_rows = 0.f;
     float vmean = 0.f, vstd = 1.f;
@@ -652,13 +698,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
       uint32_t mask0[2] = {0, 0}, mask1[2] = {0, 0};
       wait_m();
       pc.lap(3);                                   // wait: layer-0 MMAs
-      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb0, 1.f / (XS * ws0), X1, x_bytes, wchx, RP, mu0, rstd0, mask0);
+      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb0, 1.f / (XS * ws0), X1, x_bytes, wchx, RP, mu0, rstd0, mask0, mid);
       signal();
       pc.lap(4);                                   // layer-0 epilogue
       // ---- layer 1
       wait_m();
       pc.lap(5);                                   // wait: layer-1 MMAs
-      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb1, 1.f / (XS * ws1), X2, x_bytes, wchx, RP, mu1, rstd1, mask1);
+      fwd_epilogue<ACT>(a.act, tl + C_F, H, sb1, 1.f / (XS * ws1), X2, x_bytes, wchx, RP, mu1, rstd1, mask1, mid);
       signal();
       pc.lap(6);                                   // layer-1 epilogue
       // ---- head
@@ -812,13 +858,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_update_kernel(const __grid_c
       // ---- layer 1 backward (dL/dxhat_1 in C_F), dZ_1 over xhat_1 in X2
       wait_m();
       pc.lap(9);                                   // wait: head backward MMAs
-      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * wsh), X2, x_bytes, wchx, RP, mu1, rstd1, mask1, ok);
+      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * wsh), X2, x_bytes, wchx, RP, mu1, rstd1, mask1, ok, wait_mb);
       signal();
       pc.lap(10);                                  // layer-1 backward epilogue
       // ---- layer 0 backward (dL/dxhat_0 in C_F), dZ_0 over xhat_0 in X1
       wait_m();
       pc.lap(11);                                  // wait: layer-1 backward MMAs (dW1, db1, dX through 4 weight chunks)
-      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * ws1), X1, x_bytes, wchx, RP, mu0, rstd0, mask0, ok);
+      bwd_epilogue<ACT>(a.act, tl + C_F, H, 1.f / (DZS * ws1), X1, x_bytes, wchx, RP, mu0, rstd0, mask0, ok, wait_mb);
       signal();
       pc.lap(12);                                  // layer-0 backward epilogue
       pending = true;
