@@ -35,7 +35,12 @@ class HAPPO(OnPolicyBase):
 
     def _step(self, batch, norm3, scalars_row, logp_out=None):
         """One update on a device batch: grad -> (allreduce) -> clip + Adam. Returns nothing (async)."""
+        hooks = getattr(self, "grad_hooks", None)   # (before, after) the big kernel: the runner's stream choreography
+        if hooks is not None:
+            hooks[0]()
         self.actor.actor_grad(batch, self._hyper(), norm3, scalars_row, logp_out)
+        if hooks is not None:
+            hooks[1]()
         dist.all_reduce_sum_(self.actor.grad)
         self.actor.adam_step(self.cur_lr, self.opti_eps, self.weight_decay, self.max_grad_norm, self.use_max_grad_norm)
 

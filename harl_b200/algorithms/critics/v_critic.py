@@ -88,6 +88,8 @@ class VCritic:
         cb = DeviceNet.critic_batch(share_obs, value_preds, returns, index, rows, rnn_states, masks, seq_len)
         vn = value_normalizer.state if value_normalizer is not None else None
         self.critic.value_grad(cb, self._hyper(), vn, 1.0 / global_rows, scalars_row)
+        if getattr(self, "after_grad_hook", None) is not None:   # the runner's stream choreography (on_policy_ha_runner.py)
+            self.after_grad_hook()
         dist.all_reduce_sum_(self.critic.grad)
         self.critic.adam_step(self.cur_lr, self.opti_eps, self.weight_decay, self.max_grad_norm, self.use_max_grad_norm)
 
@@ -111,10 +113,10 @@ class VCritic:
         s = scal.cpu().numpy()
         return s[0] / s[1], self.critic.grad_norm.item()
 
-    def train(self, critic_buffer, value_normalizer=None, defer=False):
-        """Reference v_critic.py:159-200.  ``defer=True`` enqueues the whole update without a host read and returns
-        a closure producing the train-info (the HA runner runs the critic update on a side stream, overlapped with
-        the sequential actor updates, and reads the scalars after joining the streams)."""
+    def train_steps(self, critic_buffer, value_normalizer=None):
+        """Generator form of ``train``: every ``next()`` enqueues ONE update (one minibatch of one epoch) on the current
+        stream; after exhaustion ``self.finish_train()`` returns the train-info.  Lets the runner interleave the critic's
+        updates with the sequential actor updates in an order that is the same on every rank."""
         d = self.device
         buf = critic_buffer
         T = buf.episode_length
@@ -137,13 +139,22 @@ class VCritic:
                 self._step(so, vp, rt, idx, n, float(n * dist.world_size()), value_normalizer, scal[u], rnn, masks, seq_len, whole)
                 gnorm[u] = self.critic.grad_norm[0]
                 u += 1
+                yield u
         dist.all_reduce_sum_(scal)
 
         def finish():
             s = scal.cpu().numpy()
             return dict(value_loss=float((s[:, 0] / s[:, 1]).mean()), critic_grad_norm=float(gnorm.mean().item()))
 
-        return finish if defer else finish()
+        self.finish_train = finish
+
+    def train(self, critic_buffer, value_normalizer=None, defer=False):
+        """Reference v_critic.py:159-200.  ``defer=True`` enqueues the whole update without a host read and returns
+        a closure producing the train-info (the HA runner runs the critic update on a side stream, overlapped with
+        the sequential actor updates, and reads the scalars after joining the streams)."""
+        for _ in self.train_steps(critic_buffer, value_normalizer):
+            pass
+        return self.finish_train if defer else self.finish_train()
 
     def prep_training(self):
         pass

@@ -39,6 +39,8 @@ class OnPolicyBaseRunner:
         self.state_type = env_args.get("state_type", "EP")
         self.share_param = algo_args["algo"]["share_param"]
         self.fixed_order = algo_args["algo"]["fixed_order"]
+        if os.environ.get("HB_OVERLAP_CRITIC") is not None:   # the critic update on a side stream (default on); 0 = one stream
+            self.overlap_critic_update = os.environ["HB_OVERLAP_CRITIC"] != "0"
         set_seed(algo_args["seed"])
         self.device = init_device(algo_args["device"])
         if dist.world_size() > 1:
