@@ -195,3 +195,26 @@ def test_ma_train_iteration(name):
     for k, v in pc.items():
         np.testing.assert_allclose(v.detach().numpy(), g["out.critic/" + k], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose([vn.running_mean, vn.running_mean_sq, vn.debiasing_term], g["out.vn"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["ha_train_mlp_disc_EP", "ha_train_mlp_box_EP"])
+def test_pre_update_logp_sweep_equals_the_first_epochs_forward(name):
+    """The identity the device path relies on (hb_ppo_actor_grad_logp, on_policy_ha_runner.py in harl_b200): the
+    reference's pre-update evaluate sweep over the whole buffer (on_policy_ha_runner.py:66-83) and the forward of the FIRST
+    PPO epoch (happo.py:41-49 on the single whole-buffer minibatch) run the same network with the same weights on the
+    same rows -- a row's log-prob does not depend on the order of the rows, so the sweep's numbers are the epoch's, up to
+    the permutation.  Shown on the reference's own goldens with the oracle."""
+    g = U.load(name)
+    cfg, m = U.cfg_of(g), U.meta_of(g)
+    assert cfg["actor_num_mini_batch"] == 1
+    p = U.params_of(g, "actor0/", grad=True)
+    buf = _buf(g, "a0.")
+    T, N = buf["actions"].shape[:2]
+    sweep = oa.logp_sweep(p, cfg, m["head"], buf)                       # [T*N, ad], time-major rows
+    perm = np.random.default_rng(0).permutation(T * N)                  # what the feed-forward generator draws
+    adv = np.zeros((T, N, 1), np.float32)
+    batch = next(oa.actor_minibatches(buf, adv, np.ones((T, N, 1), np.float32), cfg, lambda n: perm))
+    with torch.no_grad():
+        lp, _, _, _ = on.actor_evaluate(p, cfg, m["head"], batch["obs"], batch["rnn"], batch["actions"], batch["masks"],
+                                        batch.get("avail"), batch["active"])
+    np.testing.assert_allclose(lp.numpy(), sweep.numpy()[perm], rtol=0, atol=2e-6)
