@@ -11,11 +11,14 @@ keeps the workload's n_rollout_threads, so N_global = N * n_rollout_threads.
 
 Rank 0 prints ONE JSON line.  Extra objects (see DESIGN.md "Measurement"):
   roofline      dominant kernel of the step, timed live with CUDA events on the launching stream
-  cpu_baseline  the CPU oracle port of the reference, timed on this box's host cores (N=1 only)
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, driven by baseline/ref_runner.py) on this box's host cores, on a
+                256-thread sample of the workload (N=1 only)
   e2e           same metric with the env on the HOST: pinned H2D of every env output and D2H of the
                 actions each rollout step, plus the D2H of the train infos, inside the timed region
---impl reference times the oracle CPU port (the reference is pure Python/PyTorch; it is not
-installable on the GPU box) on a bounded sample of the same workload.
+--impl reference times the unmodified reference's own OnPolicyHARunner.run() (baseline/_ref travels with the snapshot) at
+the bench configuration itself, >= 3 timed iterations within --ref-budget-s; --ref-cuda sets its device.cuda = True;
+--ref-cross-check adds the oracle CPU port (oracle/runner.py) as a cross-check.  --scaling strong splits the workload's
+n_rollout_threads over the ranks instead of giving each rank all of them.
 """
 import argparse
 import ctypes as C
