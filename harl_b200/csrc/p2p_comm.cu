@@ -12,12 +12,12 @@
 //      every peer has mapped through CUDA IPC; the last CTA to finish (device counter) publishes `seq` into flag
 //      [rank] of EVERY peer's flag array with system-scope release stores, one thread per peer (in parallel);
 //   2. every CTA spins (system-scope acquire loads, bounded by a clock64 budget) until its own flag array shows
-//      `seq` for all ranks, then reads all `world` slots straight out of peer memory (all loads of an element in flight
-//      together: one NVLink round trip) and adds them IN RANK ORDER --
+//      `seq` for all ranks, then reads all `world` slots straight out of peer memory (the loads of an element go out four
+//      ranks at a time: one NVLink round trip per four ranks) and adds them IN RANK ORDER --
 //      every rank computes the bit-identical sum, so the replicas never drift;
 //   3. no trailing barrier: slots are double-buffered by `seq & 1`, and a rank can only overwrite slot parity p again
 //      at seq + 2, which it reaches only after every peer has published seq + 1, i.e. finished reading seq.
-// Cost: one launch, one NVLink round trip (~2 us) + world x bucket bytes of peer reads per GPU.
+// Cost: one launch, a flag round trip plus world / 4 data round trips over NVLink, world x bucket bytes of peer reads per GPU.
 #include <stdlib.h>
 
 #include "common.cuh"
